@@ -1,0 +1,38 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and TMA tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/crab_b200.h"
+
+namespace crab {
+
+// Thread-local last error string, returned by crab_last_error().
+char* last_error_buf();
+int set_error(int code, const char* fmt, ...);
+
+#define CRAB_CHECK_CUDA(expr)                                                                              \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess)                                                                                 \
+      return crab::set_error(CRAB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                             __LINE__);                                                                    \
+  } while (0)
+
+#define CRAB_REQUIRE(cond, ...)                                         \
+  do {                                                                  \
+    if (!(cond)) return crab::set_error(CRAB_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// Encode a 2-D bf16 row-major tensor [rows, cols] (row stride ld elements) with a [box_rows, 64]-element box and
+// 128-byte swizzle. Returns 0 or a negative error code.
+int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                        uint32_t box_rows, uint32_t box_cols);
+
+int sm_count();
+
+}  // namespace crab

@@ -1,0 +1,61 @@
+"""ctypes binding of `libcrab_b200.so` (the C ABI declared in include/crab_b200.h).
+
+There is no fallback: if the shared library is missing or a call returns an error code, a Python exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libcrab_b200.so"
+_lib = None
+
+
+class CrabError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("lda", C.c_int32), ("ldb", C.c_int32), ("ldc", C.c_int32), ("ldr", C.c_int32),
+        ("res_scale", C.c_float), ("out_scale", C.c_float),
+        ("act", C.c_int32), ("out_dtype", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
+    ]
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building is `python -m crab_b200.build` / `__graft_entry__.build()`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise CrabError(
+            f"{_LIB_PATH} is missing: build it with `python crab_b200/build.py` (nvcc, sm_100a). "
+            "crab_b200 has no CPU or PyTorch fallback path."
+        )
+    lib = C.CDLL(str(_LIB_PATH))
+    lib.crab_last_error.restype = C.c_char_p
+    lib.crab_last_error.argtypes = []
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().crab_last_error()
+        raise CrabError(f"{what} failed with code {rc}: {msg.decode(errors='replace') if msg else ''}")
+
+
+def exported_symbols() -> list[str]:
+    """Names declared in include/crab_b200.h (parsed from the header) — used by the CPU-side ABI test."""
+    import re
+
+    hdr = (Path(__file__).resolve().parent.parent / "include" / "crab_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(crab_[a-z0-9_]+)\s*\(", hdr)))
