@@ -1,0 +1,464 @@
+// Attention kernels.
+//
+//  flash_attn_kernel  — FlashAttention-style forward (online softmax, never materialises S): encoder self-attention
+//                       (CLIP N=257, BEATs N<=96 with gated relative-position bias, Q-Former 32x32), Q-Former
+//                       cross-attention (32 x {48,96,256}) and causal decoder prefill (hd=128, GQA-aware).
+//                       K/V tiles are staged in XOR-swizzled shared memory with a cp.async double buffer; QK^T and
+//                       PV run on mma.sync.m16n8k16 (bf16 in, fp32 accumulate); softmax statistics in fp32.
+//                       Attention is <= 4% of the path's FLOPs; the tcgen05 budget went to the GEMMs.
+//  attn_decode_kernel — single-query decode attention over the KV cache: pure HBM streaming (16-byte loads, one
+//                       key per half-warp), split over the context when batch*heads cannot fill 148 SMs, context
+//                       length read from device memory so the step can live in a CUDA graph.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace crab {
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct FlashParams {
+  const __nv_bfloat16* q; const __nv_bfloat16* k; const __nv_bfloat16* v; __nv_bfloat16* o;
+  long long q_bs, q_rs, q_hs;  // element strides: batch, row (sequence), head
+  long long k_bs, k_rs, k_hs;
+  long long v_bs, v_rs, v_hs;
+  long long o_bs, o_rs, o_hs;
+  int B, H, KVH, Sq, Sk;
+  float scale;
+  int causal;
+  const float* gate;   // [B, H, Sq] or null
+  const float* table;  // [H, Sq, Sk] or null   (bias = gate * table)
+};
+
+template <int HD>
+struct FlashCfg {
+  static constexpr int BM = 64, BN = 64, THREADS = 128;
+  static constexpr int CHUNKS = HD / 8;  // 16-byte chunks per row
+  static constexpr int TILE_BYTES = 64 * HD * 2;
+  static constexpr int SMEM = TILE_BYTES * 5;  // Q + 2 x (K, V)
+};
+
+// smem tile: row-major [64][HD] bf16, 16-byte chunk c of row r stored at chunk (c ^ (r & 7))
+template <int HD>
+__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int r, int c) {
+  return base + (uint32_t)(r * HD * 2) + (uint32_t)(((c ^ (r & 7))) << 4);
+}
+
+template <int HD>
+__device__ __forceinline__ void load_tile(uint32_t sbase, const __nv_bfloat16* g, long long rs, int row0, int nrows_valid) {
+  constexpr int CH = HD / 8;
+  for (int i = threadIdx.x; i < 64 * CH; i += 128) {
+    const int r = i / CH, c = i % CH;
+    const bool ok = (row0 + r) < nrows_valid;
+    const __nv_bfloat16* src = g + (long long)(ok ? (row0 + r) : 0) * rs + c * 8;
+    cp_async16(tile_addr<HD>(sbase, r, c), src, ok);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
+  using Cfg = FlashCfg<HD>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK0 = sQ + Cfg::TILE_BYTES;
+  const uint32_t sV0 = sK0 + 2 * Cfg::TILE_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (p.H / p.KVH);
+  const int q0 = m_blk * Cfg::BM;
+  const __nv_bfloat16* qg = p.q + b * p.q_bs + h * p.q_hs;
+  const __nv_bfloat16* kg = p.k + b * p.k_bs + kvh * p.k_hs;
+  const __nv_bfloat16* vg = p.v + b * p.v_bs + kvh * p.v_hs;
+  const int off = p.Sk - p.Sq;  // causal: key j visible to query i iff j <= i + off
+  int n_tiles = (p.Sk + Cfg::BN - 1) / Cfg::BN;
+  if (p.causal) {
+    const int last_key = min(p.Sk - 1, q0 + Cfg::BM - 1 + off);
+    n_tiles = min(n_tiles, last_key / Cfg::BN + 1);
+  }
+
+  load_tile<HD>(sQ, qg, p.q_rs, q0, p.Sq);
+  load_tile<HD>(sK0, kg, p.k_rs, 0, p.Sk);
+  load_tile<HD>(sV0, vg, p.v_rs, 0, p.Sk);
+  cp_async_commit();
+
+  constexpr int DT = HD / 8;  // output n8-tiles per row
+  float o_acc[DT][4];
+#pragma unroll
+  for (int i = 0; i < DT; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const float sl2 = p.scale * 1.4426950408889634f;
+  const int r_lo = q0 + warp * 16 + (lane >> 2);  // global query row of c0/c1; c2/c3 are r_lo + 8
+  float gate_lo = 0.f, gate_hi = 0.f;
+  if (p.gate) {
+    if (r_lo < p.Sq) gate_lo = p.gate[((size_t)b * p.H + h) * p.Sq + r_lo];
+    if (r_lo + 8 < p.Sq) gate_hi = p.gate[((size_t)b * p.H + h) * p.Sq + r_lo + 8];
+  }
+
+  for (int t = 0; t < n_tiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < n_tiles) {
+      load_tile<HD>(sK0 + (buf ^ 1) * Cfg::TILE_BYTES, kg, p.k_rs, (t + 1) * Cfg::BN, p.Sk);
+      load_tile<HD>(sV0 + (buf ^ 1) * Cfg::TILE_BYTES, vg, p.v_rs, (t + 1) * Cfg::BN, p.Sk);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint32_t sK = sK0 + buf * Cfg::TILE_BYTES, sV = sV0 + buf * Cfg::TILE_BYTES;
+
+    // ---- S = Q K^T  (16 x 64 per warp) ----
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      uint32_t a[4];
+      {
+        // A fragment (m16 x k16): matrices (rows 0-7,k0-7), (rows 8-15,k0-7), (rows 0-7,k8-15), (rows 8-15,k8-15)
+        const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = ks * 2 + (lane >> 4);
+        ldsm_x4(tile_addr<HD>(sQ, r, c), a[0], a[1], a[2], a[3]);
+      }
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b0, b1, b2, b3;
+        // matrices: (n0-7,k0-7), (n0-7,k8-15), (n8-15,k0-7), (n8-15,k8-15)
+        const int n = np * 16 + (lane & 7) + (lane >> 4) * 8;
+        const int c = ks * 2 + ((lane >> 3) & 1);
+        ldsm_x4(tile_addr<HD>(sK, n, c), b0, b1, b2, b3);
+        mma_bf16(s[np * 2], a, b0, b1);
+        mma_bf16(s[np * 2 + 1], a, b2, b3);
+      }
+    }
+
+    // ---- scale, bias, mask, online softmax (log2 domain) ----
+    const int k0 = t * Cfg::BN;
+    float mx[2] = {m_run[0], m_run[1]};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kj = k0 + nt * 8 + (lane & 3) * 2 + (e & 1);
+        const int hi = e >> 1;
+        const int qi = r_lo + hi * 8;
+        float v = s[nt][e] * sl2;
+        if (p.table != nullptr && qi < p.Sq && kj < p.Sk)
+          v += (hi ? gate_hi : gate_lo) * p.table[((size_t)h * p.Sq + qi) * p.Sk + kj] * 1.4426950408889634f;
+        const bool masked = (kj >= p.Sk) || (p.causal && kj > qi + off);
+        v = masked ? -INFINITY : v;
+        s[nt][e] = v;
+        mx[hi] = fmaxf(mx[hi], v);
+      }
+    }
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 1));
+      mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 2));
+    }
+    float corr[2], msafe[2];
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      msafe[hi] = (mx[hi] == -INFINITY) ? 0.f : mx[hi];
+      corr[hi] = exp2f(m_run[hi] - msafe[hi]);
+      m_run[hi] = mx[hi];
+      l_run[hi] *= corr[hi];
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = exp2f(s[nt][e] - msafe[e >> 1]);
+        s[nt][e] = pv;
+        rs[e >> 1] += pv;
+      }
+    }
+    l_run[0] += rs[0];
+    l_run[1] += rs[1];
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+      o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
+      o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+    }
+
+    // ---- O += P V ----
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
+      uint32_t a[4];
+      a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < DT / 2; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        // transposed loads; matrices: (keys 0-7,d0-7), (keys 8-15,d0-7), (keys 0-7,d8-15), (keys 8-15,d8-15)
+        const int key = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = dp * 2 + (lane >> 4);
+        ldsm_x4_t(tile_addr<HD>(sV, key, c), b0, b1, b2, b3);
+        mma_bf16(o_acc[dp * 2], a, b0, b1);
+        mma_bf16(o_acc[dp * 2 + 1], a, b2, b3);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- finalise ----
+#pragma unroll
+  for (int hi = 0; hi < 2; ++hi) {
+    l_run[hi] += __shfl_xor_sync(0xffffffffu, l_run[hi], 1);
+    l_run[hi] += __shfl_xor_sync(0xffffffffu, l_run[hi], 2);
+  }
+  const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
+  const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+  __nv_bfloat16* og = p.o + b * p.o_bs + h * p.o_hs;
+#pragma unroll
+  for (int i = 0; i < DT; ++i) {
+    const int col = i * 8 + (lane & 3) * 2;
+    if (r_lo < p.Sq)
+      *reinterpret_cast<uint32_t*>(og + (long long)r_lo * p.o_rs + col) = pack_bf16x2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
+    if (r_lo + 8 < p.Sq)
+      *reinterpret_cast<uint32_t*>(og + (long long)(r_lo + 8) * p.o_rs + col) = pack_bf16x2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// decode attention
+// ----------------------------------------------------------------------------------------------------------------
+struct DecodeParams {
+  const __nv_bfloat16* q; int ldq;            // [B, ldq]; head h at column h*HD
+  const __nv_bfloat16* kc; const __nv_bfloat16* vc;  // [B, KVH, ctx_max, HD]
+  __nv_bfloat16* o; int ldo;                  // [B, ldo]
+  float* ws;                                  // [B*H, nsplit, HD + 2] partials (nsplit > 1)
+  int B, H, KVH, ctx_max, nsplit;
+  const int* len_dev; int len_host;           // number of valid keys
+  float scale;
+};
+
+template <int HD, int G>
+__global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) {
+  constexpr int LPK = HD / 8;        // lanes per key (16 for hd=128, 8 for hd=64)
+  constexpr int KPW = 32 / LPK;      // keys per warp-load
+  constexpr int NSUB = 4 * KPW;      // independent softmax states per block
+  __shared__ float sh_m[NSUB][G], sh_l[NSUB][G];
+  __shared__ float sh_acc[NSUB][G][HD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPK, li = lane % LPK;
+  const int b = blockIdx.x / p.KVH, kvh = blockIdx.x % p.KVH;
+  const int split = blockIdx.y;
+  const int len = p.len_dev ? *p.len_dev : p.len_host;
+  const int per = (len + p.nsplit - 1) / p.nsplit;
+  const int k_begin = split * per, k_end = min(len, k_begin + per);
+  const float sl2 = p.scale * 1.4426950408889634f;
+
+  float qf[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    uint4 qq = *reinterpret_cast<const uint4*>(p.q + (size_t)b * p.ldq + (size_t)(kvh * G + g) * HD + li * 8);
+    float t[8];
+    t[0] = bf16lo(qq.x); t[1] = bf16hi(qq.x); t[2] = bf16lo(qq.y); t[3] = bf16hi(qq.y);
+    t[4] = bf16lo(qq.z); t[5] = bf16hi(qq.z); t[6] = bf16lo(qq.w); t[7] = bf16hi(qq.w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qf[g][j] = t[j] * sl2;
+  }
+  float m[G], l[G], acc[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    m[g] = -INFINITY; l[g] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[g][j] = 0.f;
+  }
+  const __nv_bfloat16* kbase = p.kc + ((size_t)b * p.KVH + kvh) * p.ctx_max * HD;
+  const __nv_bfloat16* vbase = p.vc + ((size_t)b * p.KVH + kvh) * p.ctx_max * HD;
+  constexpr int U = 4;
+  // this (warp, sub) walks keys k_begin + (warp*KPW + sub) + i * NSUB.  The loop bound depends on the warp only, so
+  // every lane of a warp runs the same number of iterations (the shuffles below need the full warp).
+  for (int kb = k_begin + warp * KPW; kb < k_end; kb += NSUB * U) {
+    const int k0 = kb + sub;
+    uint4 kq[U], vq[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int key = k0 + u * NSUB;
+      if (key < k_end) {
+        kq[u] = __ldg(reinterpret_cast<const uint4*>(kbase + (size_t)key * HD) + li);
+        vq[u] = __ldg(reinterpret_cast<const uint4*>(vbase + (size_t)key * HD) + li);
+      } else {
+        kq[u] = make_uint4(0, 0, 0, 0);
+        vq[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int key = k0 + u * NSUB;
+      const bool valid = key < k_end;  // uniform across the LPK lanes of this key
+      float kf[8], vf[8];
+      kf[0] = bf16lo(kq[u].x); kf[1] = bf16hi(kq[u].x); kf[2] = bf16lo(kq[u].y); kf[3] = bf16hi(kq[u].y);
+      kf[4] = bf16lo(kq[u].z); kf[5] = bf16hi(kq[u].z); kf[6] = bf16lo(kq[u].w); kf[7] = bf16hi(kq[u].w);
+      vf[0] = bf16lo(vq[u].x); vf[1] = bf16hi(vq[u].x); vf[2] = bf16lo(vq[u].y); vf[3] = bf16hi(vq[u].y);
+      vf[4] = bf16lo(vq[u].z); vf[5] = bf16hi(vq[u].z); vf[6] = bf16lo(vq[u].w); vf[7] = bf16hi(vq[u].w);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float sc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sc += qf[g][j] * kf[j];
+#pragma unroll
+        for (int o = LPK / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        if (valid) {
+          const float mn = fmaxf(m[g], sc);
+          const float c = exp2f(m[g] - mn);
+          const float pe = exp2f(sc - mn);
+          m[g] = mn;
+          l[g] = l[g] * c + pe;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[g][j] = acc[g][j] * c + pe * vf[j];
+        }
+      }
+    }
+  }
+  // combine the NSUB partial states
+  const int sidx = warp * KPW + sub;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    if (li == 0) { sh_m[sidx][g] = m[g]; sh_l[sidx][g] = l[g]; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh_acc[sidx][g][li * 8 + j] = acc[g][j];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < G * HD; idx += 128) {
+    const int g = idx / HD, d = idx % HD;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int s2 = 0; s2 < NSUB; ++s2) mm = fmaxf(mm, sh_m[s2][g]);
+    float ll = 0.f, aa = 0.f;
+    if (mm != -INFINITY) {
+#pragma unroll
+      for (int s2 = 0; s2 < NSUB; ++s2) {
+        const float c = exp2f(sh_m[s2][g] - mm);  // exp2(-inf) = 0 for empty states
+        ll += sh_l[s2][g] * c;
+        aa += sh_acc[s2][g][d] * c;
+      }
+    }
+    const int hq = kvh * G + g;
+    if (p.nsplit == 1) {
+      p.o[(size_t)b * p.ldo + (size_t)hq * HD + d] = __float2bfloat16_rn(ll > 0.f ? aa / ll : 0.f);
+    } else {
+      float* w = p.ws + (((size_t)b * p.H + hq) * p.nsplit + split) * (HD + 2);
+      w[d] = aa;
+      if (d == 0) { w[HD] = mm; w[HD + 1] = ll; }
+    }
+  }
+}
+
+template <int HD>
+__global__ void attn_decode_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ o, int ldo, int H,
+                                           int nsplit) {
+  const int bh = blockIdx.x;
+  const int b = bh / H, h = bh % H;
+  const float* w = ws + (size_t)bh * nsplit * (HD + 2);
+  float mm = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, w[s * (HD + 2) + HD]);
+  for (int d = threadIdx.x; d < HD; d += blockDim.x) {
+    float ll = 0.f, aa = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+      const float ms = w[s * (HD + 2) + HD];
+      const float c = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
+      ll += w[s * (HD + 2) + HD + 1] * c;
+      aa += w[s * (HD + 2) + d] * c;
+    }
+    o[(size_t)b * ldo + (size_t)h * HD + d] = __float2bfloat16_rn(ll > 0.f ? aa / ll : 0.f);
+  }
+}
+
+}  // namespace crab
+
+using namespace crab;
+
+extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
+  CRAB_REQUIRE(a && a->q && a->k && a->v && a->o, "crab_flash_attn: null pointer");
+  CRAB_REQUIRE(a->head_dim == 64 || a->head_dim == 128, "crab_flash_attn: head_dim must be 64 or 128 (got %d)", a->head_dim);
+  CRAB_REQUIRE(a->B > 0 && a->H > 0 && a->KVH > 0 && a->H % a->KVH == 0 && a->Sq > 0 && a->Sk > 0, "crab_flash_attn: bad shape");
+  CRAB_REQUIRE((a->gate == nullptr) == (a->bias_table == nullptr), "crab_flash_attn: gate and bias_table go together");
+  CRAB_REQUIRE(!a->causal || a->Sk >= a->Sq, "crab_flash_attn: causal needs Sk >= Sq");
+  const long long strides[] = {a->q_bs, a->q_rs, a->q_hs, a->k_bs, a->k_rs, a->k_hs, a->v_bs, a->v_rs, a->v_hs, a->o_rs, a->o_hs, a->o_bs};
+  for (long long s : strides) CRAB_REQUIRE(s % 8 == 0, "crab_flash_attn: strides must be multiples of 8 elements");
+  CRAB_REQUIRE(((uintptr_t)a->q % 16 == 0) && ((uintptr_t)a->k % 16 == 0) && ((uintptr_t)a->v % 16 == 0) && ((uintptr_t)a->o % 4 == 0),
+               "crab_flash_attn: pointer alignment");
+  FlashParams p;
+  p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v; p.o = (__nv_bfloat16*)a->o;
+  p.q_bs = a->q_bs; p.q_rs = a->q_rs; p.q_hs = a->q_hs;
+  p.k_bs = a->k_bs; p.k_rs = a->k_rs; p.k_hs = a->k_hs;
+  p.v_bs = a->v_bs; p.v_rs = a->v_rs; p.v_hs = a->v_hs;
+  p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
+  p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.Sq = a->Sq; p.Sk = a->Sk;
+  p.scale = a->scale; p.causal = a->causal; p.gate = a->gate; p.table = a->bias_table;
+  dim3 grid((a->Sq + 63) / 64, a->H, a->B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->head_dim == 64) {
+    static bool set = false;
+    if (!set) { CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlashCfg<64>::SMEM)); set = true; }
+    flash_attn_kernel<64><<<grid, 128, FlashCfg<64>::SMEM, st>>>(p);
+  } else {
+    static bool set = false;
+    if (!set) { CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlashCfg<128>::SMEM)); set = true; }
+    flash_attn_kernel<128><<<grid, 128, FlashCfg<128>::SMEM, st>>>(p);
+  }
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_attn_decode_workspace_bytes(int B, int H, int head_dim, int nsplit, int64_t* bytes) {
+  CRAB_REQUIRE(bytes != nullptr, "crab_attn_decode_workspace_bytes: null");
+  *bytes = (int64_t)B * H * nsplit * (head_dim + 2) * 4;
+  return CRAB_OK;
+}
+
+extern "C" int crab_attn_decode(const void* q, int ldq, const void* k_cache, const void* v_cache, void* o, int ldo,
+                                float* workspace, int B, int H, int KVH, int head_dim, int ctx_max, int nsplit,
+                                const int* len_dev, int len_host, float scale, void* stream) {
+  CRAB_REQUIRE(q && k_cache && v_cache && o, "crab_attn_decode: null pointer");
+  CRAB_REQUIRE(head_dim == 128 || head_dim == 64, "crab_attn_decode: head_dim must be 64 or 128");
+  CRAB_REQUIRE(B > 0 && H > 0 && KVH > 0 && H % KVH == 0, "crab_attn_decode: bad heads");
+  CRAB_REQUIRE(nsplit >= 1 && (nsplit == 1 || workspace != nullptr), "crab_attn_decode: nsplit>1 needs a workspace");
+  CRAB_REQUIRE(ldq % 8 == 0 && ((uintptr_t)q % 16 == 0), "crab_attn_decode: q alignment");
+  const int G = H / KVH;
+  DecodeParams p;
+  p.q = (const __nv_bfloat16*)q; p.ldq = ldq; p.kc = (const __nv_bfloat16*)k_cache; p.vc = (const __nv_bfloat16*)v_cache;
+  p.o = (__nv_bfloat16*)o; p.ldo = ldo; p.ws = workspace; p.B = B; p.H = H; p.KVH = KVH; p.ctx_max = ctx_max;
+  p.nsplit = nsplit; p.len_dev = len_dev; p.len_host = len_host; p.scale = scale;
+  dim3 grid(B * KVH, nsplit);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CRAB_DECODE_CASE(HD_, G_) \
+  if (head_dim == HD_ && G == G_) { attn_decode_kernel<HD_, G_><<<grid, 128, 0, st>>>(p); } else
+  CRAB_DECODE_CASE(128, 1) CRAB_DECODE_CASE(128, 2) CRAB_DECODE_CASE(128, 4) CRAB_DECODE_CASE(128, 7)
+  CRAB_DECODE_CASE(128, 8) CRAB_DECODE_CASE(64, 1)
+  { return set_error(CRAB_ERR_INVALID, "crab_attn_decode: unsupported head_dim=%d group=%d", head_dim, G); }
+#undef CRAB_DECODE_CASE
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  if (nsplit > 1) {
+    if (head_dim == 128) attn_decode_combine_kernel<128><<<B * H, 128, 0, st>>>(workspace, p.o, ldo, H, nsplit);
+    else attn_decode_combine_kernel<64><<<B * H, 64, 0, st>>>(workspace, p.o, ldo, H, nsplit);
+    CRAB_CHECK_CUDA(cudaGetLastError());
+  }
+  return CRAB_OK;
+}

@@ -1,0 +1,489 @@
+// HBM-bound glue kernels of the hot path: norms, RoPE + KV-cache append, gathers/splices, patchify, CLIP embedding
+// assembly, BEATs gate / pos-conv packing, arg-max.  All use 16-byte vector loads, fp32 math and warp-shuffle
+// reductions; one row per warp or per block, grids sized by rows.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace crab {
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? sh[l] : 0.f;
+  t = warp_sum(t);
+  __syncthreads();
+  return t;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  f[0] = bf16lo(q.x); f[1] = bf16hi(q.x); f[2] = bf16lo(q.y); f[3] = bf16hi(q.y);
+  f[4] = bf16lo(q.z); f[5] = bf16hi(q.z); f[6] = bf16lo(q.w); f[7] = bf16hi(q.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  q.x = pack_bf16x2(f[0], f[1]); q.y = pack_bf16x2(f[2], f[3]);
+  q.z = pack_bf16x2(f[4], f[5]); q.w = pack_bf16x2(f[6], f[7]);
+  return q;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// LayerNorm / RMSNorm: one block per row, row cached in registers (cols <= 8 * 8 * blockDim.x)
+// ----------------------------------------------------------------------------------------------------------------
+template <bool RMS, int VPT /* 8-element vectors per thread */>
+__global__ void __launch_bounds__(256) norm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                   __nv_bfloat16* __restrict__ y, int ldy, int rows, int cols, float eps) {
+  __shared__ float sh[32];
+  const int row = blockIdx.x;
+  const __nv_bfloat16* xr = x + (size_t)row * ldx;
+  float v[VPT][8];
+  const int nvec = cols >> 3;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nvec) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + vi), v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += RMS ? v[i][j] * v[i][j] : v[i][j];
+    }
+  }
+  s = block_sum(s, sh);
+  float mean = 0.f, rstd;
+  if (RMS) {
+    rstd = rsqrtf(s / cols + eps);
+  } else {
+    mean = s / cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int vi = threadIdx.x + i * blockDim.x;
+      if (vi < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+      }
+    }
+    q = block_sum(q, sh);
+    rstd = rsqrtf(q / cols + eps);
+  }
+  __nv_bfloat16* yr = y + (size_t)row * ldy;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nvec) {
+      float o[8];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      if (RMS) {
+        // HF LlamaRMSNorm: weight * (x_fp32 * rstd).to(bf16)   (models/modeling_llama.py:112-117)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = g[j] * __bfloat162float(__float2bfloat16_rn(v[i][j] * rstd));
+      } else {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi);
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi + 1);
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+      }
+      *(reinterpret_cast<uint4*>(yr) + vi) = pack8(o);
+    }
+  }
+}
+
+template <bool RMS>
+static int launch_norm(const void* x, int ldx, const float* gamma, const float* beta, void* y, int ldy, int rows,
+                       int cols, float eps, cudaStream_t st) {
+  CRAB_REQUIRE(cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "norm: cols/ld must be multiples of 8 (cols=%d)", cols);
+  CRAB_REQUIRE(cols <= 16384, "norm: cols=%d too large", cols);
+  if (rows <= 0) return CRAB_OK;
+  const int nvec = cols / 8;
+  auto xx = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto yy = reinterpret_cast<__nv_bfloat16*>(y);
+  if (nvec <= 128) norm_kernel<RMS, 1><<<rows, 128, 0, st>>>(xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else if (nvec <= 256) norm_kernel<RMS, 1><<<rows, 256, 0, st>>>(xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else if (nvec <= 512) norm_kernel<RMS, 2><<<rows, 256, 0, st>>>(xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else if (nvec <= 1024) norm_kernel<RMS, 4><<<rows, 256, 0, st>>>(xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else norm_kernel<RMS, 8><<<rows, 256, 0, st>>>(xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// RoPE table (accurate, one-time) and RoPE + KV-cache append
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void rope_table_kernel(float* cs, int max_pos, int half, double theta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= max_pos * half) return;
+  const int pos = i / half, j = i % half;
+  // fp32 inv_freq and fp32 product, as LlamaRotaryEmbedding does (models/modeling_llama.py:123-156)
+  const float inv = 1.0f / (float)pow(theta, (double)(2 * j) / (double)(2 * half));
+  const float ang = (float)pos * inv;
+  double s, c;
+  sincos((double)ang, &s, &c);
+  cs[(size_t)pos * 2 * half + j] = (float)c;
+  cs[(size_t)pos * 2 * half + half + j] = (float)s;
+}
+
+// qkv: [B*S, ldq] rows hold [q (H*hd) | k (KV*hd) | v (KV*hd)].  q is rotated in place; rotated k and v go to the
+// cache [B, KV, ctx_max, hd] at position past + s.  One warp per (row, head); hd in {64, 128}.
+template <int HD>
+__global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, int ldq, const float* __restrict__ cs,
+                               __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int B, int S, int H,
+                               int KV, int ctx_max, const int* __restrict__ past_dev, int past_host) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int heads_total = H + 2 * KV;
+  if (warp >= B * S * heads_total) return;
+  const int row = warp / heads_total, hh = warp % heads_total;
+  const int b = row / S, s = row % S;
+  const int past = past_dev ? *past_dev : past_host;
+  const int pos = past + s;
+  __nv_bfloat16* src = qkv + (size_t)row * ldq + (size_t)hh * HD;
+  constexpr int EPL = HD / 32;  // elements per lane in each half... lane handles EPL/2 pairs (j, j + HD/2)
+  if (hh < H + KV) {
+    // rotate: out[j] = x[j] c[j] - x[j+h] s[j];  out[j+h] = x[j+h] c[j] + x[j] s[j]
+    constexpr int half = HD / 2;
+    constexpr int PPL = half / 32;  // pairs per lane (1 for 64, 2 for 128)
+    float lo[PPL], hi[PPL];
+#pragma unroll
+    for (int p = 0; p < PPL; ++p) {
+      const int j = lane * PPL + p;
+      lo[p] = __bfloat162float(src[j]);
+      hi[p] = __bfloat162float(src[j + half]);
+    }
+    __nv_bfloat16* dst = src;
+    if (hh >= H) dst = kc + (((size_t)b * KV + (hh - H)) * ctx_max + pos) * HD;
+#pragma unroll
+    for (int p = 0; p < PPL; ++p) {
+      const int j = lane * PPL + p;
+      const float c = cs[(size_t)pos * HD + j], sn = cs[(size_t)pos * HD + half + j];
+      dst[j] = __float2bfloat16_rn(lo[p] * c - hi[p] * sn);
+      dst[j + half] = __float2bfloat16_rn(hi[p] * c + lo[p] * sn);
+    }
+  } else {
+    __nv_bfloat16* dst = vc + (((size_t)b * KV + (hh - H - KV)) * ctx_max + pos) * HD;
+#pragma unroll
+    for (int p = 0; p < EPL; ++p) dst[lane * EPL + p] = src[lane * EPL + p];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Row gather / scatter (embedding lookup, splice of modality embeddings, left padding)
+// dst[dst_rows[i] or i] = src[src_rows[i] or i]   (cols bf16, multiples of 8)
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, int lds, const int64_t* __restrict__ src_rows,
+                                   __nv_bfloat16* __restrict__ dst, int ldd, const int64_t* __restrict__ dst_rows,
+                                   int n, int cols) {
+  const int i = blockIdx.x;
+  const int64_t sr = src_rows ? src_rows[i] : i;
+  const int64_t dr = dst_rows ? dst_rows[i] : i;
+  const uint4* s = reinterpret_cast<const uint4*>(src + sr * lds);
+  uint4* d = reinterpret_cast<uint4*>(dst + dr * ldd);
+  for (int v = threadIdx.x; v < cols / 8; v += blockDim.x) d[v] = __ldg(s + v);
+}
+
+// fp32 -> bf16 rows (encoder inputs / fp32 features entering the bf16 path)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + i) = o;
+  } else {
+    for (; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Patchify: fp32 NCHW images -> bf16 patch rows [n_img * gh * gw, ld] with column order (c, kh, kw), i.e. the
+// flattened Conv2d weight order, so the stride==kernel patch-embed conv is a GEMM.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int ld, int C, int Hh,
+                                int Ww, int p, int gh, int gw) {
+  const int prow = blockIdx.x;  // patch row index
+  const int n = prow / (gh * gw), r = prow % (gh * gw);
+  const int py = r / gw, px = r % gw;
+  const int kcols = C * p * p;
+  __nv_bfloat16* o = out + (size_t)prow * ld;
+  for (int k = threadIdx.x; k < ld; k += blockDim.x) {
+    float v = 0.f;
+    if (k < kcols) {
+      const int c = k / (p * p), rem = k % (p * p);
+      const int ky = rem / p, kx = rem % p;
+      v = img[(((size_t)n * C + c) * Hh + (py * p + ky)) * Ww + (px * p + kx)];
+    }
+    o[k] = __float2bfloat16_rn(v);
+  }
+}
+
+// CLIP embeddings: x[n, 0] = cls + pos[0]; x[n, 1+t] = patch[n, t] + pos[1+t]; then pre_layrnorm.  One block per
+// token row; D <= 2048.
+__global__ void __launch_bounds__(256)
+clip_embed_ln_kernel(const __nv_bfloat16* __restrict__ patch, const float* __restrict__ cls,
+                     const float* __restrict__ pos, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __nv_bfloat16* __restrict__ out, int tokens /*incl. cls*/, int D, float eps) {
+  __shared__ float sh[32];
+  const int row = blockIdx.x;
+  const int n = row / tokens, t = row % tokens;
+  float v[8];
+  const int c0 = threadIdx.x * 8;
+  float s = 0.f;
+  if (c0 < D) {
+    if (t == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = cls[c0 + j];
+    } else {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(patch + ((size_t)n * (tokens - 1) + (t - 1)) * D + c0)), v);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] += pos[(size_t)t * D + c0 + j]; s += v[j]; }
+  }
+  const float mean = block_sum(s, sh) / D;
+  float q = 0.f;
+  if (c0 < D) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q += d * d; }
+  }
+  const float rstd = rsqrtf(block_sum(q, sh) / D + eps);
+  if (c0 < D) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rstd * gamma[c0 + j] + beta[c0 + j];
+    *reinterpret_cast<uint4*>(out + (size_t)row * D + c0) = pack8(o);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// BEATs helpers
+// ----------------------------------------------------------------------------------------------------------------
+// gate[b, h, t] = ga * (gb * grep_a[h] - 1) + 2 with (ga, gb) = sigmoid(sum of 4 outputs each of grep_linear(q))
+// (models/beats/backbone.py:650-662).  q: [B*T, ldq] unscaled, head h at column h*64.  One warp per (row, head).
+__global__ void beats_gate_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const float* __restrict__ gw /*[8,64]*/,
+                                  const float* __restrict__ gb /*[8]*/, const float* __restrict__ grep_a /*[H]*/,
+                                  float* __restrict__ gate /*[B,H,T]*/, int B, int T, int H) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * T * H) return;
+  const int row = warp / H, h = warp % H;
+  const int b = row / T, t = row % T;
+  const __nv_bfloat16* qp = q + (size_t)row * ldq + h * 64;
+  const float x0 = __bfloat162float(qp[lane]), x1 = __bfloat162float(qp[lane + 32]);
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = warp_sum(x0 * gw[o * 64 + lane] + x1 * gw[o * 64 + 32 + lane]);
+  if (lane == 0) {
+    float a = 0.f, bb = 0.f;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { a += acc[o] + gb[o]; bb += acc[4 + o] + gb[4 + o]; }
+    const float ga = 1.f / (1.f + __expf(-a)), gbv = 1.f / (1.f + __expf(-bb));
+    gate[((size_t)b * H + h) * T + t] = ga * (gbv * grep_a[h] - 1.f) + 2.f;
+  }
+}
+
+// x [B, T, C] -> xg [G][B][T * cg]   (cg = C / G channels per conv group), for the Toeplitz-GEMM pos-conv.
+__global__ void beats_group_pack_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xg, int B,
+                                        int T, int C, int G) {
+  const int cg = C / G;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * T * C) return;
+  const int c = i % C;
+  const int t = (i / C) % T;
+  const int b = i / ((size_t)C * T);
+  const int g = c / cg, ci = c % cg;
+  xg[((size_t)g * B + b) * (T * cg) + t * cg + ci] = x[i];
+}
+
+// y[b,t,c] = x[b,t,c] + GELU(conv[g][b][t*cg+co] + bias[c])   (backbone.py:114-116), bf16 out (LayerNorm follows)
+__global__ void beats_posconv_finish_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ cg_out,
+                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int T,
+                                            int C, int G) {
+  const int cg = C / G;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * T * C) return;
+  const int c = i % C;
+  const int t = (i / C) % T;
+  const int b = i / ((size_t)C * T);
+  const int g = c / cg, co = c % cg;
+  const float v = __bfloat162float(cg_out[((size_t)g * B + b) * (T * cg) + t * cg + co]) + bias[c];
+  const float ge = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  y[i] = __float2bfloat16_rn(__bfloat162float(x[i]) + ge);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// arg-max over the first V columns of fp32 logits rows (first index wins ties, like torch.argmax on CPU/CUDA)
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ logits, int ld, int V,
+                                                     int64_t* __restrict__ out) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const float* r = logits + (size_t)blockIdx.x * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = r[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sv[w] = best; si[w] = bi; }
+  __syncthreads();
+  if (w == 0) {
+    best = (l < 8) ? sv[l] : -INFINITY;
+    bi = (l < 8) ? si[l] : 0x7fffffff;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (l == 0) out[blockIdx.x] = bi;
+  }
+}
+
+// device-side scalar increment (decode position counter inside a CUDA graph)
+__global__ void add_scalar_kernel(int* p, int v) { *p += v; }
+
+}  // namespace crab
+
+using namespace crab;
+
+extern "C" int crab_layernorm(const void* x, int ldx, const float* gamma, const float* beta, void* y, int ldy,
+                              int rows, int cols, float eps, void* stream) {
+  CRAB_REQUIRE(x && y && gamma && beta, "crab_layernorm: null pointer");
+  return launch_norm<false>(x, ldx, gamma, beta, y, ldy, rows, cols, eps, (cudaStream_t)stream);
+}
+
+extern "C" int crab_rmsnorm(const void* x, int ldx, const float* gamma, void* y, int ldy, int rows, int cols,
+                            float eps, void* stream) {
+  CRAB_REQUIRE(x && y && gamma, "crab_rmsnorm: null pointer");
+  return launch_norm<true>(x, ldx, gamma, nullptr, y, ldy, rows, cols, eps, (cudaStream_t)stream);
+}
+
+extern "C" int crab_rope_table(float* cos_sin, int max_pos, int head_dim, double theta, void* stream) {
+  CRAB_REQUIRE(cos_sin && max_pos > 0 && head_dim % 2 == 0, "crab_rope_table: bad args");
+  const int n = max_pos * (head_dim / 2);
+  rope_table_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cos_sin, max_pos, head_dim / 2, theta);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_rope_kv_append(void* qkv, int ldq, const float* cos_sin, void* k_cache, void* v_cache, int B, int S,
+                                   int H, int KV, int head_dim, int ctx_max, const int* past_dev, int past_host,
+                                   void* stream) {
+  CRAB_REQUIRE(qkv && cos_sin && k_cache && v_cache, "crab_rope_kv_append: null pointer");
+  CRAB_REQUIRE(head_dim == 64 || head_dim == 128, "crab_rope_kv_append: head_dim must be 64 or 128 (got %d)", head_dim);
+  CRAB_REQUIRE(past_dev != nullptr || past_host + S <= ctx_max, "crab_rope_kv_append: past+S exceeds ctx_max");
+  const long warps = (long)B * S * (H + 2 * KV);
+  if (warps == 0) return CRAB_OK;
+  const int blocks = (int)((warps * 32 + 255) / 256);
+  auto q = reinterpret_cast<__nv_bfloat16*>(qkv);
+  auto kc = reinterpret_cast<__nv_bfloat16*>(k_cache);
+  auto vc = reinterpret_cast<__nv_bfloat16*>(v_cache);
+  if (head_dim == 128)
+    rope_kv_kernel<128><<<blocks, 256, 0, (cudaStream_t)stream>>>(q, ldq, cos_sin, kc, vc, B, S, H, KV, ctx_max, past_dev, past_host);
+  else
+    rope_kv_kernel<64><<<blocks, 256, 0, (cudaStream_t)stream>>>(q, ldq, cos_sin, kc, vc, B, S, H, KV, ctx_max, past_dev, past_host);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_gather_rows(const void* src, int lds, const int64_t* src_rows, void* dst, int ldd,
+                                const int64_t* dst_rows, int n, int cols, void* stream) {
+  CRAB_REQUIRE(src && dst, "crab_gather_rows: null pointer");
+  CRAB_REQUIRE(cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "crab_gather_rows: cols/ld must be multiples of 8");
+  if (n <= 0) return CRAB_OK;
+  gather_rows_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds, src_rows,
+                                                         reinterpret_cast<__nv_bfloat16*>(dst), ldd, dst_rows, n, cols);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  CRAB_REQUIRE(src && dst && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0), "crab_cast_f32_bf16: bad pointer");
+  if (n <= 0) return CRAB_OK;
+  const int64_t th = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<(unsigned)((th + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), (size_t)n);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_patchify(const float* images, void* out, int ld_out, int n_img, int C, int H, int W, int patch,
+                             void* stream) {
+  CRAB_REQUIRE(images && out && patch > 0, "crab_patchify: bad args");
+  const int gh = H / patch, gw = W / patch;
+  CRAB_REQUIRE(ld_out >= C * patch * patch && ld_out % 8 == 0, "crab_patchify: ld_out too small / unaligned");
+  const int rows = n_img * gh * gw;
+  if (rows <= 0) return CRAB_OK;
+  patchify_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(images, reinterpret_cast<__nv_bfloat16*>(out), ld_out, C, H, W, patch, gh, gw);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_clip_embed_ln(const void* patch_emb, const float* cls, const float* pos, const float* gamma,
+                                  const float* beta, void* out, int n_img, int tokens, int D, float eps, void* stream) {
+  CRAB_REQUIRE(patch_emb && cls && pos && gamma && beta && out, "crab_clip_embed_ln: null pointer");
+  CRAB_REQUIRE(D % 8 == 0 && D <= 2048, "crab_clip_embed_ln: D must be <= 2048 and a multiple of 8");
+  if (n_img <= 0) return CRAB_OK;
+  clip_embed_ln_kernel<<<n_img * tokens, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(patch_emb), cls, pos, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), tokens, D, eps);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_beats_gate(const void* q, int ldq, const float* grep_w, const float* grep_b, const float* grep_a,
+                               float* gate, int B, int T, int H, void* stream) {
+  CRAB_REQUIRE(q && grep_w && grep_b && grep_a && gate, "crab_beats_gate: null pointer");
+  const long warps = (long)B * T * H;
+  if (warps == 0) return CRAB_OK;
+  beats_gate_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(q), ldq, grep_w, grep_b, grep_a, gate, B, T, H);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_beats_group_pack(const void* x, void* xg, int B, int T, int C, int G, void* stream) {
+  CRAB_REQUIRE(x && xg && G > 0 && C % G == 0, "crab_beats_group_pack: bad args");
+  const size_t n = (size_t)B * T * C;
+  if (n == 0) return CRAB_OK;
+  beats_group_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(xg), B, T, C, G);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_beats_posconv_finish(const void* x, const void* conv_g, const float* bias, void* y, int B, int T,
+                                         int C, int G, void* stream) {
+  CRAB_REQUIRE(x && conv_g && bias && y && G > 0 && C % G == 0, "crab_beats_posconv_finish: bad args");
+  const size_t n = (size_t)B * T * C;
+  if (n == 0) return CRAB_OK;
+  beats_posconv_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(conv_g), bias,
+      reinterpret_cast<__nv_bfloat16*>(y), B, T, C, G);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_argmax(const float* logits, int ld, int rows, int V, int64_t* out, void* stream) {
+  CRAB_REQUIRE(logits && out && V > 0, "crab_argmax: bad args");
+  if (rows <= 0) return CRAB_OK;
+  argmax_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, V, out);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_add_scalar_i32(int* p, int v, void* stream) {
+  CRAB_REQUIRE(p != nullptr, "crab_add_scalar_i32: null pointer");
+  add_scalar_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p, v);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}

@@ -1,0 +1,697 @@
+"""Host-side orchestration of Crab's hot path on one B200: weight packing (reference state-dict names -> packed
+bf16 device buffers) and the kernel sequences for the encoders, the Q-Former bridges, decoder prefill and the
+CUDA-graph decode step.  Python here is tensor plumbing only: every arithmetic step is a call into
+libcrab_b200.so through `crab_b200.ops` (there is no torch math on the data path, and no CPU fallback).
+
+Reference call stack being replaced:
+  UnifiedForCausalLM.generate (models/unified_llama.py:244-267)
+    -> prepare_multimodal_inputs (models/unified_arch.py:217-406)
+         -> encode_video / encode_audio (models/unified_arch.py:113-155; models/multimodal_encoder.py)
+    -> HF greedy loop over LlamaForCausalLM / Qwen2ForCausalLM with hyper-LoRA linears
+       (peft_hyper/tuners/lora.py:338-369)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+SD = Dict[str, torch.Tensor]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# configuration (mirrors the fields the reference reads from LlamaConfig/Qwen2Config, the CLIP/BEATs/Bert configs
+# and configs/unified_config.py)
+# --------------------------------------------------------------------------------------------------------------
+@dataclass
+class DecoderConfig:
+    hidden: int = 4096
+    inter: int = 11008
+    layers: int = 32
+    heads: int = 32
+    kv_heads: int = 32
+    head_dim: int = 128
+    vocab: int = 32017
+    rope_theta: float = 10000.0
+    eps: float = 1e-6
+    qkv_bias: bool = False
+    lora_r: int = 8
+    lora_alpha: int = 16
+    lora_nums: int = 3
+
+
+@dataclass
+class ClipConfig:
+    hidden: int = 1024
+    inter: int = 4096
+    heads: int = 16
+    layers: int = 24
+    patch: int = 14
+    image: int = 224
+    eps: float = 1e-5
+
+
+@dataclass
+class BeatsConfig:
+    patch: int = 16
+    embed: int = 512
+    dim: int = 768
+    ffn: int = 3072
+    heads: int = 12
+    layers: int = 12
+    conv_pos: int = 128
+    conv_groups: int = 16
+    num_buckets: int = 320
+    max_distance: int = 800
+    eps: float = 1e-5
+
+
+@dataclass
+class QformerConfig:
+    hidden: int = 768
+    heads: int = 12
+    inter: int = 3072
+    layers: int = 2
+    eps: float = 1e-12
+
+
+@dataclass
+class CrabConfig:
+    decoder: DecoderConfig = field(default_factory=DecoderConfig)
+    clip: ClipConfig = field(default_factory=ClipConfig)
+    beats: BeatsConfig = field(default_factory=BeatsConfig)
+    qformer: QformerConfig = field(default_factory=QformerConfig)
+    select_layers: Tuple[int, ...] = (14, 22, 23)
+    n_query: int = 32
+    pad_token_id: int = 0
+    max_ctx: int = 1280
+    special_ids: Dict[str, int] = field(default_factory=dict)  # from initialize_MM_tokenizer
+
+
+def _bf(t: torch.Tensor, dev) -> torch.Tensor:
+    return t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+
+
+def _f32(t: torch.Tensor, dev) -> torch.Tensor:
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _pad_cols(w: torch.Tensor, cols: int) -> torch.Tensor:
+    if w.shape[1] == cols:
+        return w.contiguous()
+    out = torch.zeros((w.shape[0], cols), dtype=w.dtype, device=w.device)
+    out[:, : w.shape[1]] = w
+    return out
+
+
+class _Lin:
+    """A packed dense layer: bf16 weight [N, K(+ext)], fp32 bias."""
+
+    __slots__ = ("w", "b")
+
+    def __init__(self, w, b=None):
+        self.w, self.b = w, b
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Encoders + bridges
+# --------------------------------------------------------------------------------------------------------------
+class _QformerWeights:
+    def __init__(self, sd: SD, p: str, cfg: QformerConfig, dev):
+        b = p + "bert."
+        self.emb_ln = (_f32(sd[b + "embeddings.LayerNorm.weight"], dev), _f32(sd[b + "embeddings.LayerNorm.bias"], dev))
+        self.layers = []
+        for i in range(cfg.layers):
+            lp = f"{b}encoder.layer.{i}."
+
+            def lin(n):
+                return _Lin(_bf(sd[lp + n + ".weight"], dev), _f32(sd[lp + n + ".bias"], dev))
+
+            def ln(n):
+                return (_f32(sd[lp + n + ".weight"], dev), _f32(sd[lp + n + ".bias"], dev))
+
+            def cat(names):
+                return _Lin(_bf(torch.cat([sd[lp + n + ".weight"] for n in names], 0), dev),
+                            _f32(torch.cat([sd[lp + n + ".bias"] for n in names], 0), dev))
+
+            self.layers.append(dict(
+                self_qkv=cat(["attention.self.query", "attention.self.key", "attention.self.value"]),
+                self_out=lin("attention.output.dense"), self_ln=ln("attention.output.LayerNorm"),
+                cross_q=lin("crossattention.self.query"),
+                cross_kv=cat(["crossattention.self.key", "crossattention.self.value"]),
+                cross_out=lin("crossattention.output.dense"), cross_ln=ln("crossattention.output.LayerNorm"),
+                ffn_in=lin("intermediate_query.dense"), ffn_out=lin("output_query.dense"),
+                ffn_ln=ln("output_query.LayerNorm")))
+
+
+class CrabEngine:
+    def __init__(self, sd: SD, cfg: CrabConfig, device: Optional[torch.device] = None, load_encoders: bool = True):
+        if not torch.cuda.is_available():
+            raise ops._l.CrabError("crab_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        ops.init(self.dev.index or 0)
+        self.cfg = cfg
+        sd = {(k[len("base_model.model."):] if k.startswith("base_model.model.") else k): v for k, v in sd.items()}
+        self._pack_decoder(sd)
+        self.has_encoders = load_encoders and ("model.vl_projector.visual_ln.weight" in sd)
+        if self.has_encoders:
+            self._pack_clip(sd)
+            self._pack_beats(sd)
+            self._pack_bridges(sd)
+        self._bufs: Dict[Tuple, torch.Tensor] = {}
+        self._graph = None
+        self._graph_bs = None
+        self.k_cache: List[torch.Tensor] = []
+        self.v_cache: List[torch.Tensor] = []
+
+    # ---- buffers -------------------------------------------------------------------------------------------
+    def _buf(self, name: str, shape, dtype=torch.bfloat16, zero=False) -> torch.Tensor:
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), device=self.dev, dtype=dtype)
+            self._bufs[key] = t
+        return t
+
+    # ---- decoder weights -------------------------------------------------------------------------------------
+    def _pack_decoder(self, sd: SD):
+        c, dev = self.cfg.decoder, self.dev
+        D, F, H, KV, hd = c.hidden, c.inter, c.heads, c.kv_heads, c.head_dim
+        assert F % 64 == 0 and D % 8 == 0 and hd in (64, 128)
+        self.lora = "model.layers.0.self_attn.q_proj.lora_A.weight" in sd
+        self.embed = _bf(sd["model.embed_tokens.weight"], dev)
+        self.final_norm = _f32(sd["model.norm.weight"], dev)
+        V = sd["lm_head.weight"].shape[0]
+        self.vocab = V
+        self.vocab_pad = (V + 7) // 8 * 8
+        lm = torch.zeros((self.vocab_pad, D), dtype=torch.bfloat16, device=dev)
+        lm[:V] = _bf(sd["lm_head.weight"], dev)
+        self.lm_head = lm
+        self.scaling = c.lora_alpha / c.lora_r
+        nl, r = c.lora_nums, c.lora_r
+        zw = nl * r  # 24 z columns per linear
+        self.EXT_QKV, self.EXT_O, self.EXT_GU, self.EXT_D = 96, 32, 64, 32
+        self.layers = []
+
+        def bcat(name):  # [out, 24] = [B0 | B1 | B2]
+            return torch.cat([sd[f"{name}.lora_B{i}.weight"].float() for i in range(nl)], dim=1)
+
+        def ra(names):  # rows [R (3); A (8)] per linear
+            return _bf(torch.cat([torch.cat([sd[n + ".lora_route.weight"], sd[n + ".lora_A.weight"]], 0) for n in names], 0), dev)
+
+        for i in range(c.layers):
+            lp = f"model.layers.{i}."
+            at, ml = lp + "self_attn.", lp + "mlp."
+            L = {}
+            nq, nk = H * hd, KV * hd
+            wq = torch.zeros((nq + 2 * nk, D + self.EXT_QKV), dtype=torch.float32)
+            wq[:nq, :D] = sd[at + "q_proj.weight"].float()
+            wq[nq:nq + nk, :D] = sd[at + "k_proj.weight"].float()
+            wq[nq + nk:, :D] = sd[at + "v_proj.weight"].float()
+            if self.lora:
+                wq[:nq, D:D + zw] = bcat(at + "q_proj")
+                wq[nq:nq + nk, D + zw:D + 2 * zw] = bcat(at + "k_proj")
+                wq[nq + nk:, D + 2 * zw:D + 3 * zw] = bcat(at + "v_proj")
+                L["ra_qkv"] = ra([at + "q_proj", at + "k_proj", at + "v_proj"])
+            L["wqkv"] = _bf(wq, dev)
+            L["bqkv"] = (_f32(torch.cat([sd[at + "q_proj.bias"], sd[at + "k_proj.bias"], sd[at + "v_proj.bias"]]), dev)
+                         if c.qkv_bias else None)
+            wo = torch.zeros((D, nq + self.EXT_O), dtype=torch.float32)
+            wo[:, :nq] = sd[at + "o_proj.weight"].float()
+            if self.lora:
+                wo[:, nq:nq + zw] = bcat(at + "o_proj")
+                L["ra_o"] = ra([at + "o_proj"])
+            L["wo"] = _bf(wo, dev)
+            wg = torch.zeros((F, D + self.EXT_GU), dtype=torch.float32)
+            wu = torch.zeros((F, D + self.EXT_GU), dtype=torch.float32)
+            wg[:, :D] = sd[ml + "gate_proj.weight"].float()
+            wu[:, :D] = sd[ml + "up_proj.weight"].float()
+            if self.lora:
+                wg[:, D:D + zw] = bcat(ml + "gate_proj")
+                wu[:, D + zw:D + 2 * zw] = bcat(ml + "up_proj")
+                L["ra_gu"] = ra([ml + "gate_proj", ml + "up_proj"])
+            # interleave [64 gate | 64 up] row groups so one output tile holds both halves (SWIGLU epilogue)
+            L["wgu"] = _bf(torch.stack([wg.view(F // 64, 64, -1), wu.view(F // 64, 64, -1)], dim=1).reshape(2 * F, -1), dev)
+            wd = torch.zeros((D, F + self.EXT_D), dtype=torch.float32)
+            wd[:, :F] = sd[ml + "down_proj.weight"].float()
+            if self.lora:
+                wd[:, F:F + zw] = bcat(ml + "down_proj")
+                L["ra_d"] = ra([ml + "down_proj"])
+            L["wd"] = _bf(wd, dev)
+            L["ln1"] = _f32(sd[lp + "input_layernorm.weight"], dev)
+            L["ln2"] = _f32(sd[lp + "post_attention_layernorm.weight"], dev)
+            self.layers.append(L)
+        self.rope = ops.rope_table(self.cfg.max_ctx, hd, c.rope_theta, dev)
+
+    # ---- CLIP --------------------------------------------------------------------------------------------------
+    def _pack_clip(self, sd: SD):
+        c, dev = self.cfg.clip, self.dev
+        p = "model.visual_encoder.vision_tower.vision_model."
+        self.clip_layers_run = max(self.cfg.select_layers)  # hidden_states[k] = output of layer k (1-based)
+        kp = 3 * c.patch * c.patch
+        self.clip_kpad = (kp + 7) // 8 * 8
+        self.clip_patch_w = _bf(_pad_cols(sd[p + "embeddings.patch_embedding.weight"].reshape(c.hidden, kp).float(), self.clip_kpad), dev)
+        self.clip_cls = _f32(sd[p + "embeddings.class_embedding"], dev)
+        self.clip_pos = _f32(sd[p + "embeddings.position_embedding.weight"], dev)
+        self.clip_pre_ln = (_f32(sd[p + "pre_layrnorm.weight"], dev), _f32(sd[p + "pre_layrnorm.bias"], dev))
+        self.clip_layers = []
+        for i in range(self.clip_layers_run):
+            lp = f"{p}encoder.layers.{i}."
+            a = lp + "self_attn."
+            self.clip_layers.append(dict(
+                ln1=(_f32(sd[lp + "layer_norm1.weight"], dev), _f32(sd[lp + "layer_norm1.bias"], dev)),
+                ln2=(_f32(sd[lp + "layer_norm2.weight"], dev), _f32(sd[lp + "layer_norm2.bias"], dev)),
+                qkv=_Lin(_bf(torch.cat([sd[a + "q_proj.weight"], sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0), dev),
+                         _f32(torch.cat([sd[a + "q_proj.bias"], sd[a + "k_proj.bias"], sd[a + "v_proj.bias"]], 0), dev)),
+                out=_Lin(_bf(sd[a + "out_proj.weight"], dev), _f32(sd[a + "out_proj.bias"], dev)),
+                fc1=_Lin(_bf(sd[lp + "mlp.fc1.weight"], dev), _f32(sd[lp + "mlp.fc1.bias"], dev)),
+                fc2=_Lin(_bf(sd[lp + "mlp.fc2.weight"], dev), _f32(sd[lp + "mlp.fc2.bias"], dev))))
+
+    # ---- BEATs -------------------------------------------------------------------------------------------------
+    def _pack_beats(self, sd: SD):
+        c, dev = self.cfg.beats, self.dev
+        p = "model.audio_encoder.audio_encoder."
+        self.beats_patch_w = _bf(sd[p + "patch_embedding.weight"].reshape(c.embed, c.patch * c.patch), dev)
+        self.beats_ln0 = (_f32(sd[p + "layer_norm.weight"], dev), _f32(sd[p + "layer_norm.bias"], dev))
+        self.beats_proj = _Lin(_bf(sd[p + "post_extract_proj.weight"], dev), _f32(sd[p + "post_extract_proj.bias"], dev))
+        pc = p + "encoder.pos_conv.0."
+        if pc + "weight_g" in sd:
+            g, v = sd[pc + "weight_g"].float(), sd[pc + "weight_v"].float()
+        else:
+            g, v = sd[pc + "parametrizations.weight.original0"].float(), sd[pc + "parametrizations.weight.original1"].float()
+        # weight_norm(dim=2) folded once at load time (models/beats/backbone.py:45)
+        self.beats_conv_w = (v * (g / v.norm(dim=(0, 1), keepdim=True))).to(dev)  # [C, C/G, K] fp32
+        self.beats_conv_b = _f32(sd[pc + "bias"], dev)
+        self.beats_enc_ln = (_f32(sd[p + "encoder.layer_norm.weight"], dev), _f32(sd[p + "encoder.layer_norm.bias"], dev))
+        self.beats_rel = sd[p + "encoder.layers.0.self_attn.relative_attention_bias.weight"].float().to(dev)  # [buckets, H]
+        self.beats_alpha = math.pow(2 * c.layers, 0.25)
+        self.beats_layers = []
+        for i in range(c.layers):
+            lp = f"{p}encoder.layers.{i}."
+            a = lp + "self_attn."
+            self.beats_layers.append(dict(
+                qkv=_Lin(_bf(torch.cat([sd[a + "q_proj.weight"], sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0), dev),
+                         _f32(torch.cat([sd[a + "q_proj.bias"], sd[a + "k_proj.bias"], sd[a + "v_proj.bias"]], 0), dev)),
+                out=_Lin(_bf(sd[a + "out_proj.weight"], dev), _f32(sd[a + "out_proj.bias"], dev)),
+                grep_w=_f32(sd[a + "grep_linear.weight"], dev), grep_b=_f32(sd[a + "grep_linear.bias"], dev),
+                grep_a=_f32(sd[a + "grep_a"].reshape(-1), dev),
+                ln1=(_f32(sd[lp + "self_attn_layer_norm.weight"], dev), _f32(sd[lp + "self_attn_layer_norm.bias"], dev)),
+                fc1=_Lin(_bf(sd[lp + "fc1.weight"], dev), _f32(sd[lp + "fc1.bias"], dev)),
+                fc2=_Lin(_bf(sd[lp + "fc2.weight"], dev), _f32(sd[lp + "fc2.bias"], dev)),
+                ln2=(_f32(sd[lp + "final_layer_norm.weight"], dev), _f32(sd[lp + "final_layer_norm.bias"], dev))))
+        self._beats_T_cache: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def _beats_tables(self, T: int):
+        """Per-sequence-length constants, built once: the (H,T,T) relative-position bias table
+        (backbone.py:392-430) and the Toeplitz-expanded pos-conv weights, one [T*cg, T*cg] matrix per conv group:
+        W[g][(t,co),(t',ci)] = w[g*cg+co, ci, t'-t+pad]  (zero outside the K taps)."""
+        if T in self._beats_T_cache:
+            return self._beats_T_cache[T]
+        c, dev = self.cfg.beats, self.dev
+        ctx = torch.arange(T, device=dev)[:, None]
+        mem = torch.arange(T, device=dev)[None, :]
+        rel = mem - ctx
+        nb = c.num_buckets // 2
+        buckets = (rel > 0).long() * nb
+        rel = rel.abs()
+        max_exact = nb // 2
+        large = max_exact + (torch.log(rel.float() / max_exact) / math.log(c.max_distance / max_exact)
+                             * (nb - max_exact)).long()
+        large = torch.minimum(large, torch.full_like(large, nb - 1))
+        buckets = buckets + torch.where(rel < max_exact, rel, large)
+        table = self.beats_rel[buckets].permute(2, 0, 1).contiguous()  # [H, T, T] fp32
+        G, K, pad = c.conv_groups, c.conv_pos, c.conv_pos // 2
+        cg = c.dim // G
+        w = self.beats_conv_w.view(G, cg, cg, K)  # [g, co, ci, k]
+        kidx = (torch.arange(T, device=dev)[None, :] - torch.arange(T, device=dev)[:, None]) + pad  # [t, t']
+        valid = (kidx >= 0) & (kidx < K)
+        wk = w[:, :, :, kidx.clamp(0, K - 1)] * valid  # [g, co, ci, t, t']
+        wexp = wk.permute(0, 3, 1, 4, 2).reshape(G, T * cg, T * cg).to(torch.bfloat16).contiguous()
+        self._beats_T_cache[T] = (table, wexp)
+        return table, wexp
+
+    # ---- bridges -----------------------------------------------------------------------------------------------
+    def _pack_bridges(self, sd: SD):
+        dev, q = self.dev, self.cfg.qformer
+        v, a = "model.vl_projector.", "model.al_projector."
+        self.visual_ln = (_f32(sd[v + "visual_ln.weight"], dev), _f32(sd[v + "visual_ln.bias"], dev))
+        self.audio_ln = (_f32(sd[a + "audio_ln.weight"], dev), _f32(sd[a + "audio_ln.bias"], dev))
+        self.vq = _QformerWeights(sd, v + "visual_Qformer.", q, dev)
+        self.aq = _QformerWeights(sd, a + "audio_Qformer.", q, dev)
+        self.v_query = _bf(sd[v + "visual_query_tokens"].reshape(-1, q.hidden), dev)
+        self.a_query = _bf(sd[a + "audio_query_tokens"].reshape(-1, q.hidden), dev)
+        self.v_proj = [_Lin(_bf(sd[v + f"visual_proj.{i}.weight"], dev), _f32(sd[v + f"visual_proj.{i}.bias"], dev)) for i in (0, 2)]
+        self.a_proj = [_Lin(_bf(sd[a + f"audio_proj.{i}.weight"], dev), _f32(sd[a + f"audio_proj.{i}.bias"], dev)) for i in (0, 2)]
+
+    # ==========================================================================================================
+    # forward pieces
+    # ==========================================================================================================
+    def clip_forward(self, pixels: torch.Tensor) -> torch.Tensor:
+        """pixels fp32 (n,3,H,W) on device -> hidden_states[select_layers[-1]] as bf16 [n*tokens, D] (CLS kept)."""
+        c = self.cfg.clip
+        n = pixels.shape[0]
+        g = pixels.shape[2] // c.patch
+        tokens = g * g + 1
+        D = c.hidden
+        patches = ops.patchify(pixels, c.patch, self.clip_kpad)
+        pe = ops.gemm(patches, self.clip_patch_w)
+        x = ops.clip_embed_ln(pe, self.clip_cls, self.clip_pos, *self.clip_pre_ln, n, tokens, D, c.eps)
+        M = n * tokens
+        h = self._buf("clip_h", (M, D))
+        qkv = self._buf("clip_qkv", (M, 3 * D))
+        o = self._buf("clip_o", (M, D))
+        m = self._buf("clip_m", (M, c.inter))
+        hd = D // c.heads
+        for L in self.clip_layers:
+            ops.layernorm(x, *L["ln1"], c.eps, out=h)
+            ops.gemm(h, L["qkv"].w, bias=L["qkv"].b, out=qkv)
+            ops.flash_attn(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B=n, H=c.heads, KVH=c.heads, Sq=tokens, Sk=tokens,
+                           head_dim=hd, q_strides=(tokens * 3 * D, 3 * D, hd), k_strides=(tokens * 3 * D, 3 * D, hd),
+                           v_strides=(tokens * 3 * D, 3 * D, hd), o_strides=(tokens * D, D, hd), scale=hd ** -0.5)
+            ops.gemm(o, L["out"].w, bias=L["out"].b, residual=x, out=x)
+            ops.layernorm(x, *L["ln2"], c.eps, out=h)
+            ops.gemm(h, L["fc1"].w, bias=L["fc1"].b, act=ops.ACT_QUICK_GELU, out=m)
+            ops.gemm(m, L["fc2"].w, bias=L["fc2"].b, residual=x, out=x)
+        return x
+
+    def _qformer(self, W: _QformerWeights, query: torch.Tensor, enc: torch.Tensor, n: int, enc_tokens: int,
+                 enc_row0: int, enc_rows_per_item: int) -> torch.Tensor:
+        """Q-Former over n items.  `enc` is a bf16 [n*enc_rows_per_item, width] matrix (already layer-normed);
+        each item's keys are rows [enc_row0, enc_row0+enc_tokens) of its block."""
+        q = self.cfg.qformer
+        Dq, nq, hd = q.hidden, query.shape[0], q.hidden // q.heads
+        x0 = ops.layernorm(query, *W.emb_ln, q.eps)  # identical for every item: computed once, then broadcast
+        rows = torch.arange(nq, device=self.dev).repeat(n)
+        x = torch.empty((n * nq, Dq), device=self.dev, dtype=torch.bfloat16)
+        ops.gather_rows(x0, x, n * nq, Dq, src_rows=rows)
+        width = enc.shape[1]
+        for L in W.layers:
+            qkv = ops.gemm(x, L["self_qkv"].w, bias=L["self_qkv"].b)
+            o = torch.empty((n * nq, Dq), device=self.dev, dtype=torch.bfloat16)
+            ops.flash_attn(qkv, qkv[:, Dq:], qkv[:, 2 * Dq:], o, B=n, H=q.heads, KVH=q.heads, Sq=nq, Sk=nq, head_dim=hd,
+                           q_strides=(nq * 3 * Dq, 3 * Dq, hd), k_strides=(nq * 3 * Dq, 3 * Dq, hd),
+                           v_strides=(nq * 3 * Dq, 3 * Dq, hd), o_strides=(nq * Dq, Dq, hd), scale=1 / math.sqrt(hd))
+            y = ops.gemm(o, L["self_out"].w, bias=L["self_out"].b, residual=x)
+            x = ops.layernorm(y, *L["self_ln"], q.eps)
+            qc = ops.gemm(x, L["cross_q"].w, bias=L["cross_q"].b)
+            kv = ops.gemm(enc, L["cross_kv"].w, bias=L["cross_kv"].b)  # [n*rows_per_item, 2*Dq]
+            kv0 = kv[enc_row0:]
+            ops.flash_attn(qc, kv0, kv0[:, Dq:], o, B=n, H=q.heads, KVH=q.heads, Sq=nq, Sk=enc_tokens, head_dim=hd,
+                           q_strides=(nq * Dq, Dq, hd), k_strides=(enc_rows_per_item * 2 * Dq, 2 * Dq, hd),
+                           v_strides=(enc_rows_per_item * 2 * Dq, 2 * Dq, hd), o_strides=(nq * Dq, Dq, hd),
+                           scale=1 / math.sqrt(hd))
+            y = ops.gemm(o, L["cross_out"].w, bias=L["cross_out"].b, residual=x)
+            x = ops.layernorm(y, *L["cross_ln"], q.eps)
+            hmid = ops.gemm(x, L["ffn_in"].w, bias=L["ffn_in"].b, act=ops.ACT_GELU)
+            y = ops.gemm(hmid, L["ffn_out"].w, bias=L["ffn_out"].b, residual=x)
+            x = ops.layernorm(y, *L["ffn_ln"], q.eps)
+        return x
+
+    def encode_video(self, pixels: torch.Tensor) -> torch.Tensor:
+        """pixels fp32 (n_frames_total,3,H,W) -> bf16 [n_frames_total*32, d_model]  (VisualEncoder last tap ->
+        VLProjector; models/unified_arch.py:144-149, models/multimodal_encoder.py:119-144)."""
+        c = self.cfg.clip
+        n = pixels.shape[0]
+        tokens = (pixels.shape[2] // c.patch) ** 2 + 1
+        x = self.clip_forward(pixels)
+        f = ops.layernorm(x, *self.visual_ln, 1e-5)  # CLS rows are normalised too but never read
+        qo = self._qformer(self.vq, self.v_query, f, n, tokens - 1, 1, tokens)
+        h = ops.gemm(qo, self.v_proj[0].w, bias=self.v_proj[0].b, act=ops.ACT_GELU)
+        return ops.gemm(h, self.v_proj[1].w, bias=self.v_proj[1].b)
+
+    def beats_forward(self, fbank: torch.Tensor) -> Tuple[torch.Tensor, int]:
+        """fbank fp32 (n, L, 128) -> (bf16 [n*T, 768], T)   (models/beats/BEATs.py:134-182, backbone.py:109-273)."""
+        c = self.cfg.beats
+        n, Lf, nm = fbank.shape
+        T = (Lf // c.patch) * (nm // c.patch)
+        Dm, Hh = c.dim, c.heads
+        hd = Dm // Hh
+        patches = ops.patchify(fbank.reshape(n, 1, Lf, nm).contiguous(), c.patch, c.patch * c.patch)
+        pe = ops.gemm(patches, self.beats_patch_w)
+        pe = ops.layernorm(pe, *self.beats_ln0, c.eps)
+        x = ops.gemm(pe, self.beats_proj.w, bias=self.beats_proj.b)  # [n*T, 768]
+        table, wexp = self._beats_tables(T)
+        G = c.conv_groups
+        xg = ops.beats_group_pack(x, n, T, Dm, G)
+        yg = torch.empty_like(xg)
+        for g in range(G):
+            ops.gemm(xg[g], wexp[g], out=yg[g])
+        y = ops.beats_posconv_finish(x, yg, self.beats_conv_b, n, T, Dm, G)
+        x = ops.layernorm(y, *self.beats_enc_ln, c.eps)
+        M = n * T
+        o = torch.empty((M, Dm), device=self.dev, dtype=torch.bfloat16)
+        for L in self.beats_layers:
+            qkv = ops.gemm(x, L["qkv"].w, bias=L["qkv"].b)
+            gate = ops.beats_gate(qkv, L["grep_w"], L["grep_b"], L["grep_a"], n, T, Hh)
+            ops.flash_attn(qkv, qkv[:, Dm:], qkv[:, 2 * Dm:], o, B=n, H=Hh, KVH=Hh, Sq=T, Sk=T, head_dim=hd,
+                           q_strides=(T * 3 * Dm, 3 * Dm, hd), k_strides=(T * 3 * Dm, 3 * Dm, hd),
+                           v_strides=(T * 3 * Dm, 3 * Dm, hd), o_strides=(T * Dm, Dm, hd), scale=hd ** -0.5, gate=gate,
+                           bias_table=table)
+            y = ops.gemm(o, L["out"].w, bias=L["out"].b, residual=x, res_scale=self.beats_alpha)
+            x = ops.layernorm(y, *L["ln1"], c.eps)
+            hmid = ops.gemm(x, L["fc1"].w, bias=L["fc1"].b, act=ops.ACT_GELU)
+            y = ops.gemm(hmid, L["fc2"].w, bias=L["fc2"].b, residual=x, res_scale=self.beats_alpha)
+            x = ops.layernorm(y, *L["ln2"], c.eps)
+        return x, T
+
+    def encode_audio(self, fbank: torch.Tensor) -> torch.Tensor:
+        """fbank fp32 (n_segments_total, L, 128) -> bf16 [n_segments_total*32, d_model]
+        (AudioEncoder -> ALProjector; models/unified_arch.py:152-155, models/multimodal_encoder.py:226-244)."""
+        x, T = self.beats_forward(fbank)
+        n = fbank.shape[0]
+        f = ops.layernorm(x, *self.audio_ln, 1e-5)
+        qo = self._qformer(self.aq, self.a_query, f, n, T, 0, T)
+        h = ops.gemm(qo, self.a_proj[0].w, bias=self.a_proj[0].b, act=ops.ACT_GELU)
+        return ops.gemm(h, self.a_proj[1].w, bias=self.a_proj[1].b)
+
+    # ---- prepare_multimodal_inputs -----------------------------------------------------------------------------
+    def prepare_inputs(self, batch_input_ids: Sequence[torch.Tensor], batch_X_modals: Sequence[dict]):
+        """Splice modality embeddings at the placeholder ids, left-pad with pad-token embeddings
+        (models/unified_arch.py:262-373).  The index bookkeeping runs on the host over the (host) token ids; the data
+        movement is two gathers on the device.  Encoders run batched across samples (the reference runs them one
+        sample at a time).  Returns (inputs_embeds bf16 [B,S,D], attention_mask int32 [B,S], position_ids [B,S])."""
+        ids = self.cfg.special_ids
+        key_of = {ids["<image>"]: "<image>", ids["<video>"]: "<video>", ids["<audio>"]: "<audio>"}
+        nq = self.cfg.n_query
+        D = self.cfg.decoder.hidden
+        B = len(batch_input_ids)
+        vis_items, aud_items = [], []  # tensors to encode, in order
+        plans = []  # per sample: list of ("text", ids) | ("vis", item_idx, n_rows) | ("aud", item_idx, n_rows)
+        for b in range(B):
+            t = batch_input_ids[b].detach().cpu()
+            tl = t.tolist()
+            plan, pre = [], 0
+            for i, tok in enumerate(tl):
+                if tok in key_of:
+                    plan.append(("text", t[pre:i]))
+                    key = key_of[tok]
+                    X = batch_X_modals[b][key]
+                    if key == "<audio>":
+                        X = X if X.dim() == 3 else X.unsqueeze(0)
+                        plan.append(("aud", len(aud_items), X.shape[0] * nq))
+                        aud_items.append(X)
+                    else:
+                        plan.append(("vis", len(vis_items), X.shape[0] * nq))
+                        vis_items.append(X)
+                    pre = i + 1
+            plan.append(("text", t[pre:]))
+            plans.append(plan)
+        lens = [sum((len(p[1]) if p[0] == "text" else p[2]) for p in plan) for plan in plans]
+        S = max(lens)
+        # encoders, batched by input shape
+        vis_out = self._encode_grouped(vis_items, self.encode_video)
+        aud_out = self._encode_grouped(aud_items, self.encode_audio)
+        embeds = torch.empty((B * S, D), device=self.dev, dtype=torch.bfloat16)
+        txt_src, txt_dst = [], []
+        mask = torch.zeros((B, S), dtype=torch.int32)
+        for b, plan in enumerate(plans):
+            padn = S - lens[b]
+            txt_src.append(torch.full((padn,), self.cfg.pad_token_id, dtype=torch.long))
+            txt_dst.append(torch.arange(b * S, b * S + padn))
+            mask[b, padn:] = 1
+            pos = b * S + padn
+            for p in plan:
+                if p[0] == "text":
+                    txt_src.append(p[1].long())
+                    txt_dst.append(torch.arange(pos, pos + len(p[1])))
+                    pos += len(p[1])
+                else:
+                    src = (vis_out if p[0] == "vis" else aud_out)[p[1]]
+                    dst_rows = torch.arange(pos, pos + p[2], device=self.dev)
+                    ops.gather_rows(src, embeds, p[2], D, dst_rows=dst_rows)
+                    pos += p[2]
+        src = torch.cat(txt_src).to(self.dev, non_blocking=True)
+        dst = torch.cat(txt_dst).to(self.dev, non_blocking=True)
+        if src.numel():
+            ops.gather_rows(self.embed, embeds, src.numel(), D, src_rows=src, dst_rows=dst)
+        position_ids = torch.cumsum(mask, dim=-1) - 1
+        position_ids[position_ids == -1] = 0
+        return embeds.view(B, S, D), mask, position_ids
+
+    def _encode_grouped(self, items: List[torch.Tensor], fn) -> List[torch.Tensor]:
+        out: List[Optional[torch.Tensor]] = [None] * len(items)
+        groups: Dict[Tuple, List[int]] = {}
+        for i, x in enumerate(items):
+            groups.setdefault(tuple(x.shape[1:]), []).append(i)
+        nq = self.cfg.n_query
+        for shape, idxs in groups.items():
+            xs = torch.cat([items[i].to(self.dev, dtype=torch.float32, non_blocking=True) for i in idxs], 0).contiguous()
+            y = fn(xs)
+            r = 0
+            for i in idxs:
+                nrows = items[i].shape[0] * nq
+                out[i] = y[r:r + nrows]
+                r += nrows
+        return out  # type: ignore
+
+    # ---- decoder -----------------------------------------------------------------------------------------------
+    def _alloc_cache(self, B: int):
+        c = self.cfg.decoder
+        if self.k_cache and self.k_cache[0].shape[0] == B:
+            return
+        self.k_cache = [torch.zeros((B, c.kv_heads, self.cfg.max_ctx, c.head_dim), device=self.dev, dtype=torch.bfloat16)
+                        for _ in range(c.layers)]
+        self.v_cache = [torch.zeros_like(k) for k in self.k_cache]
+        self._graph = None
+
+    def _decoder_layers(self, x: torch.Tensor, B: int, S: int, past: int, past_dev=None, len_dev=None, nsplit=1,
+                        ws=None, tag="pf"):
+        """x bf16 [B*S, D], updated in place through all layers.  S > 1: prefill (flash attention over the cache);
+        S == 1 with past_dev/len_dev: one decode step."""
+        c = self.cfg.decoder
+        D, F, H, KV, hd = c.hidden, c.inter, c.heads, c.kv_heads, c.head_dim
+        M = B * S
+        nq, nk = H * hd, KV * hd
+        xn = self._buf(tag + "_xn", (M, D + self.EXT_QKV), zero=True)
+        qkv = self._buf(tag + "_qkv", (M, nq + 2 * nk))
+        at = self._buf(tag + "_attn", (M, nq + self.EXT_O), zero=True)
+        hh = self._buf(tag + "_h", (M, F + self.EXT_D), zero=True)
+        ctx = self.cfg.max_ctx
+        for li, L in enumerate(self.layers):
+            ops.rmsnorm(x, L["ln1"], c.eps, out=xn[:, :D])
+            if self.lora:
+                ops.gemm(xn[:, :D], L["ra_qkv"], act=ops.ACT_LORA_Z, out_scale=self.scaling, out=xn[:, D:D + 72])
+            ops.gemm(xn, L["wqkv"], bias=L["bqkv"], out=qkv, k=D + (self.EXT_QKV if self.lora else 0))
+            ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, S, H, KV, hd, past=past, past_dev=past_dev)
+            if S == 1 and len_dev is not None:
+                ops.attn_decode(qkv, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV, head_dim=hd,
+                                scale=1 / math.sqrt(hd), len_dev=len_dev, nsplit=nsplit, workspace=ws)
+            else:
+                ops.flash_attn(qkv, self.k_cache[li], self.v_cache[li], at, B=B, H=H, KVH=KV, Sq=S, Sk=past + S, head_dim=hd,
+                               q_strides=(S * (nq + 2 * nk), nq + 2 * nk, hd), k_strides=(KV * ctx * hd, hd, ctx * hd),
+                               v_strides=(KV * ctx * hd, hd, ctx * hd), o_strides=(S * (nq + self.EXT_O), nq + self.EXT_O, hd),
+                               scale=1 / math.sqrt(hd), causal=True)
+            if self.lora:
+                ops.gemm(at[:, :nq], L["ra_o"], act=ops.ACT_LORA_Z, out_scale=self.scaling, out=at[:, nq:nq + 24])
+            ops.gemm(at, L["wo"], residual=x, out=x, k=nq + (self.EXT_O if self.lora else 0))
+            ops.rmsnorm(x, L["ln2"], c.eps, out=xn[:, :D])
+            if self.lora:
+                ops.gemm(xn[:, :D], L["ra_gu"], act=ops.ACT_LORA_Z, out_scale=self.scaling, out=xn[:, D:D + 48])
+            ops.gemm(xn, L["wgu"], act=ops.ACT_SWIGLU, out=hh[:, :F], k=D + (self.EXT_GU if self.lora else 0))
+            if self.lora:
+                ops.gemm(hh[:, :F], L["ra_d"], act=ops.ACT_LORA_Z, out_scale=self.scaling, out=hh[:, F:F + 24])
+            ops.gemm(hh, L["wd"], residual=x, out=x, k=F + (self.EXT_D if self.lora else 0))
+        return x
+
+    def _head(self, x_last: torch.Tensor, logits: torch.Tensor, next_ids: torch.Tensor):
+        """final RMSNorm -> lm_head (fp32 logits) -> greedy arg-max."""
+        c = self.cfg.decoder
+        hn = ops.rmsnorm(x_last, self.final_norm, c.eps, out=self._buf("head_hn", tuple(x_last.shape)))
+        ops.gemm(hn, self.lm_head, out=logits)
+        ops.argmax(logits, self.vocab, out=next_ids)
+
+    def prefill(self, inputs_embeds: torch.Tensor):
+        """inputs_embeds bf16 [B,S,D] (consumed in place) -> (last-position logits fp32 [B, vocab], next ids [B])."""
+        B, S, D = inputs_embeds.shape
+        assert S < self.cfg.max_ctx
+        self._alloc_cache(B)
+        if inputs_embeds.dtype != torch.bfloat16 or not inputs_embeds.is_cuda or not inputs_embeds.is_contiguous():
+            inputs_embeds = inputs_embeds.to(device=self.dev, dtype=torch.bfloat16).contiguous()
+        x = inputs_embeds.view(B * S, D)
+        self._decoder_layers(x, B, S, past=0)
+        self.cur_len = S
+        last = self._buf("last_x", (B, D))
+        rows = (torch.arange(B, device=self.dev) * S + (S - 1))
+        ops.gather_rows(x, last, B, D, src_rows=rows)
+        self.logits = self._buf("logits", (B, self.vocab_pad), torch.float32)
+        self.next_ids = self._buf("next_ids", (B,), torch.int64)
+        self._head(last, self.logits, self.next_ids)
+        return self.logits[:, : self.vocab], self.next_ids
+
+    # ---- decode ------------------------------------------------------------------------------------------------
+    def _decode_body(self, B: int, nsplit: int, ws):
+        D = self.cfg.decoder.hidden
+        x = self._buf("dec_x", (B, D))
+        ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)  # embed_tokens of the previous arg-max
+        self._decoder_layers(x, B, 1, past=0, past_dev=self.past_dev, len_dev=self.len_dev, nsplit=nsplit, ws=ws, tag="dec")
+        self._head(x, self.logits, self.next_ids)
+        ops.add_scalar_i32(self.past_dev, 1)
+        ops.add_scalar_i32(self.len_dev, 1)
+
+    def begin_decode(self, B: int, use_graph: bool = True):
+        """Capture one decode step (all layers + head + arg-max + position bump) in a CUDA graph; the context length
+        lives in device memory so the same graph is replayed every step."""
+        c = self.cfg.decoder
+        self.past_dev = torch.tensor([self.cur_len], dtype=torch.int32, device=self.dev)
+        self.len_dev = torch.tensor([self.cur_len + 1], dtype=torch.int32, device=self.dev)
+        blocks = B * c.kv_heads
+        nsplit = 1 if blocks >= 2 * 148 else max(1, min(16, (2 * 148 + blocks - 1) // blocks))
+        ws = self._buf("dec_ws", (B * c.heads * nsplit * (c.head_dim + 2),), torch.float32) if nsplit > 1 else None
+        self._dec_args = (B, nsplit, ws)
+        self._graph = None
+        if use_graph:
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream())
+            saved = (self.next_ids.clone(), self.past_dev.clone(), self.len_dev.clone())
+            with torch.cuda.stream(s):
+                self._decode_body(*self._dec_args)  # warm-up outside capture (lazy kernel attribute setup)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.next_ids.copy_(saved[0]); self.past_dev.copy_(saved[1]); self.len_dev.copy_(saved[2])
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                self._decode_body(*self._dec_args)
+            self._graph_kernels = ops.launch_count() - n0
+            self.next_ids.copy_(saved[0]); self.past_dev.copy_(saved[1]); self.len_dev.copy_(saved[2])
+            self._graph = g
+
+    def decode_step(self):
+        """One greedy step: consumes self.next_ids, leaves the new arg-max there and fp32 logits in self.logits."""
+        if self._graph is not None:
+            self._graph.replay()
+            ops.count_launches(self._graph_kernels)
+        else:
+            self._decode_body(*self._dec_args)
+        self.cur_len += 1
+        return self.logits[:, : self.vocab], self.next_ids
+
+    @torch.no_grad()
+    def generate_from_embeds(self, inputs_embeds: torch.Tensor, max_new_tokens: int, use_graph: bool = True,
+                             return_logits: bool = False, teacher_tokens: Optional[torch.Tensor] = None):
+        """Greedy loop (EOS handling is the caller's: fixed-length).  Returns ids [B, n] (int64, device)."""
+        B = inputs_embeds.shape[0]
+        assert inputs_embeds.shape[1] + max_new_tokens <= self.cfg.max_ctx, "raise CrabConfig.max_ctx"
+        logits, nxt = self.prefill(inputs_embeds)
+        out = torch.empty((B, max_new_tokens), device=self.dev, dtype=torch.int64)
+        out[:, 0].copy_(nxt)
+        all_logits = [logits.clone()] if return_logits else None
+        if max_new_tokens > 1:
+            self.begin_decode(B, use_graph)
+        for step in range(1, max_new_tokens):
+            if teacher_tokens is not None:
+                self.next_ids.copy_(teacher_tokens[:, step - 1])
+            logits, nxt = self.decode_step()
+            out[:, step].copy_(nxt)
+            if return_logits:
+                all_logits.append(logits.clone())
+        return (out, torch.stack(all_logits, 0)) if return_logits else out
+
+    @torch.no_grad()
+    def generate(self, batch_input_ids, batch_X_modals, max_new_tokens: int, use_graph: bool = True):
+        embeds, _, _ = self.prepare_inputs(batch_input_ids, batch_X_modals)
+        return self.generate_from_embeds(embeds, max_new_tokens, use_graph)

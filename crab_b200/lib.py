@@ -59,3 +59,16 @@ def exported_symbols() -> list[str]:
     hdr = (Path(__file__).resolve().parent.parent / "include" / "crab_b200.h").read_text()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     return sorted(set(re.findall(r"\b(crab_[a-z0-9_]+)\s*\(", hdr)))
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+        ("q_bs", C.c_int64), ("q_rs", C.c_int64), ("q_hs", C.c_int64),
+        ("k_bs", C.c_int64), ("k_rs", C.c_int64), ("k_hs", C.c_int64),
+        ("v_bs", C.c_int64), ("v_rs", C.c_int64), ("v_hs", C.c_int64),
+        ("o_bs", C.c_int64), ("o_rs", C.c_int64), ("o_hs", C.c_int64),
+        ("B", C.c_int32), ("H", C.c_int32), ("KVH", C.c_int32), ("Sq", C.c_int32), ("Sk", C.c_int32),
+        ("head_dim", C.c_int32), ("scale", C.c_float), ("causal", C.c_int32),
+        ("gate", C.c_void_p), ("bias_table", C.c_void_p),
+    ]

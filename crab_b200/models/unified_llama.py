@@ -1,0 +1,271 @@
+"""Mirror of the reference's `models/unified_llama.py` (UnifiedConfig / UnifiedModel / UnifiedForCausalLM over
+LLaMA), backed by `crab_b200.engine.CrabEngine`.
+
+What is kept: class names, `from_pretrained(path, config=, torch_dtype=)`, `get_model()`, `forward(...)`,
+`generate(batch_input_ids, batch_labels, batch_X_modals, batch_task_names, **kw)`, `prepare_inputs_for_generation`,
+`.npu()`, `.device`, the state-dict key names (`model.layers.N.self_attn.q_proj.weight` …) and real `nn.Linear` leaves
+named q/k/v/o/gate/up/down_proj so `peft_hyper.get_peft_model` (scripts/quick_start.py:475-493) can wrap them with
+its hyper-LoRA `Linear` (peft_hyper/tuners/lora.py:118-159).  What is replaced: all arithmetic.  The modules hold
+parameters only; on first use (or after the weights change) they are packed into the engine's bf16 device buffers.
+
+Reference: models/unified_llama.py:11-40 (classes), :47-161 (forward), :244-267 (generate), :365-382
+(prepare_inputs_for_generation), :385-387 (device).
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+from types import SimpleNamespace
+from typing import List, Optional
+
+import torch
+from torch import nn
+from transformers import LlamaConfig
+
+from ..engine import CrabEngine, DecoderConfig
+from .unified_arch import UnifiedMetaForCausalLM, UnifiedMetaModel, build_crab_config
+
+
+class UnifiedConfig(LlamaConfig):
+    model_type = "unified_llm"
+
+
+class _NormWeight(nn.Module):
+    def __init__(self, dim: int, dtype):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim, dtype=dtype), requires_grad=False)
+
+
+class _Attn(nn.Module):
+    def __init__(self, c, dtype, bias: bool):
+        super().__init__()
+        hd = getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads
+        kv = getattr(c, "num_key_value_heads", None) or c.num_attention_heads
+        self.q_proj = nn.Linear(c.hidden_size, c.num_attention_heads * hd, bias=bias, dtype=dtype)
+        self.k_proj = nn.Linear(c.hidden_size, kv * hd, bias=bias, dtype=dtype)
+        self.v_proj = nn.Linear(c.hidden_size, kv * hd, bias=bias, dtype=dtype)
+        self.o_proj = nn.Linear(c.num_attention_heads * hd, c.hidden_size, bias=False, dtype=dtype)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, c, dtype):
+        super().__init__()
+        self.gate_proj = nn.Linear(c.hidden_size, c.intermediate_size, bias=False, dtype=dtype)
+        self.up_proj = nn.Linear(c.hidden_size, c.intermediate_size, bias=False, dtype=dtype)
+        self.down_proj = nn.Linear(c.intermediate_size, c.hidden_size, bias=False, dtype=dtype)
+
+
+class _Layer(nn.Module):
+    def __init__(self, c, dtype, qkv_bias):
+        super().__init__()
+        self.self_attn = _Attn(c, dtype, qkv_bias)
+        self.mlp = _Mlp(c, dtype)
+        self.input_layernorm = _NormWeight(c.hidden_size, dtype)
+        self.post_attention_layernorm = _NormWeight(c.hidden_size, dtype)
+
+
+class UnifiedModel(UnifiedMetaModel, nn.Module):
+    """Decoder parameter container (`model.*` keys of the reference checkpoints)."""
+
+    config_class = UnifiedConfig
+    qkv_bias = False
+
+    def __init__(self, config, dtype=torch.float32):
+        nn.Module.__init__(self)
+        self.config = config
+        self.embed_tokens = nn.Embedding(config.vocab_size, config.hidden_size, dtype=dtype)
+        self.layers = nn.ModuleList([_Layer(config, dtype, self.qkv_bias) for _ in range(config.num_hidden_layers)])
+        self.norm = _NormWeight(config.hidden_size, dtype)
+        self.pad_token_id = getattr(config, "pad_token_id", None) or 0
+        self._owner = None
+
+    def _engine_stale(self):
+        if self._owner is not None:
+            self._owner()._engine = None
+
+
+class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
+    config_class = UnifiedConfig
+    _model_cls = UnifiedModel
+
+    def __init__(self, config, torch_dtype=None, max_ctx: int = 2048, **kwargs):
+        nn.Module.__init__(self)
+        dtype = torch_dtype or torch.float32
+        with torch.device("cpu"):
+            self.model = self._model_cls(config, dtype)
+            self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False, dtype=dtype)
+        import weakref
+
+        self.model._owner = weakref.ref(self)
+        self.config = config
+        self.vocab_size = config.vocab_size
+        self.pretraining_tp = getattr(config, "pretraining_tp", 1)
+        self.max_ctx = max_ctx
+        self.is_avs_task = False
+        self._engine: Optional[CrabEngine] = None
+        self._target = torch.device("cpu")
+        self.generation_config = SimpleNamespace(max_new_tokens=20)
+
+    # ---- construction / weights --------------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, config=None, torch_dtype=None, **kwargs):
+        """Build the container and load an HF LLaMA/Qwen2 checkpoint directory (safetensors or .bin shards)."""
+        if config is None:
+            config = cls.config_class.from_pretrained(pretrained_model_name_or_path)
+        model = cls(config, torch_dtype=torch_dtype, **{k: v for k, v in kwargs.items() if k == "max_ctx"})
+        files = sorted(glob.glob(os.path.join(str(pretrained_model_name_or_path), "*.safetensors")))
+        sd = {}
+        if files:
+            from safetensors.torch import load_file
+
+            for f in files:
+                sd.update(load_file(f))
+        else:
+            for f in sorted(glob.glob(os.path.join(str(pretrained_model_name_or_path), "pytorch_model*.bin"))):
+                sd.update(torch.load(f, map_location="cpu"))
+        if sd:
+            model.load_state_dict(sd, strict=False)
+        return model
+
+    def get_model(self):
+        return self.model
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def resize_token_embeddings(self, new_num_tokens: int):
+        """Grow embed_tokens / lm_head (new rows: mean of the old ones — initialisation is irrelevant for inference
+        because the fine-tuned checkpoint overwrites them, scripts/quick_start.py:537-554)."""
+        old_e, old_h = self.model.embed_tokens.weight.data, self.lm_head.weight.data
+        if new_num_tokens == old_e.shape[0]:
+            return self.model.embed_tokens
+        n = min(old_e.shape[0], new_num_tokens)
+        e = nn.Embedding(new_num_tokens, old_e.shape[1], dtype=old_e.dtype)
+        h = nn.Linear(old_h.shape[1], new_num_tokens, bias=False, dtype=old_h.dtype)
+        with torch.no_grad():
+            e.weight[:] = old_e.float().mean(0).to(old_e.dtype)
+            h.weight[:] = old_h.float().mean(0).to(old_h.dtype)
+            e.weight[:n] = old_e[:n]
+            h.weight[:n] = old_h[:n]
+        self.model.embed_tokens, self.lm_head = e, h
+        self.config.vocab_size = self.vocab_size = new_num_tokens
+        self._engine = None
+        return e
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        sd = {(k[len("base_model.model."):] if k.startswith("base_model.model.") else k): v for k, v in state_dict.items()}
+        self._engine = None
+        return nn.Module.load_state_dict(self, sd, strict=strict)
+
+    # ---- device handling: parameters stay on the host as the load-time copy; the engine owns device memory ------
+    def cuda(self, device=None):
+        self._target = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                    (device if isinstance(device, int) else torch.device(device).index or 0))
+        return self
+
+    def npu(self, device=None):  # scripts/quick_start.py:558 (the reference was developed on Ascend)
+        return self.cuda(device)
+
+    def to(self, *args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, (str, torch.device)) and torch.device(a).type == "cuda":
+                return self.cuda(torch.device(a).index)
+        return nn.Module.to(self, *args, **kwargs)
+
+    @property
+    def device(self):
+        # a wrapper's nn.Module.cuda() moves the parameters without calling our .cuda(): follow them
+        if self._target.type != "cuda" and self.lm_head.weight.is_cuda:
+            self._target = self.lm_head.weight.device
+        return self._target
+
+    @property
+    def dtype(self):
+        return torch.bfloat16
+
+    def decoder_config(self) -> DecoderConfig:
+        c = self.config
+        hd = getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads
+        return DecoderConfig(hidden=c.hidden_size, inter=c.intermediate_size, layers=c.num_hidden_layers,
+                             heads=c.num_attention_heads, kv_heads=getattr(c, "num_key_value_heads", None) or c.num_attention_heads,
+                             head_dim=hd, vocab=self.lm_head.weight.shape[0],
+                             rope_theta=float(getattr(c, "rope_theta", None) or (getattr(c, "rope_parameters", None) or {}).get("rope_theta", 10000.0)),
+                             eps=c.rms_norm_eps, qkv_bias=self.model.qkv_bias)
+
+    def engine(self) -> CrabEngine:
+        if self._engine is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("call .cuda() / .npu() first: crab_b200 has no CPU execution path")
+            # state_dict() of this container includes any hyper-LoRA tensors peft_hyper attached to the linears
+            self._engine = CrabEngine(self.state_dict(), build_crab_config(self.decoder_config(), self, self.max_ctx),
+                                      self._target)
+        return self._engine
+
+    # ---- forward / generate -------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, batch_input_ids=None, batch_labels=None, batch_X_modals=None, batch_task_names=None,
+                input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
+                **kwargs):
+        """Inference forward: returns an object with `.logits` for the LAST position, fp32 (b, 1, vocab).
+        `inputs_embeds` / `batch_*` start a new sequence (prefill); a (b,1) `input_ids` continues it (decode step,
+        models/unified_llama.py:125-127).  Training (loss/backward) is out of scope."""
+        eng = self.engine()
+        if input_ids is not None and input_ids.shape[1] == 1 and getattr(eng, "cur_len", 0) > 0:
+            if eng._graph is None and not hasattr(eng, "_dec_args"):
+                eng.begin_decode(input_ids.shape[0], use_graph=False)
+            eng.next_ids.copy_(input_ids[:, 0].to(eng.dev))
+            logits, _ = eng.decode_step()
+        else:
+            if inputs_embeds is None and batch_input_ids is not None:
+                inputs_embeds = self.prepare_multimodal_inputs(batch_input_ids, None, batch_X_modals, batch_task_names)["inputs_embeds"]
+            elif inputs_embeds is None and input_ids is not None:
+                b, s = input_ids.shape
+                inputs_embeds = self.encode_ids(input_ids).view(b, s, -1)
+            if hasattr(eng, "_dec_args"):
+                del eng._dec_args
+            logits, _ = eng.prefill(inputs_embeds.clone())
+        return SimpleNamespace(logits=logits.unsqueeze(1).clone(), past_key_values=True, loss=None)
+
+    @torch.no_grad()
+    def generate(self, batch_input_ids=None, batch_labels=None, batch_X_modals=None, batch_task_names=None, *,
+                 inputs_embeds=None, max_new_tokens: Optional[int] = None, eos_token_id=None, do_sample=False, **kwargs):
+        """Greedy generation; returns only the new ids (b, <= max_new_tokens), like HF generate with inputs_embeds.
+        Rows that hit `eos_token_id` are padded with pad_token_id afterwards (HF semantics); decoding stops early when
+        every row has finished."""
+        if do_sample:
+            raise NotImplementedError("the B200 path implements greedy decoding (the quick-start default)")
+        eng = self.engine()
+        if inputs_embeds is None:
+            inputs_embeds, _, _ = eng.prepare_inputs(batch_input_ids, batch_X_modals)
+        n = max_new_tokens or self.generation_config.max_new_tokens
+        if eos_token_id is None:
+            return eng.generate_from_embeds(inputs_embeds, n)
+        eos = torch.as_tensor(eos_token_id if isinstance(eos_token_id, (list, tuple)) else [eos_token_id], device=eng.dev)
+        B = inputs_embeds.shape[0]
+        _, nxt = eng.prefill(inputs_embeds)
+        out = torch.full((B, n), int(self.model.pad_token_id or 0), device=eng.dev, dtype=torch.int64)
+        done = torch.zeros(B, dtype=torch.bool, device=eng.dev)
+        if n > 1:
+            eng.begin_decode(B)
+        steps = 0
+        for step in range(n):
+            tok = torch.where(done, torch.full_like(nxt, int(self.model.pad_token_id or 0)), nxt)
+            out[:, step] = tok
+            done |= torch.isin(tok, eos)
+            steps = step + 1
+            if step % 8 == 7 and bool(done.all()):  # one host sync every 8 tokens instead of every token
+                break
+            if step + 1 < n:
+                _, nxt = eng.decode_step()
+        return out[:, :steps]
+
+    def generate_avs(self, *a, **k):
+        raise NotImplementedError("generate_avs / SegModule are out of scope for the B200 path (SURVEY.md §8f)")
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
+        """Kept for peft_hyper.PeftModelForCausalLM, which wraps this attribute (peft_model.py:518-520)."""
+        if past_key_values is not None:
+            return {"input_ids": input_ids[:, -1:], "past_key_values": past_key_values, **kwargs}
+        return {"input_ids": None if inputs_embeds is not None else input_ids, "inputs_embeds": inputs_embeds, **kwargs}

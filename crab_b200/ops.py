@@ -11,6 +11,19 @@ import torch
 
 from . import lib as _l
 
+_launches = 0
+
+
+def launch_count() -> int:
+    """Number of crab_b200 CUDA kernels launched (or replayed from a captured graph) so far in this process."""
+    return _launches
+
+
+def count_launches(n: int) -> None:
+    global _launches
+    _launches += n
+
+
 ACT_NONE, ACT_QUICK_GELU, ACT_GELU, ACT_SWIGLU, ACT_LORA_Z = 0, 1, 2, 3, 4
 BF16, F32 = 0, 1
 
@@ -66,4 +79,179 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         out_dtype=(BF16 if out.dtype == torch.bfloat16 else F32), block_n=block_n, max_ctas=max_ctas,
     )
     _l.check(_l.load().crab_gemm_bf16(C.byref(args), _stream()), "crab_gemm_bf16")
+    count_launches(1)
     return out
+
+
+def _i(v):
+    return C.c_int(int(v))
+
+
+def _vp(t):
+    return C.c_void_p(None if t is None else t.data_ptr())
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Row-wise LayerNorm of a 2-D bf16 view (row stride free); gamma/beta fp32."""
+    _req_cuda(x, gamma, beta, out)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16 and gamma.dtype == torch.float32
+    if out is None:
+        out = torch.empty((x.shape[0], x.shape[1]), device=x.device, dtype=torch.bfloat16)
+    _l.check(_l.load().crab_layernorm(_vp(x), _i(x.stride(0)), _vp(gamma), _vp(beta), _vp(out), _i(out.stride(0)),
+                                      _i(x.shape[0]), _i(x.shape[1]), C.c_float(eps), _stream()), "crab_layernorm")
+    count_launches(1)
+    return out
+
+
+def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_cuda(x, gamma, out)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16 and gamma.dtype == torch.float32
+    if out is None:
+        out = torch.empty((x.shape[0], x.shape[1]), device=x.device, dtype=torch.bfloat16)
+    _l.check(_l.load().crab_rmsnorm(_vp(x), _i(x.stride(0)), _vp(gamma), _vp(out), _i(out.stride(0)), _i(x.shape[0]),
+                                    _i(x.shape[1]), C.c_float(eps), _stream()), "crab_rmsnorm")
+    count_launches(1)
+    return out
+
+
+def rope_table(max_pos: int, head_dim: int, theta: float, device) -> torch.Tensor:
+    t = torch.empty((max_pos, head_dim), device=device, dtype=torch.float32)
+    _l.check(_l.load().crab_rope_table(_vp(t), _i(max_pos), _i(head_dim), C.c_double(theta), _stream()), "crab_rope_table")
+    count_launches(1)
+    return t
+
+
+def rope_kv_append(qkv: torch.Tensor, cos_sin: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, B: int,
+                   S: int, H: int, KVH: int, head_dim: int, past: int = 0, past_dev: Optional[torch.Tensor] = None):
+    """qkv (B*S, >= (H+2KVH)*hd) bf16: rotate q in place, write rotated k and v into the caches (B,KVH,ctx_max,hd)."""
+    _req_cuda(qkv, cos_sin, k_cache, v_cache, past_dev)
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and k_cache.is_contiguous() and v_cache.is_contiguous()
+    assert cos_sin.shape[1] == head_dim and k_cache.shape[1] == KVH and k_cache.shape[3] == head_dim
+    ctx_max = k_cache.shape[2]
+    assert past_dev is not None or cos_sin.shape[0] >= past + S
+    _l.check(_l.load().crab_rope_kv_append(_vp(qkv), _i(qkv.stride(0)), _vp(cos_sin), _vp(k_cache), _vp(v_cache), _i(B),
+                                           _i(S), _i(H), _i(KVH), _i(head_dim), _i(ctx_max), _vp(past_dev), _i(past),
+                                           _stream()), "crab_rope_kv_append")
+    count_launches(1)
+
+
+def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, KVH: int,
+               Sq: int, Sk: int, head_dim: int, q_strides, k_strides, v_strides, o_strides, scale: float,
+               causal: bool = False, gate: Optional[torch.Tensor] = None, bias_table: Optional[torch.Tensor] = None):
+    """Strides are (batch, row, head) in elements; q/k/v/out are any bf16 tensors whose data_ptr is the origin."""
+    _req_cuda(q, k, v, out, gate, bias_table)
+    a = _l.AttnArgs(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), o=out.data_ptr(),
+                    q_bs=q_strides[0], q_rs=q_strides[1], q_hs=q_strides[2],
+                    k_bs=k_strides[0], k_rs=k_strides[1], k_hs=k_strides[2],
+                    v_bs=v_strides[0], v_rs=v_strides[1], v_hs=v_strides[2],
+                    o_bs=o_strides[0], o_rs=o_strides[1], o_hs=o_strides[2],
+                    B=B, H=H, KVH=KVH, Sq=Sq, Sk=Sk, head_dim=head_dim, scale=scale, causal=int(causal),
+                    gate=_ptr(gate), bias_table=_ptr(bias_table))
+    _l.check(_l.load().crab_flash_attn(C.byref(a), _stream()), "crab_flash_attn")
+    count_launches(1)
+    return out
+
+
+def attn_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out: torch.Tensor, *, B: int, H: int,
+                KVH: int, head_dim: int, scale: float, length: int = 0, len_dev: Optional[torch.Tensor] = None,
+                nsplit: int = 1, workspace: Optional[torch.Tensor] = None):
+    _req_cuda(q, k_cache, v_cache, out, len_dev, workspace)
+    assert q.dim() == 2 and out.dim() == 2 and q.stride(1) == 1 and out.stride(1) == 1
+    ctx_max = k_cache.shape[2]
+    if nsplit > 1 and workspace is None:
+        workspace = torch.empty(B * H * nsplit * (head_dim + 2), device=q.device, dtype=torch.float32)
+    _l.check(_l.load().crab_attn_decode(_vp(q), _i(q.stride(0)), _vp(k_cache), _vp(v_cache), _vp(out), _i(out.stride(0)),
+                                        _vp(workspace), _i(B), _i(H), _i(KVH), _i(head_dim), _i(ctx_max), _i(nsplit),
+                                        _vp(len_dev), _i(length), C.c_float(scale), _stream()), "crab_attn_decode")
+    count_launches(2 if nsplit > 1 else 1)
+    return out
+
+
+def gather_rows(src: torch.Tensor, dst: torch.Tensor, n: int, cols: int, src_rows: Optional[torch.Tensor] = None,
+                dst_rows: Optional[torch.Tensor] = None):
+    _req_cuda(src, dst, src_rows, dst_rows)
+    assert src.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16 and src.stride(-1) == 1 and dst.stride(-1) == 1
+    for r in (src_rows, dst_rows):
+        assert r is None or (r.dtype == torch.int64 and r.is_contiguous() and r.numel() >= n)
+    _l.check(_l.load().crab_gather_rows(_vp(src), _i(src.stride(-2)), _vp(src_rows), _vp(dst), _i(dst.stride(-2)),
+                                        _vp(dst_rows), _i(n), _i(cols), _stream()), "crab_gather_rows")
+    count_launches(1)
+
+
+def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    _req_cuda(src)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    out = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    _l.check(_l.load().crab_cast_f32_bf16(_vp(src), _vp(out), C.c_int64(src.numel()), _stream()), "crab_cast_f32_bf16")
+    count_launches(1)
+    return out
+
+
+def patchify(images: torch.Tensor, patch: int, ld_out: int) -> torch.Tensor:
+    """fp32 (n, C, H, W) -> bf16 (n * (H//p) * (W//p), ld_out) patch rows, zero-padded beyond C*p*p."""
+    _req_cuda(images)
+    assert images.dtype == torch.float32 and images.is_contiguous() and images.dim() == 4
+    n, c, h, w = images.shape
+    rows = n * (h // patch) * (w // patch)
+    out = torch.empty((rows, ld_out), device=images.device, dtype=torch.bfloat16)
+    _l.check(_l.load().crab_patchify(_vp(images), _vp(out), _i(ld_out), _i(n), _i(c), _i(h), _i(w), _i(patch), _stream()),
+             "crab_patchify")
+    count_launches(1)
+    return out
+
+
+def clip_embed_ln(patch_emb, cls, pos, gamma, beta, n_img: int, tokens: int, D: int, eps: float) -> torch.Tensor:
+    _req_cuda(patch_emb, cls, pos, gamma, beta)
+    assert patch_emb.is_contiguous() and patch_emb.dtype == torch.bfloat16
+    out = torch.empty((n_img * tokens, D), device=patch_emb.device, dtype=torch.bfloat16)
+    _l.check(_l.load().crab_clip_embed_ln(_vp(patch_emb), _vp(cls), _vp(pos), _vp(gamma), _vp(beta), _vp(out), _i(n_img),
+                                          _i(tokens), _i(D), C.c_float(eps), _stream()), "crab_clip_embed_ln")
+    count_launches(1)
+    return out
+
+
+def beats_gate(q: torch.Tensor, grep_w, grep_b, grep_a, B: int, T: int, H: int) -> torch.Tensor:
+    _req_cuda(q, grep_w, grep_b, grep_a)
+    gate = torch.empty((B, H, T), device=q.device, dtype=torch.float32)
+    _l.check(_l.load().crab_beats_gate(_vp(q), _i(q.stride(0)), _vp(grep_w), _vp(grep_b), _vp(grep_a), _vp(gate), _i(B),
+                                       _i(T), _i(H), _stream()), "crab_beats_gate")
+    count_launches(1)
+    return gate
+
+
+def beats_group_pack(x: torch.Tensor, B: int, T: int, Cc: int, G: int) -> torch.Tensor:
+    _req_cuda(x)
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    out = torch.empty((G, B, T * (Cc // G)), device=x.device, dtype=torch.bfloat16)
+    _l.check(_l.load().crab_beats_group_pack(_vp(x), _vp(out), _i(B), _i(T), _i(Cc), _i(G), _stream()), "crab_beats_group_pack")
+    count_launches(1)
+    return out
+
+
+def beats_posconv_finish(x: torch.Tensor, conv_g: torch.Tensor, bias: torch.Tensor, B: int, T: int, Cc: int, G: int):
+    _req_cuda(x, conv_g, bias)
+    assert x.is_contiguous() and conv_g.is_contiguous()
+    out = torch.empty((B * T, Cc), device=x.device, dtype=torch.bfloat16)
+    _l.check(_l.load().crab_beats_posconv_finish(_vp(x), _vp(conv_g), _vp(bias), _vp(out), _i(B), _i(T), _i(Cc), _i(G),
+                                                 _stream()), "crab_beats_posconv_finish")
+    count_launches(1)
+    return out
+
+
+def argmax(logits: torch.Tensor, V: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_cuda(logits, out)
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    if out is None:
+        out = torch.empty((logits.shape[0],), device=logits.device, dtype=torch.int64)
+    _l.check(_l.load().crab_argmax(_vp(logits), _i(logits.stride(0)), _i(logits.shape[0]), _i(V), _vp(out), _stream()),
+             "crab_argmax")
+    count_launches(1)
+    return out
+
+
+def add_scalar_i32(p: torch.Tensor, v: int):
+    _req_cuda(p)
+    assert p.dtype == torch.int32
+    _l.check(_l.load().crab_add_scalar_i32(_vp(p), _i(v), _stream()), "crab_add_scalar_i32")
+    count_launches(1)

@@ -68,6 +68,85 @@ typedef struct crab_gemm_args {
 
 int crab_gemm_bf16(const crab_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Norms
+ * replaces: nn.LayerNorm in CLIP / BEATs / Q-Former / projectors (models/multimodal_encoder.py:99,128;
+ *           models/beats/backbone.py:118,262,273; models/Qformer.py:66,284,371) and LlamaRMSNorm
+ *           (models/modeling_llama.py:103-117: fp32 statistics, weight * x.to(bf16)).
+ * x, y: bf16 [rows, ld]; gamma/beta fp32 [cols]; cols % 8 == 0.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int crab_layernorm(const void* x, int ldx, const float* gamma, const float* beta, void* y, int ldy, int rows,
+                   int cols, float eps, void* stream);
+int crab_rmsnorm(const void* x, int ldx, const float* gamma, void* y, int ldy, int rows, int cols, float eps,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Rotary embedding + KV-cache append
+ * replaces: LlamaRotaryEmbedding + apply_rotary_pos_emb (models/modeling_llama.py:123-156, 204-236) and HF
+ *           DynamicCache.update (torch.cat growth) with a static cache [B, KVH, ctx_max, head_dim].
+ * crab_rope_table: cos_sin fp32 [max_pos, head_dim] = [cos(head_dim/2) | sin(head_dim/2)] per position.
+ * crab_rope_kv_append: qkv bf16 [B*S, ldq] rows = [q (H*hd) | k (KVH*hd) | v (KVH*hd)]; q rotated in place, rotated k
+ *           and v written to the caches at position past+s; `past` is read from *past_dev when non-NULL (CUDA graphs).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int crab_rope_table(float* cos_sin, int max_pos, int head_dim, double theta, void* stream);
+int crab_rope_kv_append(void* qkv, int ldq, const float* cos_sin, void* k_cache, void* v_cache, int B, int S, int H,
+                        int KVH, int head_dim, int ctx_max, const int* past_dev, int past_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Attention
+ * crab_flash_attn replaces: eager softmax(QK^T)V in CLIPAttention (transformers clip), BEATs MultiheadAttention
+ *           incl. the gated relative-position bias (models/beats/backbone.py:623-671), BertSelfAttention self/cross
+ *           (models/Qformer.py:207-266) and causal LlamaAttention / Qwen2Attention prefill
+ *           (models/modeling_llama.py:405-450, models/qwen/modeling_qwen2.py:190-199 repeat_kv).
+ *           All strides are in elements; head_dim in {64,128}; bias = gate[B,H,Sq] * bias_table[H,Sq,Sk] (fp32) or NULL.
+ * crab_attn_decode replaces: the same attention at q_len == 1 over the KV cache (decode step), split over the
+ *           context into `nsplit` partitions (workspace from crab_attn_decode_workspace_bytes when nsplit > 1).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct crab_attn_args {
+  const void* q; const void* k; const void* v; void* o; /* bf16 */
+  int64_t q_bs, q_rs, q_hs;                              /* batch / row / head strides */
+  int64_t k_bs, k_rs, k_hs;
+  int64_t v_bs, v_rs, v_hs;
+  int64_t o_bs, o_rs, o_hs;
+  int32_t B, H, KVH, Sq, Sk, head_dim;
+  float scale;
+  int32_t causal;                                        /* key j visible to query i iff j <= i + (Sk - Sq) */
+  const float* gate;
+  const float* bias_table;
+} crab_attn_args;
+int crab_flash_attn(const crab_attn_args* args, void* stream);
+int crab_attn_decode_workspace_bytes(int B, int H, int head_dim, int nsplit, int64_t* bytes);
+int crab_attn_decode(const void* q, int ldq, const void* k_cache, const void* v_cache, void* o, int ldo,
+                     float* workspace, int B, int H, int KVH, int head_dim, int ctx_max, int nsplit,
+                     const int* len_dev, int len_host, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Gathers, casts, patchify, CLIP embeddings, BEATs helpers, arg-max
+ * crab_gather_rows replaces: embed_tokens lookups and the torch.cat / left-pad splice of
+ *           prepare_multimodal_inputs (models/unified_arch.py:262-373): dst[dst_rows[i]] = src[src_rows[i]]
+ *           (NULL index array = identity).
+ * crab_patchify replaces: the im2col half of the stride==kernel patch-embed convs (CLIP 14x14, BEATs 16x16,
+ *           models/beats/BEATs.py:148-151); rows are patches in (h', w') order, columns in (c, kh, kw) order.
+ * crab_clip_embed_ln replaces: CLIPVisionEmbeddings cls/pos add + pre_layrnorm.
+ * crab_beats_gate replaces: the grep_linear gate (models/beats/backbone.py:650-662).
+ * crab_beats_group_pack / crab_beats_posconv_finish bracket the grouped pos-conv (backbone.py:33-46,114-116), which
+ *           runs as one Toeplitz GEMM per conv group through crab_gemm_bf16.
+ * crab_argmax replaces: HF greedy argmax over logits[:, -1].
+ * ---------------------------------------------------------------------------------------------------------------- */
+int crab_gather_rows(const void* src, int lds, const int64_t* src_rows, void* dst, int ldd, const int64_t* dst_rows,
+                     int n, int cols, void* stream);
+int crab_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+int crab_patchify(const float* images, void* out, int ld_out, int n_img, int C, int H, int W, int patch, void* stream);
+int crab_clip_embed_ln(const void* patch_emb, const float* cls, const float* pos, const float* gamma,
+                       const float* beta, void* out, int n_img, int tokens, int D, float eps, void* stream);
+int crab_beats_gate(const void* q, int ldq, const float* grep_w, const float* grep_b, const float* grep_a, float* gate,
+                    int B, int T, int H, void* stream);
+int crab_beats_group_pack(const void* x, void* xg, int B, int T, int C, int G, void* stream);
+int crab_beats_posconv_finish(const void* x, const void* conv_g, const float* bias, void* y, int B, int T, int C,
+                              int G, void* stream);
+int crab_argmax(const float* logits, int ld, int rows, int V, int64_t* out, void* stream);
+int crab_add_scalar_i32(int* p, int v, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
