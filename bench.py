@@ -1,0 +1,473 @@
+#!/usr/bin/env python
+"""bench.py — Crab AV-prompt hot path on B200: prefill + greedy-decode tokens/s (BASELINE.json metric).
+
+A "step" is ONE pass of the hot path over ONE batch of synthetic AVQA-shaped input:
+    CLIP ViT-L/14 over 8x224^2 frames + BEATs over 10x1 s fbank segments + both Q-Former bridges
+    -> splice into a 512-token prompt (S = 1086) -> LLaMA-2-7B-dim decoder prefill (hyper-LoRA on all 7 linears)
+    -> 128 greedy tokens through a CUDA-graph decode step.
+Workload at N=1: BASELINE.json configs[2] "bs32 synthetic AVQA (10s audio, 8 frames, 512-tok prompt) bf16 on 1xB200";
+at N>1 every rank runs its own 32 samples (weak scaling: configs[3] at N=8) and the generated ids are all-gathered.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3                    # our arm
+    python bench.py --impl reference --gpus 1 --steps 1 --warmup 0  # reference arm: CPU oracle port, bounded sample
+    torchrun --nproc-per-node N ... bench.py --gpus N ...            # one rank per GPU
+
+One JSON line on stdout (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return {k: float(d[k]) for k in FALLBACK_PEAKS}, "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# synthetic weights, generated tensor-by-tensor on the device from (name, seed): random init of the real architecture
+# ------------------------------------------------------------------------------------------------------------------
+class LazySynthSD:
+    """dict-like state dict: tensors are produced on demand on `device` so 7B parameters never sit on the host."""
+
+    def __init__(self, manifest, seed, device):
+        self.m, self.seed, self.dev = manifest, seed, device
+
+    def __contains__(self, k):
+        return k in self.m
+
+    def items(self):
+        for k in self.m:
+            yield k, self[k]
+
+    def get(self, k, default=None):
+        return self[k] if k in self.m else default
+
+    def __getitem__(self, key):
+        shape = tuple(self.m[key])
+        h = int.from_bytes(hashlib.sha256(f"{self.seed}:{key}".encode()).digest()[:8], "little") & 0x7FFFFFFFFFFFFFFF
+        g = torch.Generator(device=self.dev).manual_seed(h)
+        r = torch.randn(shape, generator=g, device=self.dev, dtype=torch.float32)
+        last = key.rsplit(".", 1)[-1]
+        n = math.prod(shape)
+        if "lora_B" in key:
+            return 0.05 * r
+        if "lora_A" in key or "lora_route" in key:
+            return r / math.sqrt(shape[-1])
+        if last == "weight_g":
+            return 0.5 + 0.1 * r.abs()
+        if last == "grep_a":
+            return 1.0 + 0.2 * r
+        if "relative_attention_bias" in key or "query_tokens" in key or "class_embedding" in key or "position_embedding" in key:
+            return 0.5 * r
+        if "embed_tokens" in key:
+            return r
+        if len(shape) == 1:
+            return 0.05 * r if last == "bias" else 1.0 + 0.1 * r
+        return r / math.sqrt(n // shape[0])
+
+
+def make_inputs(bs, frames, audio_segs, audio_len, prompt_len, base_vocab, ids_map, rank):
+    """Pinned host tensors, per-sample seeds 1000+i."""
+    ids, X = [], []
+    for i in range(bs):
+        g = torch.Generator(device="cpu").manual_seed(1000 + i + 100000 * rank)
+        video = torch.randn(frames, 3, 224, 224, generator=g).pin_memory()
+        audio = (0.5 * torch.randn(audio_segs, audio_len, 128, generator=g)).pin_memory()
+        t = torch.randint(3, base_vocab, (prompt_len,), generator=g)
+        t[10] = ids_map["<video>"]
+        t[20] = ids_map["<audio>"]
+        ids.append(t)
+        X.append({"<video>": video, "<audio>": audio})
+    return ids, X
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) >= 7 and r[3 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores, on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_port_run(args, threads):
+    """Times oracle/crab_oracle.py (the CPU restatement of the reference's path; the reference itself is Python +
+    HF and cannot travel to the GPU box).  Bounded sample: ONE sample of the batch, `cpu_layers` of each stack, and
+    `cpu_steps` decode steps, scaled to the full depth / 128 steps (every layer of a stack costs the same).
+    Returns (tokens_per_s, sample_description, detail)."""
+    from oracle import crab_oracle as O
+    from oracle import synth
+
+    torch.set_num_threads(threads)
+    Ls, steps = args.cpu_layers, args.cpu_steps
+    dec = O.DecoderCfg(hidden=4096, inter=11008, layers=Ls, heads=32, kv_heads=32, head_dim=128, vocab=32017)
+    cfg = O.CrabCfg(decoder=dec, clip=O.ClipCfg(layers=Ls), beats=O.BeatsCfg(layers=Ls), qformer=O.QformerCfg(),
+                    select_layers=(Ls,), image_tokens=256, base_vocab=32000)
+    from crab_b200.engine import BeatsConfig, ClipConfig, CrabConfig, DecoderConfig, QformerConfig
+    from crab_b200.models.unified_arch import full_manifest
+
+    ecfg = CrabConfig(decoder=DecoderConfig(layers=Ls), clip=ClipConfig(layers=Ls), beats=BeatsConfig(layers=Ls),
+                      qformer=QformerConfig())
+    man = full_manifest(ecfg)
+    sd = synth.synth_state_dict(man, 42)
+    video, audio, ids = synth.synth_inputs(1000, frames=8, image=224, audio_segs=10, audio_len=98,
+                                           prompt_len=args.prompt_len, base_vocab=32000,
+                                           video_id=cfg.special_ids["<video>"], audio_id=cfg.special_ids["<audio>"])
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        taps = O.visual_encoder(sd, video.unsqueeze(0), cfg.clip, cfg.select_layers)
+        t_clip = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        vl = O.vl_projector(sd, taps[-1], cfg.qformer, 256)[0]
+        t_vl = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        be = O.audio_encoder(sd, audio.unsqueeze(0), cfg.beats)
+        t_beats = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        al = O.al_projector(sd, be, cfg.qformer)[0]
+        t_al = time.perf_counter() - t0
+        emb = sd["model.embed_tokens.weight"]
+        x = torch.cat([emb[ids[:10]], vl, emb[ids[11:20]], al, emb[ids[21:]]], 0).unsqueeze(0)
+        S = x.shape[1]
+        t0 = time.perf_counter()
+        h, cache = O.decoder_forward(sd, x, dec)
+        t_pf = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        logits = O.lm_head(sd, h[:, -1])
+        t_head = time.perf_counter() - t0
+        nxt = logits.argmax(-1)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            h, cache = O.decoder_forward(sd, emb[nxt].unsqueeze(1), dec, cache)
+            nxt = O.lm_head(sd, h[:, -1]).argmax(-1)
+        t_dec = (time.perf_counter() - t0) / steps
+    # scale the sampled depth to the full stacks: CLIP 23 layers, BEATs 12, decoder 32 (+ lm_head once per step)
+    t_dec_layers = max(t_dec - t_head, 0.0)
+    t_prefill = t_clip * 23 / Ls + t_vl + t_beats * 12 / Ls + t_al + t_pf * 32 / Ls + t_head
+    t_step = t_dec_layers * 32 / Ls + t_head
+    t_total = t_prefill + 127 * t_step
+    tok_s = (S + args.new_tokens) / t_total
+    detail = {"prefill_tok_s": S / t_prefill, "decode_tok_s": 1.0 / t_step, "t_prefill_s": t_prefill, "t_decode_step_s": t_step,
+              "S": S, "measured": {"clip_s": t_clip, "vl_s": t_vl, "beats_s": t_beats, "al_s": t_al, "prefill_s": t_pf,
+                                   "lm_head_s": t_head, "decode_step_s": t_dec}}
+    sample = (f"1 of {args.bs} samples (fp32, {threads} threads): {Ls} of 23 CLIP / {Ls} of 12 BEATs / {Ls} of 32 decoder "
+              f"layers at full width, S={S}, {steps} decode steps; times scaled by layer count and to 128 tokens")
+    return tok_s, sample, detail
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    for _ in range(max(args.warmup, 0)):
+        cpu_port_run(args, threads)
+    t0 = time.perf_counter()
+    for _ in range(max(args.steps, 1)):
+        vals.append(cpu_port_run(args, threads))
+    wall = time.perf_counter() - t0
+    v, sample, detail = sorted(vals, key=lambda z: z[0])[len(vals) // 2]
+    line = {"metric": "AV-prompt prefill+decode tokens/sec", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": max(args.steps, 1), "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": workload_config(args, note="CPU oracle port of the reference path (oracle/crab_oracle.py); "
+                                                 "bs-1 bounded sample, see cpu_baseline.sample"),
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample, **detail},
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, note=None):
+    c = {"workload": f"bs{args.bs}_avqa_10s-audio_8x224-video_{args.prompt_len}tok-prompt_{args.new_tokens}new_llama7b-dims_hyperlora",
+         "per_gpu_batch": args.bs, "frames": 8, "audio_segments": 10, "prompt_len": args.prompt_len,
+         "seq_len_after_splice": args.prompt_len + 574, "new_tokens": args.new_tokens, "decoder_layers": args.layers,
+         "l2_policy": "working set per step (14 GB weights + 20 GB KV) >> 126 MB L2; no explicit flush"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="crab_b200", choices=["crab_b200", "reference"])
+    ap.add_argument("--bs", type=int, default=32)
+    ap.add_argument("--prompt-len", type=int, default=512)
+    ap.add_argument("--new-tokens", type=int, default=128)
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--cpu-layers", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (crab_b200 arm) needs a B200: there is no CPU fallback. Use --impl reference for the CPU arm.")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    from crab_b200 import ops
+    from crab_b200.engine import BeatsConfig, ClipConfig, CrabConfig, CrabEngine, DecoderConfig, QformerConfig
+    from crab_b200.models.unified_arch import full_manifest, special_token_ids
+    from crab_b200.models.unified_llama import UnifiedConfig, UnifiedForCausalLM
+
+    peaks, peaks_src = load_peaks()
+    S = args.prompt_len + 574
+    max_ctx = (S + args.new_tokens + 7) // 8 * 8
+    ids_map = special_token_ids(32000)
+    cfg = CrabConfig(decoder=DecoderConfig(layers=args.layers), clip=ClipConfig(), beats=BeatsConfig(),
+                     qformer=QformerConfig(), max_ctx=max_ctx, special_ids=ids_map)
+    sd = LazySynthSD(full_manifest(cfg), 42, dev)
+    t0 = time.time()
+    eng = CrabEngine(sd, cfg, dev)
+    hf_cfg = UnifiedConfig(hidden_size=4096, intermediate_size=11008, num_hidden_layers=args.layers,
+                           num_attention_heads=32, num_key_value_heads=32, vocab_size=32017)
+    model = UnifiedForCausalLM.from_engine(hf_cfg, eng)  # the public API object a quick_start user holds
+    torch.cuda.synchronize()
+    t_load = time.time() - t0
+
+    ids, X_host = make_inputs(args.bs, 8, 10, 98, args.prompt_len, 32000, ids_map, rank)
+    X_dev = [{k: v.to(dev) for k, v in x.items()} for x in X_host]
+    h2d = sum(v.numel() * v.element_size() for x in X_host for v in x.values()) + sum(t.numel() * 8 for t in ids)
+    d2h = args.bs * args.new_tokens * 8
+    tokens_per_step = args.bs * (S + args.new_tokens)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(ev=None):
+        """inputs resident in HBM; the three phases are bracketed by CUDA events on the launching stream."""
+        if ev is not None:
+            ev[0].record()
+        embeds, _, _ = eng.prepare_inputs(ids, X_dev)
+        if ev is not None:
+            ev[1].record()
+        _, nxt = eng.prefill(embeds)
+        out = torch.empty((args.bs, args.new_tokens), device=dev, dtype=torch.int64)
+        out[:, 0].copy_(nxt)
+        if ev is not None:
+            ev[2].record()
+        eng.begin_decode_cached(args.bs)
+        for s_ in range(1, args.new_tokens):
+            _, nxt = eng.decode_step()
+            out[:, s_].copy_(nxt)
+        if ev is not None:
+            ev[3].record()
+        if world > 1:
+            gathered = torch.empty((world * args.bs, args.new_tokens), device=dev, dtype=torch.int64)
+            dist.all_gather_into_tensor(gathered, out)
+            out = gathered
+        return out
+
+    def step_e2e():
+        """through the public API with HOST inputs: H2D of this step's inputs and D2H of the generated ids inside."""
+        out = model.generate(batch_input_ids=ids, batch_labels=None, batch_X_modals=X_host, batch_task_names=["avqa"] * args.bs,
+                             use_cache=True, max_new_tokens=args.new_tokens)
+        return out.cpu()
+
+    # ---- warm-up (also builds the decode graph once) -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        ref_out = step_resident()
+    barrier()
+
+    # ---- timed: resident ---------------------------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = ops.launch_count()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    ops.start_kernel_timing()
+    barrier()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for i in range(args.steps):
+        out = step_resident(evs[i])
+    e_end.record()
+    barrier()
+    kt = ops.stop_kernel_timing()
+    launches = (ops.launch_count() - n0) // args.steps
+    ms_total = e_start.elapsed_time(e_end)
+    clocks = sampler.stop()
+    deterministic = bool(torch.equal(out[: args.bs] if world > 1 else out, ref_out[: args.bs] if world > 1 else ref_out))
+    t_enc = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    t_pf = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    t_dec = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+    tm = torch.tensor([ms_total, t_enc, t_pf, t_dec], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total, t_enc, t_pf, t_dec = tm.tolist()
+    ms_step = ms_total / args.steps
+    value = world * tokens_per_step / (ms_step / 1e3)
+
+    # ---- timed: e2e through the public API -----------------------------------------------------------------------------
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_e2e = step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = world * tokens_per_step / t_e2e.item()
+    e2e_same = bool(torch.equal(out_e2e.to(dev), out[: args.bs] if world > 1 else out))
+
+    # ---- per-kernel split of one eager (un-graphed) decode step: same kernels as the graph -------------------------------
+    embeds, _, _ = eng.prepare_inputs(ids, X_dev)
+    eng.prefill(embeds)
+    eng.begin_decode(args.bs, use_graph=False)
+    eng.decode_step()
+    ops.start_kernel_timing()
+    for _ in range(4):
+        eng.decode_step()
+    kd = ops.stop_kernel_timing()
+    for d in kd.values():
+        for k in ("ms", "flops", "bytes"):
+            d[k] /= 4
+        d["launches"] //= 4
+
+    if rank == 0:
+        # ---------------- roofline of the dominant kernel -----------------------------------------------------------
+        for d in kt.values():
+            for k in ("ms", "flops", "bytes"):
+                d[k] /= args.steps
+            d["launches"] //= args.steps
+        dec_eager_ms = sum(d["ms"] for d in kd.values())
+        graph_step_ms = t_dec / max(args.new_tokens - 1, 1)
+        shares = {k: d["ms"] for k, d in kt.items()}                      # encoders + prefill, measured in the timed region
+        for k, d in kd.items():                                           # decode kernels: eager split scaled to the graph time
+            shares["decode:" + k] = d["ms"] / max(dec_eager_ms, 1e-9) * t_dec
+        top = max(shares, key=shares.get)
+        ctx_mean = S + 1 + (args.new_tokens - 1) / 2.0
+        kv_bytes = args.bs * ctx_mean * 2 * 32 * 128 * 2 * args.layers
+        wbytes = sum(L[k].numel() * 2 for L in eng.layers for k in ("wqkv", "wo", "wgu", "wd")) + eng.lm_head.numel() * 2
+        decode_bytes = wbytes + kv_bytes
+        if top.startswith("decode:"):
+            d = kd[top[len("decode:"):]]
+            scale = graph_step_ms / max(dec_eager_ms, 1e-9)
+            if "gemm" in top:
+                ach = d["bytes"] / (d["ms"] * scale * 1e-3) / 1e9
+            else:
+                ach = kv_bytes / (d["ms"] * scale * 1e-3) / 1e9 if "attn_decode" in top else 0.0
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "launches_per_step": d["launches"] * (args.new_tokens - 1),
+                    "avg_launch_ms": d["ms"] * scale / max(d["launches"], 1)}
+        else:
+            d = kt[top]
+            ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / max(d["launches"], 1)}
+        roof["peak_source"] = peaks_src
+        roof["share_of_step"] = shares[top] / ms_step
+        gemm_ms = sum(d["ms"] for k, d in kt.items() if k.startswith("gemm"))
+        gemm_fl = sum(d["flops"] for k, d in kt.items() if k.startswith("gemm"))
+        phases = {
+            "encoders_bridge_splice_ms": t_enc, "decoder_prefill_ms": t_pf, "decode_127_steps_ms": t_dec,
+            "prefill_tok_s": world * args.bs * S / ((t_enc + t_pf) / 1e3),
+            "decoder_prefill_tok_s": world * args.bs * S / (t_pf / 1e3),
+            "decode_tok_s": world * args.bs * (args.new_tokens - 1) / (t_dec / 1e3),
+            "decode_step_ms": graph_step_ms,
+            "prefill_gemm_tflops": gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
+            "prefill_gemm_frac_of_peak": (gemm_fl / (gemm_ms * 1e-3) / 1e12) / peaks["bf16_tflops_sustained"] if gemm_ms else None,
+            "prefill_algorithmic_tflop": 15.86 * args.bs * (args.layers / 32.0),
+            "prefill_frac_of_tensor_roofline": (15.86e12 * args.bs / ((t_enc + t_pf) / 1e3)) / (peaks["bf16_tflops_sustained"] * 1e12)
+            if args.layers == 32 else None,
+            "decode_bytes_per_step": decode_bytes, "decode_gbs": decode_bytes / (graph_step_ms * 1e-3) / 1e9,
+            "decode_frac_of_hbm_roofline": decode_bytes / (graph_step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                threads = os.cpu_count() or 1
+                v, sample, detail = cpu_port_run(args, threads)
+                cpu = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample, **detail}
+            except Exception as e:  # the CPU leg must never take the GPU numbers down with it
+                cpu = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
+        line = {
+            "metric": "AV-prompt prefill+decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "crab_b200.models.unified_llama.UnifiedForCausalLM.generate", "ids_equal_resident_run": e2e_same},
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "phases": phases,
+            "deterministic_across_steps": deterministic, "weights": "random-init (seeded), generated on device",
+            "load_s": round(t_load, 1),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -165,6 +165,10 @@ class CrabEngine:
         self._bufs: Dict[Tuple, torch.Tensor] = {}
         self._graph = None
         self._graph_bs = None
+        self._use_graph = False
+        self.past_dev = None
+        self.len_dev = None
+        self.cur_len = 0
         self.k_cache: List[torch.Tensor] = []
         self.v_cache: List[torch.Tensor] = []
 
@@ -197,51 +201,62 @@ class CrabEngine:
         self.EXT_QKV, self.EXT_O, self.EXT_GU, self.EXT_D = 96, 32, 64, 32
         self.layers = []
 
-        def bcat(name):  # [out, 24] = [B0 | B1 | B2]
-            return torch.cat([sd[f"{name}.lora_B{i}.weight"].float() for i in range(nl)], dim=1)
+        def put(dst, src):  # packed buffers are assembled directly in bf16 on the device, slice by slice
+            dst.copy_(src.detach().to(device=dev, dtype=torch.bfloat16, non_blocking=True))
+
+        def bcat(dst, name):  # [out, 24] = [B0 | B1 | B2]
+            for j in range(nl):
+                put(dst[:, j * r:(j + 1) * r], sd[f"{name}.lora_B{j}.weight"])
 
         def ra(names):  # rows [R (3); A (8)] per linear
-            return _bf(torch.cat([torch.cat([sd[n + ".lora_route.weight"], sd[n + ".lora_A.weight"]], 0) for n in names], 0), dev)
+            out = torch.empty((len(names) * (nl + r), sd[names[0] + ".lora_A.weight"].shape[1]), device=dev, dtype=torch.bfloat16)
+            for j, n in enumerate(names):
+                put(out[j * (nl + r):j * (nl + r) + nl], sd[n + ".lora_route.weight"])
+                put(out[j * (nl + r) + nl:(j + 1) * (nl + r)], sd[n + ".lora_A.weight"])
+            return out
+
+        def zeros(rows, cols):
+            return torch.zeros((rows, cols), device=dev, dtype=torch.bfloat16)
 
         for i in range(c.layers):
             lp = f"model.layers.{i}."
             at, ml = lp + "self_attn.", lp + "mlp."
             L = {}
             nq, nk = H * hd, KV * hd
-            wq = torch.zeros((nq + 2 * nk, D + self.EXT_QKV), dtype=torch.float32)
-            wq[:nq, :D] = sd[at + "q_proj.weight"].float()
-            wq[nq:nq + nk, :D] = sd[at + "k_proj.weight"].float()
-            wq[nq + nk:, :D] = sd[at + "v_proj.weight"].float()
+            wq = zeros(nq + 2 * nk, D + self.EXT_QKV)
+            put(wq[:nq, :D], sd[at + "q_proj.weight"])
+            put(wq[nq:nq + nk, :D], sd[at + "k_proj.weight"])
+            put(wq[nq + nk:, :D], sd[at + "v_proj.weight"])
             if self.lora:
-                wq[:nq, D:D + zw] = bcat(at + "q_proj")
-                wq[nq:nq + nk, D + zw:D + 2 * zw] = bcat(at + "k_proj")
-                wq[nq + nk:, D + 2 * zw:D + 3 * zw] = bcat(at + "v_proj")
+                bcat(wq[:nq, D:D + zw], at + "q_proj")
+                bcat(wq[nq:nq + nk, D + zw:D + 2 * zw], at + "k_proj")
+                bcat(wq[nq + nk:, D + 2 * zw:D + 3 * zw], at + "v_proj")
                 L["ra_qkv"] = ra([at + "q_proj", at + "k_proj", at + "v_proj"])
-            L["wqkv"] = _bf(wq, dev)
-            L["bqkv"] = (_f32(torch.cat([sd[at + "q_proj.bias"], sd[at + "k_proj.bias"], sd[at + "v_proj.bias"]]), dev)
-                         if c.qkv_bias else None)
-            wo = torch.zeros((D, nq + self.EXT_O), dtype=torch.float32)
-            wo[:, :nq] = sd[at + "o_proj.weight"].float()
+            L["wqkv"] = wq
+            L["bqkv"] = (torch.cat([_f32(sd[at + "q_proj.bias"], dev), _f32(sd[at + "k_proj.bias"], dev),
+                                    _f32(sd[at + "v_proj.bias"], dev)]) if c.qkv_bias else None)
+            wo = zeros(D, nq + self.EXT_O)
+            put(wo[:, :nq], sd[at + "o_proj.weight"])
             if self.lora:
-                wo[:, nq:nq + zw] = bcat(at + "o_proj")
+                bcat(wo[:, nq:nq + zw], at + "o_proj")
                 L["ra_o"] = ra([at + "o_proj"])
-            L["wo"] = _bf(wo, dev)
-            wg = torch.zeros((F, D + self.EXT_GU), dtype=torch.float32)
-            wu = torch.zeros((F, D + self.EXT_GU), dtype=torch.float32)
-            wg[:, :D] = sd[ml + "gate_proj.weight"].float()
-            wu[:, :D] = sd[ml + "up_proj.weight"].float()
+            L["wo"] = wo
+            # gate/up rows interleaved in [64 gate | 64 up] groups so one output tile holds both halves (SWIGLU)
+            wgu = zeros(2 * F, D + self.EXT_GU).view(F // 64, 2, 64, D + self.EXT_GU)
+            put(wgu[:, 0, :, :D], sd[ml + "gate_proj.weight"].view(F // 64, 64, D))
+            put(wgu[:, 1, :, :D], sd[ml + "up_proj.weight"].view(F // 64, 64, D))
             if self.lora:
-                wg[:, D:D + zw] = bcat(ml + "gate_proj")
-                wu[:, D + zw:D + 2 * zw] = bcat(ml + "up_proj")
+                for j in range(nl):
+                    put(wgu[:, 0, :, D + j * r:D + (j + 1) * r], sd[f"{ml}gate_proj.lora_B{j}.weight"].view(F // 64, 64, r))
+                    put(wgu[:, 1, :, D + zw + j * r:D + zw + (j + 1) * r], sd[f"{ml}up_proj.lora_B{j}.weight"].view(F // 64, 64, r))
                 L["ra_gu"] = ra([ml + "gate_proj", ml + "up_proj"])
-            # interleave [64 gate | 64 up] row groups so one output tile holds both halves (SWIGLU epilogue)
-            L["wgu"] = _bf(torch.stack([wg.view(F // 64, 64, -1), wu.view(F // 64, 64, -1)], dim=1).reshape(2 * F, -1), dev)
-            wd = torch.zeros((D, F + self.EXT_D), dtype=torch.float32)
-            wd[:, :F] = sd[ml + "down_proj.weight"].float()
+            L["wgu"] = wgu.view(2 * F, D + self.EXT_GU)
+            wd = zeros(D, F + self.EXT_D)
+            put(wd[:, :F], sd[ml + "down_proj.weight"])
             if self.lora:
-                wd[:, F:F + zw] = bcat(ml + "down_proj")
+                bcat(wd[:, F:F + zw], ml + "down_proj")
                 L["ra_d"] = ra([ml + "down_proj"])
-            L["wd"] = _bf(wd, dev)
+            L["wd"] = wd
             L["ln1"] = _f32(sd[lp + "input_layernorm.weight"], dev)
             L["ln2"] = _f32(sd[lp + "post_attention_layernorm.weight"], dev)
             self.layers.append(L)
@@ -633,22 +648,26 @@ class CrabEngine:
         ops.add_scalar_i32(self.len_dev, 1)
 
     def begin_decode(self, B: int, use_graph: bool = True):
-        """Capture one decode step (all layers + head + arg-max + position bump) in a CUDA graph; the context length
-        lives in device memory so the same graph is replayed every step."""
+        """Prepare the decode loop after a prefill.  With `use_graph`, one decode step (all layers + head + arg-max +
+        position bump) is captured in a CUDA graph ONCE per (batch, buffers) and replayed every step of every later
+        request: the context length lives in device memory (`past_dev`, `len_dev`), so nothing in the graph changes."""
         c = self.cfg.decoder
-        self.past_dev = torch.tensor([self.cur_len], dtype=torch.int32, device=self.dev)
-        self.len_dev = torch.tensor([self.cur_len + 1], dtype=torch.int32, device=self.dev)
+        if getattr(self, "past_dev", None) is None:
+            self.past_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self.len_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.past_dev.fill_(self.cur_len)
+        self.len_dev.fill_(self.cur_len + 1)
         blocks = B * c.kv_heads
         nsplit = 1 if blocks >= 2 * 148 else max(1, min(16, (2 * 148 + blocks - 1) // blocks))
         ws = self._buf("dec_ws", (B * c.heads * nsplit * (c.head_dim + 2),), torch.float32) if nsplit > 1 else None
         self._dec_args = (B, nsplit, ws)
-        self._graph = None
-        if use_graph:
+        self._use_graph = use_graph
+        if use_graph and (self._graph is None or self._graph_bs != B):
             s = torch.cuda.Stream(device=self.dev)
             s.wait_stream(torch.cuda.current_stream())
             saved = (self.next_ids.clone(), self.past_dev.clone(), self.len_dev.clone())
             with torch.cuda.stream(s):
-                self._decode_body(*self._dec_args)  # warm-up outside capture (lazy kernel attribute setup)
+                self._decode_body(*self._dec_args)  # warm-up outside capture (buffers, kernel attributes)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.next_ids.copy_(saved[0]); self.past_dev.copy_(saved[1]); self.len_dev.copy_(saved[2])
@@ -657,12 +676,15 @@ class CrabEngine:
             with torch.cuda.graph(g):
                 self._decode_body(*self._dec_args)
             self._graph_kernels = ops.launch_count() - n0
+            ops.count_launches(-self._graph_kernels)  # capture launches nothing
             self.next_ids.copy_(saved[0]); self.past_dev.copy_(saved[1]); self.len_dev.copy_(saved[2])
-            self._graph = g
+            self._graph, self._graph_bs = g, B
+
+    begin_decode_cached = begin_decode
 
     def decode_step(self):
         """One greedy step: consumes self.next_ids, leaves the new arg-max there and fp32 logits in self.logits."""
-        if self._graph is not None:
+        if self._use_graph:
             self._graph.replay()
             ops.count_launches(self._graph_kernels)
         else:

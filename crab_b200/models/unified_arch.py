@@ -142,6 +142,52 @@ def projector_manifest(kind: str, q: QformerConfig, enc_width: int, d_model: int
     return m
 
 
+def decoder_manifest(d: DecoderConfig, lora: bool = True) -> Dict[str, Tuple[int, ...]]:
+    """Decoder parameter names/shapes as in reference checkpoints (HF LLaMA/Qwen2 names + the hyper-LoRA tensors
+    peft_hyper adds per wrapped linear: lora_A, lora_route, lora_B0..B{n-1}; peft_hyper/tuners/lora.py:283-290)."""
+    m: Dict[str, Tuple[int, ...]] = {"model.embed_tokens.weight": (d.vocab, d.hidden), "model.norm.weight": (d.hidden,),
+                                     "lm_head.weight": (d.vocab, d.hidden)}
+    nq, nk = d.heads * d.head_dim, d.kv_heads * d.head_dim
+    for i in range(d.layers):
+        lp = f"model.layers.{i}."
+        lins = {"self_attn.q_proj": (nq, d.hidden), "self_attn.k_proj": (nk, d.hidden), "self_attn.v_proj": (nk, d.hidden),
+                "self_attn.o_proj": (d.hidden, nq), "mlp.gate_proj": (d.inter, d.hidden), "mlp.up_proj": (d.inter, d.hidden),
+                "mlp.down_proj": (d.hidden, d.inter)}
+        for n, (o, k) in lins.items():
+            m[lp + n + ".weight"] = (o, k)
+            if d.qkv_bias and n.split(".")[-1] in ("q_proj", "k_proj", "v_proj"):
+                m[lp + n + ".bias"] = (o,)
+            if lora:
+                m[lp + n + ".lora_A.weight"] = (d.lora_r, k)
+                m[lp + n + ".lora_route.weight"] = (d.lora_nums, k)
+                for j in range(d.lora_nums):
+                    m[lp + n + f".lora_B{j}.weight"] = (o, d.lora_r)
+        m[lp + "input_layernorm.weight"] = (d.hidden,)
+        m[lp + "post_attention_layernorm.weight"] = (d.hidden,)
+    return m
+
+
+def full_manifest(cfg: CrabConfig, d_model: Optional[int] = None, lora: bool = True) -> Dict[str, Tuple[int, ...]]:
+    """Every tensor the engine reads, under the reference's state-dict names (`model.visual_encoder.…`, …)."""
+    d_model = d_model or cfg.decoder.hidden
+    m = decoder_manifest(cfg.decoder, lora)
+    c = cfg.clip
+    for k, v in clip_manifest(c.hidden, c.inter, c.layers, c.patch, c.image).items():
+        m["model.visual_encoder." + k] = v
+    for k, v in beats_manifest(cfg.beats).items():
+        m["model.audio_encoder." + k] = v
+    for k, v in projector_manifest("visual", cfg.qformer, c.hidden, d_model, cfg.n_query).items():
+        m["model.vl_projector." + k] = v
+    for k, v in projector_manifest("audio", cfg.qformer, cfg.beats.dim, d_model, cfg.n_query).items():
+        m["model.al_projector." + k] = v
+    return m
+
+
+def special_token_ids(base_vocab: int, mask_token_nums: int = 6) -> Dict[str, int]:
+    names = _IMAGE_TOKENS + _VIDEO_TOKENS + _AUDIO_TOKENS + _MASK_TOKENS + [f"<mask_{i}>" for i in range(mask_token_nums)]
+    return {t: base_vocab + i for i, t in enumerate(names)}
+
+
 def _load_weights_into(tree: nn.Module, sd: Dict[str, torch.Tensor], prefix: str = "") -> List[str]:
     own = dict(tree.named_parameters())
     missing = []

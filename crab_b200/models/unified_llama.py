@@ -128,6 +128,24 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
             model.load_state_dict(sd, strict=False)
         return model
 
+    @classmethod
+    def from_engine(cls, config, engine: CrabEngine):
+        """Wrap an already-packed engine (weights live only in its device buffers; the parameter containers are
+        created on the `meta` device).  Used when weights are produced directly on the GPU."""
+        with torch.device("meta"):
+            model = cls.__new__(cls)
+            nn.Module.__init__(model)
+            model.model = cls._model_cls(config, torch.bfloat16)
+            model.lm_head = nn.Linear(config.hidden_size, engine.vocab, bias=False, dtype=torch.bfloat16)
+        model.config, model.vocab_size, model.max_ctx = config, engine.vocab, engine.cfg.max_ctx
+        model.pretraining_tp, model.is_avs_task = 1, False
+        model._engine, model._target = engine, engine.dev
+        model.generation_config = SimpleNamespace(max_new_tokens=20)
+        model.model.pad_token_id = engine.cfg.pad_token_id
+        ids = engine.cfg.special_ids
+        model.SPECIAL_TOKEN_2_IDS, model.IDS_2_SPECIAL_TOKEN = dict(ids), {v: k for k, v in ids.items()}
+        return model
+
     def get_model(self):
         return self.model
 
@@ -213,8 +231,9 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
         models/unified_llama.py:125-127).  Training (loss/backward) is out of scope."""
         eng = self.engine()
         if input_ids is not None and input_ids.shape[1] == 1 and getattr(eng, "cur_len", 0) > 0:
-            if eng._graph is None and not hasattr(eng, "_dec_args"):
+            if not getattr(eng, "_fwd_decode", False):
                 eng.begin_decode(input_ids.shape[0], use_graph=False)
+                eng._fwd_decode = True
             eng.next_ids.copy_(input_ids[:, 0].to(eng.dev))
             logits, _ = eng.decode_step()
         else:
@@ -223,8 +242,7 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
             elif inputs_embeds is None and input_ids is not None:
                 b, s = input_ids.shape
                 inputs_embeds = self.encode_ids(input_ids).view(b, s, -1)
-            if hasattr(eng, "_dec_args"):
-                del eng._dec_args
+            eng._fwd_decode = False
             logits, _ = eng.prefill(inputs_embeds.clone())
         return SimpleNamespace(logits=logits.unsqueeze(1).clone(), past_key_values=True, loss=None)
 

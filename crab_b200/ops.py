@@ -24,6 +24,66 @@ def count_launches(n: int) -> None:
     _launches += n
 
 
+_timer = None  # when a list: every wrapper appends (tag, flops, bytes, start_event, end_event)
+
+
+def start_kernel_timing() -> None:
+    """Bracket every subsequent kernel launch with CUDA events on the launching stream (not during graph capture)."""
+    global _timer
+    _timer = []
+
+
+def stop_kernel_timing():
+    """-> {tag: dict(launches, ms, flops, bytes)} aggregated over the launches since start_kernel_timing()."""
+    global _timer
+    rec, _timer = _timer or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for tag, fl, by, e0, e1 in rec:
+        d = out.setdefault(tag, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        d["launches"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += fl
+        d["bytes"] += by
+    return out
+
+
+class _timed:
+    __slots__ = ("tag", "fl", "by", "e0")
+
+    def __init__(self, tag, flops=0.0, nbytes=0.0):
+        self.tag, self.fl, self.by, self.e0 = tag, flops, nbytes, None
+
+    def __enter__(self):
+        if _timer is not None and not torch.cuda.is_current_stream_capturing():
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _timer.append((self.tag, self.fl, self.by, self.e0, e1))
+        return False
+
+
+def auto_block_n(M: int, N: int, act: int, sms: int = 148) -> int:
+    """Tile-width heuristic (same rule as the C side's block_n=0): widest tile that still gives every SM work."""
+    if act == ACT_LORA_Z:
+        return 64
+    mt = (M + 127) // 128
+    if mt * ((N + 255) // 256) >= sms:
+        bn = 256
+    elif mt * ((N + 127) // 128) >= sms or N < 128:
+        bn = 64 if N <= 64 else 128
+    else:
+        bn = 64
+    if act == ACT_SWIGLU and bn == 64:
+        bn = 128
+    return bn
+
+
 ACT_NONE, ACT_QUICK_GELU, ACT_GELU, ACT_SWIGLU, ACT_LORA_Z = 0, 1, 2, 3, 4
 BF16, F32 = 0, 1
 
@@ -71,6 +131,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         assert bias.dtype == torch.float32 and bias.numel() >= N
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.stride(1) == 1
+    if block_n == 0:
+        block_n = auto_block_n(M, N, act)
     args = _l.GemmArgs(
         A=_ptr(a), B=_ptr(w), C=_ptr(out), bias=_ptr(bias), residual=_ptr(residual),
         M=M, N=N, K=K, lda=a.stride(0), ldb=w.stride(0), ldc=out.stride(0),
@@ -78,7 +140,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         res_scale=res_scale, out_scale=out_scale, act=act,
         out_dtype=(BF16 if out.dtype == torch.bfloat16 else F32), block_n=block_n, max_ctas=max_ctas,
     )
-    _l.check(_l.load().crab_gemm_bf16(C.byref(args), _stream()), "crab_gemm_bf16")
+    with _timed(f"gemm_bf16_tcgen05<{block_n}>", 2.0 * M * N * K, 2.0 * (M * K + N * K) + out.element_size() * M * n_out):
+        _l.check(_l.load().crab_gemm_bf16(C.byref(args), _stream()), "crab_gemm_bf16")
     count_launches(1)
     return out
 
@@ -98,8 +161,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16 and gamma.dtype == torch.float32
     if out is None:
         out = torch.empty((x.shape[0], x.shape[1]), device=x.device, dtype=torch.bfloat16)
-    _l.check(_l.load().crab_layernorm(_vp(x), _i(x.stride(0)), _vp(gamma), _vp(beta), _vp(out), _i(out.stride(0)),
-                                      _i(x.shape[0]), _i(x.shape[1]), C.c_float(eps), _stream()), "crab_layernorm")
+    with _timed("crab_layernorm"):
+        _l.check(_l.load().crab_layernorm(_vp(x), _i(x.stride(0)), _vp(gamma), _vp(beta), _vp(out), _i(out.stride(0)),
+                                          _i(x.shape[0]), _i(x.shape[1]), C.c_float(eps), _stream()), "crab_layernorm")
     count_launches(1)
     return out
 
@@ -109,8 +173,9 @@ def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float, out: Optional[torc
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16 and gamma.dtype == torch.float32
     if out is None:
         out = torch.empty((x.shape[0], x.shape[1]), device=x.device, dtype=torch.bfloat16)
-    _l.check(_l.load().crab_rmsnorm(_vp(x), _i(x.stride(0)), _vp(gamma), _vp(out), _i(out.stride(0)), _i(x.shape[0]),
-                                    _i(x.shape[1]), C.c_float(eps), _stream()), "crab_rmsnorm")
+    with _timed("crab_rmsnorm"):
+        _l.check(_l.load().crab_rmsnorm(_vp(x), _i(x.stride(0)), _vp(gamma), _vp(out), _i(out.stride(0)), _i(x.shape[0]),
+                                        _i(x.shape[1]), C.c_float(eps), _stream()), "crab_rmsnorm")
     count_launches(1)
     return out
 
@@ -130,9 +195,10 @@ def rope_kv_append(qkv: torch.Tensor, cos_sin: torch.Tensor, k_cache: torch.Tens
     assert cos_sin.shape[1] == head_dim and k_cache.shape[1] == KVH and k_cache.shape[3] == head_dim
     ctx_max = k_cache.shape[2]
     assert past_dev is not None or cos_sin.shape[0] >= past + S
-    _l.check(_l.load().crab_rope_kv_append(_vp(qkv), _i(qkv.stride(0)), _vp(cos_sin), _vp(k_cache), _vp(v_cache), _i(B),
-                                           _i(S), _i(H), _i(KVH), _i(head_dim), _i(ctx_max), _vp(past_dev), _i(past),
-                                           _stream()), "crab_rope_kv_append")
+    with _timed("crab_rope_kv_append"):
+        _l.check(_l.load().crab_rope_kv_append(_vp(qkv), _i(qkv.stride(0)), _vp(cos_sin), _vp(k_cache), _vp(v_cache), _i(B),
+                                               _i(S), _i(H), _i(KVH), _i(head_dim), _i(ctx_max), _vp(past_dev), _i(past),
+                                               _stream()), "crab_rope_kv_append")
     count_launches(1)
 
 
@@ -148,7 +214,8 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
                     o_bs=o_strides[0], o_rs=o_strides[1], o_hs=o_strides[2],
                     B=B, H=H, KVH=KVH, Sq=Sq, Sk=Sk, head_dim=head_dim, scale=scale, causal=int(causal),
                     gate=_ptr(gate), bias_table=_ptr(bias_table))
-    _l.check(_l.load().crab_flash_attn(C.byref(a), _stream()), "crab_flash_attn")
+    with _timed("crab_flash_attn"):
+        _l.check(_l.load().crab_flash_attn(C.byref(a), _stream()), "crab_flash_attn")
     count_launches(1)
     return out
 
@@ -161,9 +228,10 @@ def attn_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, o
     ctx_max = k_cache.shape[2]
     if nsplit > 1 and workspace is None:
         workspace = torch.empty(B * H * nsplit * (head_dim + 2), device=q.device, dtype=torch.float32)
-    _l.check(_l.load().crab_attn_decode(_vp(q), _i(q.stride(0)), _vp(k_cache), _vp(v_cache), _vp(out), _i(out.stride(0)),
-                                        _vp(workspace), _i(B), _i(H), _i(KVH), _i(head_dim), _i(ctx_max), _i(nsplit),
-                                        _vp(len_dev), _i(length), C.c_float(scale), _stream()), "crab_attn_decode")
+    with _timed("crab_attn_decode"):
+        _l.check(_l.load().crab_attn_decode(_vp(q), _i(q.stride(0)), _vp(k_cache), _vp(v_cache), _vp(out), _i(out.stride(0)),
+                                            _vp(workspace), _i(B), _i(H), _i(KVH), _i(head_dim), _i(ctx_max), _i(nsplit),
+                                            _vp(len_dev), _i(length), C.c_float(scale), _stream()), "crab_attn_decode")
     count_launches(2 if nsplit > 1 else 1)
     return out
 
@@ -174,8 +242,9 @@ def gather_rows(src: torch.Tensor, dst: torch.Tensor, n: int, cols: int, src_row
     assert src.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16 and src.stride(-1) == 1 and dst.stride(-1) == 1
     for r in (src_rows, dst_rows):
         assert r is None or (r.dtype == torch.int64 and r.is_contiguous() and r.numel() >= n)
-    _l.check(_l.load().crab_gather_rows(_vp(src), _i(src.stride(-2)), _vp(src_rows), _vp(dst), _i(dst.stride(-2)),
-                                        _vp(dst_rows), _i(n), _i(cols), _stream()), "crab_gather_rows")
+    with _timed("crab_gather_rows"):
+        _l.check(_l.load().crab_gather_rows(_vp(src), _i(src.stride(-2)), _vp(src_rows), _vp(dst), _i(dst.stride(-2)),
+                                            _vp(dst_rows), _i(n), _i(cols), _stream()), "crab_gather_rows")
     count_launches(1)
 
 
@@ -183,7 +252,8 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     _req_cuda(src)
     assert src.dtype == torch.float32 and src.is_contiguous()
     out = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
-    _l.check(_l.load().crab_cast_f32_bf16(_vp(src), _vp(out), C.c_int64(src.numel()), _stream()), "crab_cast_f32_bf16")
+    with _timed("crab_cast_f32_bf16"):
+        _l.check(_l.load().crab_cast_f32_bf16(_vp(src), _vp(out), C.c_int64(src.numel()), _stream()), "crab_cast_f32_bf16")
     count_launches(1)
     return out
 
@@ -195,8 +265,9 @@ def patchify(images: torch.Tensor, patch: int, ld_out: int) -> torch.Tensor:
     n, c, h, w = images.shape
     rows = n * (h // patch) * (w // patch)
     out = torch.empty((rows, ld_out), device=images.device, dtype=torch.bfloat16)
-    _l.check(_l.load().crab_patchify(_vp(images), _vp(out), _i(ld_out), _i(n), _i(c), _i(h), _i(w), _i(patch), _stream()),
-             "crab_patchify")
+    with _timed("crab_patchify"):
+        _l.check(_l.load().crab_patchify(_vp(images), _vp(out), _i(ld_out), _i(n), _i(c), _i(h), _i(w), _i(patch), _stream()),
+                 "crab_patchify")
     count_launches(1)
     return out
 
@@ -205,8 +276,9 @@ def clip_embed_ln(patch_emb, cls, pos, gamma, beta, n_img: int, tokens: int, D: 
     _req_cuda(patch_emb, cls, pos, gamma, beta)
     assert patch_emb.is_contiguous() and patch_emb.dtype == torch.bfloat16
     out = torch.empty((n_img * tokens, D), device=patch_emb.device, dtype=torch.bfloat16)
-    _l.check(_l.load().crab_clip_embed_ln(_vp(patch_emb), _vp(cls), _vp(pos), _vp(gamma), _vp(beta), _vp(out), _i(n_img),
-                                          _i(tokens), _i(D), C.c_float(eps), _stream()), "crab_clip_embed_ln")
+    with _timed("crab_clip_embed_ln"):
+        _l.check(_l.load().crab_clip_embed_ln(_vp(patch_emb), _vp(cls), _vp(pos), _vp(gamma), _vp(beta), _vp(out), _i(n_img),
+                                              _i(tokens), _i(D), C.c_float(eps), _stream()), "crab_clip_embed_ln")
     count_launches(1)
     return out
 
@@ -214,8 +286,9 @@ def clip_embed_ln(patch_emb, cls, pos, gamma, beta, n_img: int, tokens: int, D: 
 def beats_gate(q: torch.Tensor, grep_w, grep_b, grep_a, B: int, T: int, H: int) -> torch.Tensor:
     _req_cuda(q, grep_w, grep_b, grep_a)
     gate = torch.empty((B, H, T), device=q.device, dtype=torch.float32)
-    _l.check(_l.load().crab_beats_gate(_vp(q), _i(q.stride(0)), _vp(grep_w), _vp(grep_b), _vp(grep_a), _vp(gate), _i(B),
-                                       _i(T), _i(H), _stream()), "crab_beats_gate")
+    with _timed("crab_beats_gate"):
+        _l.check(_l.load().crab_beats_gate(_vp(q), _i(q.stride(0)), _vp(grep_w), _vp(grep_b), _vp(grep_a), _vp(gate), _i(B),
+                                           _i(T), _i(H), _stream()), "crab_beats_gate")
     count_launches(1)
     return gate
 
@@ -224,7 +297,8 @@ def beats_group_pack(x: torch.Tensor, B: int, T: int, Cc: int, G: int) -> torch.
     _req_cuda(x)
     assert x.is_contiguous() and x.dtype == torch.bfloat16
     out = torch.empty((G, B, T * (Cc // G)), device=x.device, dtype=torch.bfloat16)
-    _l.check(_l.load().crab_beats_group_pack(_vp(x), _vp(out), _i(B), _i(T), _i(Cc), _i(G), _stream()), "crab_beats_group_pack")
+    with _timed("crab_beats_group_pack"):
+        _l.check(_l.load().crab_beats_group_pack(_vp(x), _vp(out), _i(B), _i(T), _i(Cc), _i(G), _stream()), "crab_beats_group_pack")
     count_launches(1)
     return out
 
@@ -233,8 +307,9 @@ def beats_posconv_finish(x: torch.Tensor, conv_g: torch.Tensor, bias: torch.Tens
     _req_cuda(x, conv_g, bias)
     assert x.is_contiguous() and conv_g.is_contiguous()
     out = torch.empty((B * T, Cc), device=x.device, dtype=torch.bfloat16)
-    _l.check(_l.load().crab_beats_posconv_finish(_vp(x), _vp(conv_g), _vp(bias), _vp(out), _i(B), _i(T), _i(Cc), _i(G),
-                                                 _stream()), "crab_beats_posconv_finish")
+    with _timed("crab_beats_posconv_finish"):
+        _l.check(_l.load().crab_beats_posconv_finish(_vp(x), _vp(conv_g), _vp(bias), _vp(out), _i(B), _i(T), _i(Cc), _i(G),
+                                                     _stream()), "crab_beats_posconv_finish")
     count_launches(1)
     return out
 
@@ -244,8 +319,9 @@ def argmax(logits: torch.Tensor, V: int, out: Optional[torch.Tensor] = None) -> 
     assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
     if out is None:
         out = torch.empty((logits.shape[0],), device=logits.device, dtype=torch.int64)
-    _l.check(_l.load().crab_argmax(_vp(logits), _i(logits.stride(0)), _i(logits.shape[0]), _i(V), _vp(out), _stream()),
-             "crab_argmax")
+    with _timed("crab_argmax"):
+        _l.check(_l.load().crab_argmax(_vp(logits), _i(logits.stride(0)), _i(logits.shape[0]), _i(V), _vp(out), _stream()),
+                 "crab_argmax")
     count_launches(1)
     return out
 
@@ -253,5 +329,6 @@ def argmax(logits: torch.Tensor, V: int, out: Optional[torch.Tensor] = None) -> 
 def add_scalar_i32(p: torch.Tensor, v: int):
     _req_cuda(p)
     assert p.dtype == torch.int32
-    _l.check(_l.load().crab_add_scalar_i32(_vp(p), _i(v), _stream()), "crab_add_scalar_i32")
+    with _timed("crab_add_scalar_i32"):
+        _l.check(_l.load().crab_add_scalar_i32(_vp(p), _i(v), _stream()), "crab_add_scalar_i32")
     count_launches(1)
