@@ -263,6 +263,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
   constexpr int NSUB = 4 * KPW;      // independent softmax states per block
   __shared__ float sh_m[NSUB][G], sh_l[NSUB][G];
   __shared__ float sh_acc[NSUB][G][HD];
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / LPK, li = lane % LPK;
   const int b = blockIdx.x / p.KVH, kvh = blockIdx.x % p.KVH;
@@ -373,6 +375,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
 template <int HD>
 __global__ void attn_decode_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ o, int ldo, int H,
                                            int nsplit) {
+  pdl_trigger();
+  pdl_wait();
   const int bh = blockIdx.x;
   const int b = bh / H, h = bh % H;
   const float* w = ws + (size_t)bh * nsplit * (HD + 2);
@@ -448,17 +452,18 @@ extern "C" int crab_attn_decode(const void* q, int ldq, const void* k_cache, con
   p.nsplit = nsplit; p.len_dev = len_dev; p.len_host = len_host; p.scale = scale;
   dim3 grid(B * KVH, nsplit);
   cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
 #define CRAB_DECODE_CASE(HD_, G_) \
-  if (head_dim == HD_ && G == G_) { attn_decode_kernel<HD_, G_><<<grid, 128, 0, st>>>(p); } else
+  if (head_dim == HD_ && G == G_) { e = launch_pdl(attn_decode_kernel<HD_, G_>, grid, dim3(128), 0, st, p); } else
   CRAB_DECODE_CASE(128, 1) CRAB_DECODE_CASE(128, 2) CRAB_DECODE_CASE(128, 4) CRAB_DECODE_CASE(128, 7)
   CRAB_DECODE_CASE(128, 8) CRAB_DECODE_CASE(64, 1)
   { return set_error(CRAB_ERR_INVALID, "crab_attn_decode: unsupported head_dim=%d group=%d", head_dim, G); }
 #undef CRAB_DECODE_CASE
-  CRAB_CHECK_CUDA(cudaGetLastError());
+  CRAB_CHECK_CUDA(e);
   if (nsplit > 1) {
-    if (head_dim == 128) attn_decode_combine_kernel<128><<<B * H, 128, 0, st>>>(workspace, p.o, ldo, H, nsplit);
-    else attn_decode_combine_kernel<64><<<B * H, 64, 0, st>>>(workspace, p.o, ldo, H, nsplit);
-    CRAB_CHECK_CUDA(cudaGetLastError());
+    if (head_dim == 128) e = launch_pdl(attn_decode_combine_kernel<128>, dim3(B * H), dim3(128), 0, st, (const float*)workspace, p.o, ldo, H, nsplit);
+    else e = launch_pdl(attn_decode_combine_kernel<64>, dim3(B * H), dim3(64), 0, st, (const float*)workspace, p.o, ldo, H, nsplit);
+    CRAB_CHECK_CUDA(e);
   }
   return CRAB_OK;
 }

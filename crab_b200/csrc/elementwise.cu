@@ -35,6 +35,8 @@ template <bool RMS, int VPT /* 8-element vectors per thread */>
 __global__ void __launch_bounds__(256) norm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                                    __nv_bfloat16* __restrict__ y, int ldy, int rows, int cols, float eps) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const int row = blockIdx.x;
   const __nv_bfloat16* xr = x + (size_t)row * ldx;
@@ -102,12 +104,13 @@ static int launch_norm(const void* x, int ldx, const float* gamma, const float* 
   const int nvec = cols / 8;
   auto xx = reinterpret_cast<const __nv_bfloat16*>(x);
   auto yy = reinterpret_cast<__nv_bfloat16*>(y);
-  if (nvec <= 128) norm_kernel<RMS, 1><<<rows, 128, 0, st>>>(xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
-  else if (nvec <= 256) norm_kernel<RMS, 1><<<rows, 256, 0, st>>>(xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
-  else if (nvec <= 512) norm_kernel<RMS, 2><<<rows, 256, 0, st>>>(xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
-  else if (nvec <= 1024) norm_kernel<RMS, 4><<<rows, 256, 0, st>>>(xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
-  else norm_kernel<RMS, 8><<<rows, 256, 0, st>>>(xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
-  CRAB_CHECK_CUDA(cudaGetLastError());
+  cudaError_t e;
+  if (nvec <= 128) e = launch_pdl(norm_kernel<RMS, 1>, dim3(rows), dim3(128), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else if (nvec <= 256) e = launch_pdl(norm_kernel<RMS, 1>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else if (nvec <= 512) e = launch_pdl(norm_kernel<RMS, 2>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else if (nvec <= 1024) e = launch_pdl(norm_kernel<RMS, 4>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else e = launch_pdl(norm_kernel<RMS, 8>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  CRAB_CHECK_CUDA(e);
   return CRAB_OK;
 }
 
@@ -128,45 +131,51 @@ __global__ void rope_table_kernel(float* cs, int max_pos, int half, double theta
 }
 
 // qkv: [B*S, ldq] rows hold [q (H*hd) | k (KV*hd) | v (KV*hd)].  q is rotated in place; rotated k and v go to the
-// cache [B, KV, ctx_max, hd] at position past + s.  One warp per (row, head); hd in {64, 128}.
+// cache [B, KV, ctx_max, hd] at position past + s.  One thread per (row, head, 8-element chunk of the low half): it
+// owns the pair of 16-byte vectors (j..j+7, j+hd/2..j+hd/2+7), so every access is a 128-bit load/store.
 template <int HD>
-__global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, int ldq, const float* __restrict__ cs,
-                               __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int B, int S, int H,
-                               int KV, int ctx_max, const int* __restrict__ past_dev, int past_host) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, int ldq, const float* __restrict__ cs,
+                                                      __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int B, int S,
+                                                      int H, int KV, int ctx_max, const int* __restrict__ past_dev,
+                                                      int past_host) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int half = HD / 2;
+  constexpr int CPH = half / 8;  // chunks per head
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int heads_total = H + 2 * KV;
-  if (warp >= B * S * heads_total) return;
-  const int row = warp / heads_total, hh = warp % heads_total;
+  if (tid >= (long long)B * S * heads_total * CPH) return;
+  const int ch = (int)(tid % CPH);
+  const int hh = (int)((tid / CPH) % heads_total);
+  const int row = (int)(tid / ((long long)CPH * heads_total));
   const int b = row / S, s = row % S;
-  const int past = past_dev ? *past_dev : past_host;
-  const int pos = past + s;
-  __nv_bfloat16* src = qkv + (size_t)row * ldq + (size_t)hh * HD;
-  constexpr int EPL = HD / 32;  // elements per lane in each half... lane handles EPL/2 pairs (j, j + HD/2)
+  const int pos = (past_dev ? *past_dev : past_host) + s;
+  __nv_bfloat16* src = qkv + (size_t)row * ldq + (size_t)hh * HD + ch * 8;
+  const uint4 qlo = *reinterpret_cast<const uint4*>(src);
+  const uint4 qhi = *reinterpret_cast<const uint4*>(src + half);
   if (hh < H + KV) {
-    // rotate: out[j] = x[j] c[j] - x[j+h] s[j];  out[j+h] = x[j+h] c[j] + x[j] s[j]
-    constexpr int half = HD / 2;
-    constexpr int PPL = half / 32;  // pairs per lane (1 for 64, 2 for 128)
-    float lo[PPL], hi[PPL];
+    float lo[8], hi[8], o_lo[8], o_hi[8];
+    unpack8(qlo, lo);
+    unpack8(qhi, hi);
+    const float* cp = cs + (size_t)pos * HD + ch * 8;
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(cp)), c1 = __ldg(reinterpret_cast<const float4*>(cp) + 1);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(cp + half)), s1 = __ldg(reinterpret_cast<const float4*>(cp + half) + 1);
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-    for (int p = 0; p < PPL; ++p) {
-      const int j = lane * PPL + p;
-      lo[p] = __bfloat162float(src[j]);
-      hi[p] = __bfloat162float(src[j + half]);
+    for (int j = 0; j < 8; ++j) {
+      // out[j] = x[j] c[j] - x[j+h] s[j];  out[j+h] = x[j+h] c[j] + x[j] s[j]   (rotate_half, modeling_llama.py:204-236)
+      o_lo[j] = lo[j] * c[j] - hi[j] * sn[j];
+      o_hi[j] = hi[j] * c[j] + lo[j] * sn[j];
     }
     __nv_bfloat16* dst = src;
-    if (hh >= H) dst = kc + (((size_t)b * KV + (hh - H)) * ctx_max + pos) * HD;
-#pragma unroll
-    for (int p = 0; p < PPL; ++p) {
-      const int j = lane * PPL + p;
-      const float c = cs[(size_t)pos * HD + j], sn = cs[(size_t)pos * HD + half + j];
-      dst[j] = __float2bfloat16_rn(lo[p] * c - hi[p] * sn);
-      dst[j + half] = __float2bfloat16_rn(hi[p] * c + lo[p] * sn);
-    }
+    if (hh >= H) dst = kc + (((size_t)b * KV + (hh - H)) * ctx_max + pos) * HD + ch * 8;
+    *reinterpret_cast<uint4*>(dst) = pack8(o_lo);
+    *reinterpret_cast<uint4*>(dst + half) = pack8(o_hi);
   } else {
-    __nv_bfloat16* dst = vc + (((size_t)b * KV + (hh - H - KV)) * ctx_max + pos) * HD;
-#pragma unroll
-    for (int p = 0; p < EPL; ++p) dst[lane * EPL + p] = src[lane * EPL + p];
+    __nv_bfloat16* dst = vc + (((size_t)b * KV + (hh - H - KV)) * ctx_max + pos) * HD + ch * 8;
+    *reinterpret_cast<uint4*>(dst) = qlo;
+    *reinterpret_cast<uint4*>(dst + half) = qhi;
   }
 }
 
@@ -177,6 +186,8 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, int ldq, const f
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, int lds, const int64_t* __restrict__ src_rows,
                                    __nv_bfloat16* __restrict__ dst, int ldd, const int64_t* __restrict__ dst_rows,
                                    int n, int cols) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x;
   const int64_t sr = src_rows ? src_rows[i] : i;
   const int64_t dr = dst_rows ? dst_rows[i] : i;
@@ -319,6 +330,8 @@ __global__ void beats_posconv_finish_kernel(const __nv_bfloat16* __restrict__ x,
 // ----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ logits, int ld, int V,
                                                      int64_t* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sv[8];
   __shared__ int si[8];
   const float* r = logits + (size_t)blockIdx.x * ld;
@@ -350,8 +363,110 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ l
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Small-M (decode) row kernel: optional RMSNorm, then the hyper-LoRA pre-pass for up to 3 linears sharing the row:
+//   t = y . [R_g ; A_g]^T  (11 outputs per linear),  z[g*24 + i*8 + j] = scale * softmax(t[g,0:3])_i * t[g,3+j]
+// One block per row; the row stays in registers.  Replaces a norm launch + a 1-CTA skinny GEMM per linear group
+// (peft_hyper/tuners/lora.py:344-350; models/modeling_llama.py:103-117).
+// ----------------------------------------------------------------------------------------------------------------
+template <bool NORM, int VPT>
+__global__ void __launch_bounds__(256) row_loraz_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                        const float* __restrict__ gamma, float eps,
+                                                        __nv_bfloat16* __restrict__ y, int ldy,
+                                                        const __nv_bfloat16* __restrict__ ra, int ldra, int groups,
+                                                        __nv_bfloat16* __restrict__ z, int ldz, float scale, int cols) {
+  // grid = (rows, max(groups, 1)): block (row, g) owns the 11 outputs of linear g; the norm is recomputed per block
+  // (8 KB row read) and written by the g == 0 block only.
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float sh[32];
+  __shared__ float red[8][11];
+  __shared__ float tot[11];
+  const int row = blockIdx.x, grp = blockIdx.y;
+  const int nvec = cols >> 3;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const __nv_bfloat16* xr = x + (size_t)row * ldx;
+  float v[VPT][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vi = threadIdx.x + i * 256;
+    if (vi < nvec) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + vi), v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+  if (NORM) {
+    const float rstd = rsqrtf(block_sum(ss, sh) / cols + eps);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int vi = threadIdx.x + i * 256;
+      if (vi < nvec) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // same two roundings as norm_kernel<RMS>; the GEMM then reads these bf16 values
+          v[i][j] = __bfloat162float(__float2bfloat16_rn(g[j] * __bfloat162float(__float2bfloat16_rn(v[i][j] * rstd))));
+        if (grp == 0) *(reinterpret_cast<uint4*>(y + (size_t)row * ldy) + vi) = pack8(v[i]);
+      }
+    }
+  }
+  if (groups == 0) return;
+  const __nv_bfloat16* rg = ra + (size_t)grp * 11 * ldra;
+  float acc[11];
+#pragma unroll
+  for (int o = 0; o < 11; ++o) acc[o] = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vi = threadIdx.x + i * 256;
+    if (vi < nvec) {
+      uint4 q[11];
+#pragma unroll
+      for (int o = 0; o < 11; ++o) q[o] = __ldg(reinterpret_cast<const uint4*>(rg + (size_t)o * ldra) + vi);  // 11 loads in flight
+#pragma unroll
+      for (int o = 0; o < 11; ++o) {
+        float rf[8];
+        unpack8(q[o], rf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o] += v[i][j] * rf[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 11; ++o) {
+    acc[o] = warp_sum(acc[o]);
+    if (l == 0) red[w][o] = acc[o];
+  }
+  __syncthreads();
+  if (threadIdx.x < 11) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 24) {
+    const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+    const float l0 = tot[0], l1 = tot[1], l2 = tot[2];
+    const float mx = fmaxf(l0, fmaxf(l1, l2));
+    const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx), e2 = __expf(l2 - mx);
+    const float ri = (i == 0 ? e0 : (i == 1 ? e1 : e2)) / (e0 + e1 + e2);
+    z[(size_t)row * ldz + grp * 24 + threadIdx.x] = __float2bfloat16_rn(scale * ri * tot[3 + j]);
+  }
+}
+
 // device-side scalar increment (decode position counter inside a CUDA graph)
-__global__ void add_scalar_kernel(int* p, int v) { *p += v; }
+__global__ void add_scalar_kernel(int* p, int v) {
+  pdl_trigger();
+  pdl_wait();
+  *p += v;
+}
 
 }  // namespace crab
 
@@ -383,17 +498,17 @@ extern "C" int crab_rope_kv_append(void* qkv, int ldq, const float* cos_sin, voi
   CRAB_REQUIRE(qkv && cos_sin && k_cache && v_cache, "crab_rope_kv_append: null pointer");
   CRAB_REQUIRE(head_dim == 64 || head_dim == 128, "crab_rope_kv_append: head_dim must be 64 or 128 (got %d)", head_dim);
   CRAB_REQUIRE(past_dev != nullptr || past_host + S <= ctx_max, "crab_rope_kv_append: past+S exceeds ctx_max");
-  const long warps = (long)B * S * (H + 2 * KV);
-  if (warps == 0) return CRAB_OK;
-  const int blocks = (int)((warps * 32 + 255) / 256);
+  CRAB_REQUIRE(ldq % 8 == 0 && ((uintptr_t)qkv % 16 == 0), "crab_rope_kv_append: qkv must be 16-byte aligned with ldq %% 8 == 0");
+  const long long threads = (long long)B * S * (H + 2 * KV) * (head_dim / 16);
+  if (threads == 0) return CRAB_OK;
+  const unsigned blocks = (unsigned)((threads + 255) / 256);
   auto q = reinterpret_cast<__nv_bfloat16*>(qkv);
   auto kc = reinterpret_cast<__nv_bfloat16*>(k_cache);
   auto vc = reinterpret_cast<__nv_bfloat16*>(v_cache);
   if (head_dim == 128)
-    rope_kv_kernel<128><<<blocks, 256, 0, (cudaStream_t)stream>>>(q, ldq, cos_sin, kc, vc, B, S, H, KV, ctx_max, past_dev, past_host);
+    CRAB_CHECK_CUDA(launch_pdl(rope_kv_kernel<128>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, q, ldq, cos_sin, kc, vc, B, S, H, KV, ctx_max, past_dev, past_host));
   else
-    rope_kv_kernel<64><<<blocks, 256, 0, (cudaStream_t)stream>>>(q, ldq, cos_sin, kc, vc, B, S, H, KV, ctx_max, past_dev, past_host);
-  CRAB_CHECK_CUDA(cudaGetLastError());
+    CRAB_CHECK_CUDA(launch_pdl(rope_kv_kernel<64>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, q, ldq, cos_sin, kc, vc, B, S, H, KV, ctx_max, past_dev, past_host));
   return CRAB_OK;
 }
 
@@ -402,9 +517,9 @@ extern "C" int crab_gather_rows(const void* src, int lds, const int64_t* src_row
   CRAB_REQUIRE(src && dst, "crab_gather_rows: null pointer");
   CRAB_REQUIRE(cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "crab_gather_rows: cols/ld must be multiples of 8");
   if (n <= 0) return CRAB_OK;
-  gather_rows_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds, src_rows,
-                                                         reinterpret_cast<__nv_bfloat16*>(dst), ldd, dst_rows, n, cols);
-  CRAB_CHECK_CUDA(cudaGetLastError());
+  CRAB_CHECK_CUDA(launch_pdl(gather_rows_kernel, dim3(n), dim3(128), 0, (cudaStream_t)stream,
+                             reinterpret_cast<const __nv_bfloat16*>(src), lds, src_rows,
+                             reinterpret_cast<__nv_bfloat16*>(dst), ldd, dst_rows, n, cols));
   return CRAB_OK;
 }
 
@@ -476,14 +591,43 @@ extern "C" int crab_beats_posconv_finish(const void* x, const void* conv_g, cons
 extern "C" int crab_argmax(const float* logits, int ld, int rows, int V, int64_t* out, void* stream) {
   CRAB_REQUIRE(logits && out && V > 0, "crab_argmax: bad args");
   if (rows <= 0) return CRAB_OK;
-  argmax_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(logits, ld, V, out);
-  CRAB_CHECK_CUDA(cudaGetLastError());
+  CRAB_CHECK_CUDA(launch_pdl(argmax_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, logits, ld, V, out));
+  return CRAB_OK;
+}
+
+
+extern "C" int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, float eps, void* y, int ldy,
+                                   const void* ra, int ldra, int groups, void* z, int ldz, float scale, int rows,
+                                   int cols, void* stream) {
+  CRAB_REQUIRE(x != nullptr, "crab_row_norm_loraz: null x");
+  CRAB_REQUIRE(cols % 8 == 0 && ldx % 8 == 0 && cols <= 8 * 256 * 8, "crab_row_norm_loraz: cols=%d unsupported", cols);
+  CRAB_REQUIRE(groups >= 0 && groups <= 3, "crab_row_norm_loraz: groups must be 0..3");
+  CRAB_REQUIRE(groups == 0 || (ra && z && ldra % 8 == 0), "crab_row_norm_loraz: ra/z needed when groups > 0");
+  CRAB_REQUIRE((gamma == nullptr) == (y == nullptr), "crab_row_norm_loraz: gamma and y go together");
+  if (gamma) CRAB_REQUIRE(ldy % 8 == 0, "crab_row_norm_loraz: ldy alignment");
+  if (rows <= 0) return CRAB_OK;
+  const int nvec = cols / 8;
+  const int vpt = (nvec + 255) / 256;
+  auto xx = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto yy = reinterpret_cast<__nv_bfloat16*>(y);
+  auto rr = reinterpret_cast<const __nv_bfloat16*>(ra);
+  auto zz = reinterpret_cast<__nv_bfloat16*>(z);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+#define CRAB_ROW_CASE(V)                                                                                              \
+  if (vpt <= V) {                                                                                                     \
+    const dim3 grid(rows, groups > 0 ? groups : 1);                                                                   \
+    if (gamma) e = launch_pdl(row_loraz_kernel<true, V>, grid, dim3(256), 0, st, xx, ldx, gamma, eps, yy, ldy, rr, ldra, groups, zz, ldz, scale, cols); \
+    else e = launch_pdl(row_loraz_kernel<false, V>, grid, dim3(256), 0, st, xx, ldx, gamma, eps, yy, ldy, rr, ldra, groups, zz, ldz, scale, cols);      \
+  } else
+  CRAB_ROW_CASE(2) CRAB_ROW_CASE(4) CRAB_ROW_CASE(8) { return set_error(CRAB_ERR_INVALID, "crab_row_norm_loraz: cols too large"); }
+#undef CRAB_ROW_CASE
+  CRAB_CHECK_CUDA(e);
   return CRAB_OK;
 }
 
 extern "C" int crab_add_scalar_i32(int* p, int v, void* stream) {
   CRAB_REQUIRE(p != nullptr, "crab_add_scalar_i32: null pointer");
-  add_scalar_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p, v);
-  CRAB_CHECK_CUDA(cudaGetLastError());
+  CRAB_CHECK_CUDA(launch_pdl(add_scalar_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, p, v));
   return CRAB_OK;
 }

@@ -1,5 +1,6 @@
 // Error reporting, device probe and TMA tensor-map encoding for the C ABI.
 #include "host_common.h"
+#include <stdlib.h>
 
 namespace crab {
 
@@ -27,6 +28,15 @@ int sm_count() {
       cached = 148;
   }
   return cached;
+}
+
+static int g_pdl = -1;
+int pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("CRAB_PDL");
+    g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -69,6 +79,11 @@ int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint6
 extern "C" const char* crab_last_error(void) { return crab::last_error_buf(); }
 
 extern "C" int crab_version(void) { return 1; }
+
+extern "C" int crab_set_pdl(int on) {
+  crab::g_pdl = on ? 1 : 0;
+  return CRAB_OK;
+}
 
 extern "C" int crab_init(int dev) {
   using namespace crab;

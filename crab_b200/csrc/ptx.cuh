@@ -173,6 +173,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Kernels of the decode chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: `pdl_trigger` lets the next kernel's CTAs become resident (and,
+// for the weight-streaming GEMM, prefetch weights) while this one still runs; `pdl_wait` blocks until every earlier
+// grid has completed and its writes are visible.  Every PDL kernel calls pdl_wait before touching any buffer another
+// kernel writes, so completion is transitive along the chain.  Both are no-ops for a normal launch.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -586,11 +586,18 @@ class CrabEngine:
         at = self._buf(tag + "_attn", (M, nq + self.EXT_O), zero=True)
         hh = self._buf(tag + "_h", (M, F + self.EXT_D), zero=True)
         ctx = self.cfg.max_ctx
+        skinny = (S == 1 and len_dev is not None and M <= 32)  # decode step: weight-streaming kernels
+        sc = self.scaling
         for li, L in enumerate(self.layers):
-            ops.rmsnorm(x, L["ln1"], c.eps, out=xn[:, :D])
-            if self.lora:
-                ops.gemm(xn[:, :D], L["ra_qkv"], act=ops.ACT_LORA_Z, out_scale=self.scaling, out=xn[:, D:D + 72])
-            ops.gemm(xn, L["wqkv"], bias=L["bqkv"], out=qkv, k=D + (self.EXT_QKV if self.lora else 0))
+            if skinny:
+                ops.row_norm_loraz(x, gamma=L["ln1"], eps=c.eps, y=xn[:, :D], ra=L.get("ra_qkv"), groups=3 if self.lora else 0,
+                                   z=xn[:, D:] if self.lora else None, scale=sc)
+                ops.gemm_skinny(xn, L["wqkv"], bias=L["bqkv"], out=qkv, k=D + (self.EXT_QKV if self.lora else 0))
+            else:
+                ops.rmsnorm(x, L["ln1"], c.eps, out=xn[:, :D])
+                if self.lora:
+                    ops.gemm(xn[:, :D], L["ra_qkv"], act=ops.ACT_LORA_Z, out_scale=sc, out=xn[:, D:D + 72])
+                ops.gemm(xn, L["wqkv"], bias=L["bqkv"], out=qkv, k=D + (self.EXT_QKV if self.lora else 0))
             ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, S, H, KV, hd, past=past, past_dev=past_dev)
             if S == 1 and len_dev is not None:
                 ops.attn_decode(qkv, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV, head_dim=hd,
@@ -600,23 +607,37 @@ class CrabEngine:
                                q_strides=(S * (nq + 2 * nk), nq + 2 * nk, hd), k_strides=(KV * ctx * hd, hd, ctx * hd),
                                v_strides=(KV * ctx * hd, hd, ctx * hd), o_strides=(S * (nq + self.EXT_O), nq + self.EXT_O, hd),
                                scale=1 / math.sqrt(hd), causal=True)
-            if self.lora:
-                ops.gemm(at[:, :nq], L["ra_o"], act=ops.ACT_LORA_Z, out_scale=self.scaling, out=at[:, nq:nq + 24])
-            ops.gemm(at, L["wo"], residual=x, out=x, k=nq + (self.EXT_O if self.lora else 0))
-            ops.rmsnorm(x, L["ln2"], c.eps, out=xn[:, :D])
-            if self.lora:
-                ops.gemm(xn[:, :D], L["ra_gu"], act=ops.ACT_LORA_Z, out_scale=self.scaling, out=xn[:, D:D + 48])
-            ops.gemm(xn, L["wgu"], act=ops.ACT_SWIGLU, out=hh[:, :F], k=D + (self.EXT_GU if self.lora else 0))
-            if self.lora:
-                ops.gemm(hh[:, :F], L["ra_d"], act=ops.ACT_LORA_Z, out_scale=self.scaling, out=hh[:, F:F + 24])
-            ops.gemm(hh, L["wd"], residual=x, out=x, k=F + (self.EXT_D if self.lora else 0))
+            if skinny:
+                if self.lora:
+                    ops.row_norm_loraz(at[:, :nq], ra=L["ra_o"], groups=1, z=at[:, nq:], scale=sc)
+                ops.gemm_skinny(at, L["wo"], residual=x, out=x, k=nq + (self.EXT_O if self.lora else 0))
+                ops.row_norm_loraz(x, gamma=L["ln2"], eps=c.eps, y=xn[:, :D], ra=L.get("ra_gu"), groups=2 if self.lora else 0,
+                                   z=xn[:, D:] if self.lora else None, scale=sc)
+                ops.gemm_skinny(xn, L["wgu"], act=ops.ACT_SWIGLU, out=hh[:, :F], k=D + (self.EXT_GU if self.lora else 0))
+                if self.lora:
+                    ops.row_norm_loraz(hh[:, :F], ra=L["ra_d"], groups=1, z=hh[:, F:], scale=sc)
+                ops.gemm_skinny(hh, L["wd"], residual=x, out=x, k=F + (self.EXT_D if self.lora else 0))
+            else:
+                if self.lora:
+                    ops.gemm(at[:, :nq], L["ra_o"], act=ops.ACT_LORA_Z, out_scale=sc, out=at[:, nq:nq + 24])
+                ops.gemm(at, L["wo"], residual=x, out=x, k=nq + (self.EXT_O if self.lora else 0))
+                ops.rmsnorm(x, L["ln2"], c.eps, out=xn[:, :D])
+                if self.lora:
+                    ops.gemm(xn[:, :D], L["ra_gu"], act=ops.ACT_LORA_Z, out_scale=sc, out=xn[:, D:D + 48])
+                ops.gemm(xn, L["wgu"], act=ops.ACT_SWIGLU, out=hh[:, :F], k=D + (self.EXT_GU if self.lora else 0))
+                if self.lora:
+                    ops.gemm(hh[:, :F], L["ra_d"], act=ops.ACT_LORA_Z, out_scale=sc, out=hh[:, F:F + 24])
+                ops.gemm(hh, L["wd"], residual=x, out=x, k=F + (self.EXT_D if self.lora else 0))
         return x
 
     def _head(self, x_last: torch.Tensor, logits: torch.Tensor, next_ids: torch.Tensor):
         """final RMSNorm -> lm_head (fp32 logits) -> greedy arg-max."""
         c = self.cfg.decoder
         hn = ops.rmsnorm(x_last, self.final_norm, c.eps, out=self._buf("head_hn", tuple(x_last.shape)))
-        ops.gemm(hn, self.lm_head, out=logits)
+        if x_last.shape[0] <= 32:
+            ops.gemm_skinny(hn, self.lm_head, out=logits)
+        else:
+            ops.gemm(hn, self.lm_head, out=logits)
         ops.argmax(logits, self.vocab, out=next_ids)
 
     def prefill(self, inputs_embeds: torch.Tensor):

@@ -332,3 +332,60 @@ def add_scalar_i32(p: torch.Tensor, v: int):
     with _timed("crab_add_scalar_i32"):
         _l.check(_l.load().crab_add_scalar_i32(_vp(p), _i(v), _stream()), "crab_add_scalar_i32")
     count_launches(1)
+
+
+# ---- decode-step kernels ------------------------------------------------------------------------------------------
+_SKINNY_WS_BYTES = 32 << 20
+_SKINNY_COUNTERS = 2048
+_skinny_bufs = {}
+
+
+def _skinny_scratch(device):
+    """Split-K workspace + ticket counters, shared by all skinny GEMMs on a device (they run in stream order).
+    Allocated once so the pointers captured in CUDA graphs stay valid."""
+    key = (device.type, device.index)
+    if key not in _skinny_bufs:
+        _skinny_bufs[key] = (torch.empty(_SKINNY_WS_BYTES // 4, device=device, dtype=torch.float32),
+                             torch.zeros(_SKINNY_COUNTERS, device=device, dtype=torch.int32))
+    return _skinny_bufs[key]
+
+
+def gemm_skinny(x: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+                residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
+                out_dtype: torch.dtype = torch.bfloat16, k: Optional[int] = None, n: Optional[int] = None,
+                splits: int = 0) -> torch.Tensor:
+    """out[M, N'] = epilogue(x[M<=32, K] @ w[N, K]^T): the decode-step weight-streaming GEMM (swap-AB, split-K)."""
+    _req_cuda(x, w, bias, residual, out)
+    assert x.dim() == 2 and w.dim() == 2 and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    M = x.shape[0]
+    K = k if k is not None else x.shape[1]
+    N = n if n is not None else w.shape[0]
+    n_out = N // 2 if act == ACT_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), device=x.device, dtype=out_dtype)
+    ws, cnt = _skinny_scratch(x.device)
+    args = _l.SkinnyArgs(X=_ptr(x), W=_ptr(w), C=_ptr(out), bias=_ptr(bias), residual=_ptr(residual),
+                         workspace=_ptr(ws), counters=_ptr(cnt), workspace_bytes=ws.numel() * 4, n_counters=cnt.numel(),
+                         M=M, N=N, K=K, ldx=x.stride(0), ldw=w.stride(0), ldc=out.stride(0),
+                         ldr=(residual.stride(0) if residual is not None else 0), act=act,
+                         out_dtype=(BF16 if out.dtype == torch.bfloat16 else F32), splits=splits)
+    with _timed("gemm_skinny_tcgen05", 2.0 * M * N * K, 2.0 * (M * K + N * K) + out.element_size() * M * n_out):
+        _l.check(_l.load().crab_gemm_skinny_bf16(C.byref(args), _stream()), "crab_gemm_skinny_bf16")
+    count_launches(1)
+    return out
+
+
+def row_norm_loraz(x: torch.Tensor, *, gamma: Optional[torch.Tensor] = None, eps: float = 0.0,
+                   y: Optional[torch.Tensor] = None, ra: Optional[torch.Tensor] = None, groups: int = 0,
+                   z: Optional[torch.Tensor] = None, scale: float = 1.0):
+    """Per-row (decode) RMSNorm (optional) + hyper-LoRA router/A pre-pass writing the 24*groups z columns."""
+    _req_cuda(x, gamma, y, ra, z)
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    with _timed("crab_row_norm_loraz"):
+        _l.check(_l.load().crab_row_norm_loraz(_vp(x), _i(x.stride(0)), _vp(gamma), C.c_float(eps), _vp(y),
+                                               _i(y.stride(0) if y is not None else 0), _vp(ra),
+                                               _i(ra.stride(0) if ra is not None else 0), _i(groups), _vp(z),
+                                               _i(z.stride(0) if z is not None else 0), C.c_float(scale), _i(rows), _i(cols),
+                                               _stream()), "crab_row_norm_loraz")
+    count_launches(1)

@@ -31,6 +31,8 @@ const char* crab_last_error(void);
 /* Library / device probe: returns CRAB_OK when device `dev` is compute capability 10.x. */
 int crab_init(int dev);
 int crab_version(void);
+/* Programmatic dependent launch for the decode-chain kernels (default on; env CRAB_PDL=0 disables). */
+int crab_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Dense linear:  C[M,N] = epilogue( A[M,K] . B[N,K]^T )       (tcgen05 + TMEM + TMA, persistent, warp-specialised)
@@ -146,6 +148,35 @@ int crab_beats_posconv_finish(const void* x, const void* conv_g, const float* bi
                               int G, void* stream);
 int crab_argmax(const float* logits, int ld, int rows, int V, int64_t* out, void* stream);
 int crab_add_scalar_i32(int* p, int v, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Decode-step (M <= 32 rows) kernels
+ * crab_gemm_skinny_bf16 replaces: the same nn.Linear / hyper-LoRA linears at q_len == 1 (HF generate's per-token
+ *           forward, models/unified_llama.py:125-127): swap-AB tcgen05 weight streaming, split-K with a deterministic
+ *           last-CTA reduction.  crab_gemm_skinny_plan returns the split count, workspace size and ticket-counter
+ *           count for (N, K); `counters` must be zero before the first launch (the kernel re-zeroes them).
+ * crab_row_norm_loraz replaces: LlamaRMSNorm + lora_route / lora_A projections + fp32 router softmax for up to three
+ *           linears sharing one input row (peft_hyper/tuners/lora.py:344-350).  gamma/y NULL = no norm (LoRA only).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct crab_skinny_args {
+  const void* X;        /* bf16 [M, ldx], M <= 32 */
+  const void* W;        /* bf16 [N, ldw] */
+  void* C;              /* [M, ldc] bf16 or fp32 */
+  const float* bias;    /* fp32 [N] or NULL */
+  const void* residual; /* bf16 [M, ldr] or NULL */
+  float* workspace;
+  int32_t* counters;
+  int64_t workspace_bytes;
+  int32_t n_counters;
+  int32_t M, N, K, ldx, ldw, ldc, ldr;
+  int32_t act;          /* CRAB_ACT_NONE or CRAB_ACT_SWIGLU */
+  int32_t out_dtype;
+  int32_t splits;       /* 0 = auto */
+} crab_skinny_args;
+int crab_gemm_skinny_plan(int N, int K, int* splits, int64_t* workspace_bytes, int* n_counters);
+int crab_gemm_skinny_bf16(const crab_skinny_args* args, void* stream);
+int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, float eps, void* y, int ldy, const void* ra,
+                        int ldra, int groups, void* z, int ldz, float scale, int rows, int cols, void* stream);
 
 #ifdef __cplusplus
 }

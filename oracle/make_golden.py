@@ -52,6 +52,39 @@ CASES = {
 }
 
 
+QWEN_CASES = {
+    # Qwen2 backbone: q/k/v bias, grouped KV heads (4 query heads share 2 KV heads... here 4:2), rope_theta 1e6
+    "qwen_small": dict(
+        kind="qwen",
+        llama_cfg=dict(hidden_size=512, intermediate_size=768, num_hidden_layers=2, num_attention_heads=4,
+                       num_key_value_heads=2, vocab_size=352, max_position_embeddings=1024, rms_norm_eps=1e-6,
+                       rope_theta=1000000.0, tie_word_embeddings=False),
+        bs=2, seq_len=75, new_tokens=8, weight_seed=11, input_seed=5,
+    ),
+}
+
+
+@torch.no_grad()
+def run_qwen_case(name: str, case: dict) -> dict:
+    from transformers import Qwen2ForCausalLM
+
+    model = R.build_reference_qwen(qwen_cfg=case["llama_cfg"], lora=True)
+    manifest = load_synth_weights(model, case["weight_seed"])
+    g = torch.Generator(device="cpu").manual_seed(case["input_seed"])
+    emb = torch.randn(case["bs"], case["seq_len"], case["llama_cfg"]["hidden_size"], generator=g)
+    out = {"case": case, "manifest": manifest, "inputs_embeds": emb.clone()}
+    inner = model.base_model.model  # the reference's UnifiedForCausalLM (Qwen)
+    gen = Qwen2ForCausalLM.generate(inner, inputs_embeds=emb, max_new_tokens=case["new_tokens"], do_sample=False,
+                                    eos_token_id=None, pad_token_id=0, use_cache=True)
+    out["generated_ids"] = gen.clone()
+    fo = model(inputs_embeds=emb, use_cache=True, output_hidden_states=True)
+    out["prefill_last_logits"] = fo.logits[:, -1].float().clone()
+    out["hidden_states"] = [h[:, -4:].clone() for h in fo.hidden_states]
+    step = model(input_ids=gen[:, :1], past_key_values=fo.past_key_values, use_cache=True)
+    out["step1_logits"] = step.logits[:, -1].float().clone()
+    return out
+
+
 def _beats_cfg(over: dict) -> dict:
     return dict(R.BEATS_CFG_PUBLIC, **over)
 
@@ -119,10 +152,10 @@ def main():
     if not R.reference_available():
         raise SystemExit("reference checkout not found; goldens can only be regenerated in the build container")
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    for name, case in CASES.items():
+    for name, case in list(CASES.items()) + list(QWEN_CASES.items()):
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
-        out = run_case(name, case)
+        out = run_qwen_case(name, case) if case["kind"] == "qwen" else run_case(name, case)
         # keep fixtures small: fp32 tensors only of modest size
         torch.save(out, GOLDEN / f"{name}.pt")
         sz = (GOLDEN / f"{name}.pt").stat().st_size

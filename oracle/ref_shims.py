@@ -210,3 +210,25 @@ def build_reference_model(*, llama_cfg: dict, d_model: int, clip: dict, beats_cf
     model.initialize_MM_tokenizer(tok, mask_token_nums=6)
     model.eval()
     return model, tok
+
+
+def build_reference_qwen(*, qwen_cfg: dict, lora=True, dtype=torch.float32, seed=42):
+    """The reference's Qwen2 wrapper (models/unified_qwen.py) + hyper-LoRA, decoder only: its multimodal entry is stale
+    (SURVEY.md §2.1), so the contract for the Qwen backbone is forward/generate over `inputs_embeds`."""
+    install_shims()
+    torch.manual_seed(seed)
+    from transformers import Qwen2Config
+    from models.unified_qwen import UnifiedForCausalLM
+
+    cfg = Qwen2Config(**qwen_cfg)
+    cfg._attn_implementation = "eager"
+    model = UnifiedForCausalLM(cfg).to(dtype)
+    if lora:
+        from peft_hyper import LoraConfig, TaskType, get_peft_model
+
+        lcfg = LoraConfig(task_type=TaskType.CAUSAL_LM, inference_mode=False, r=8, lora_alpha=16, lora_dropout=0.05,
+                          lora_nums=3, target_modules=["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj",
+                                                       "down_proj", "up_proj"])
+        model = get_peft_model(model, lcfg)
+    model.eval()
+    return model

@@ -13,7 +13,7 @@ from helpers import GOLDEN, engine_cfg, load_golden, rel_l2
 from oracle import crab_oracle as O
 
 pytestmark = pytest.mark.gpu
-CASES = sorted(p.stem for p in GOLDEN.glob("llama_*.pt")) + sorted(p.stem for p in GOLDEN.glob("qwen_*.pt"))
+CASES = sorted(p.stem for p in GOLDEN.glob("llama_*.pt"))
 
 
 @pytest.fixture(scope="module", params=CASES)
@@ -97,3 +97,62 @@ def test_generate_end_to_end(setup):
     print(f"free-running greedy ids: {out.tolist()} vs reference {g['generated_ids'].tolist()} (match {match:.2f})")
     assert out.shape == g["generated_ids"].shape
     assert torch.equal(out[:, 0], g["generated_ids"][:, 0]) or match > 0.5
+
+
+def test_qwen_decoder_vs_reference(cuda_dev):
+    """Qwen2 backbone through the same kernels: qkv bias in the GEMM epilogue, GQA in flash / decode attention, rope
+    theta 1e6; compared with the reference's unified_qwen + peft_hyper outputs (tests/golden/qwen_small.pt)."""
+    from crab_b200 import engine as E
+    from oracle import synth
+
+    g = torch.load(GOLDEN / "qwen_small.pt", weights_only=False)
+    case = g["case"]
+    sd = O.strip_peft_prefix(synth.synth_state_dict(g["manifest"], case["weight_seed"]))
+    lc = case["llama_cfg"]
+    hd = lc["hidden_size"] // lc["num_attention_heads"]
+    dec_o = O.DecoderCfg(hidden=lc["hidden_size"], inter=lc["intermediate_size"], layers=lc["num_hidden_layers"],
+                         heads=lc["num_attention_heads"], kv_heads=lc["num_key_value_heads"], head_dim=hd,
+                         vocab=lc["vocab_size"], rope_theta=lc["rope_theta"], eps=lc["rms_norm_eps"], qkv_bias=True)
+    cfg = E.CrabConfig(decoder=E.DecoderConfig(hidden=dec_o.hidden, inter=dec_o.inter, layers=dec_o.layers, heads=dec_o.heads,
+                                               kv_heads=dec_o.kv_heads, head_dim=hd, vocab=dec_o.vocab,
+                                               rope_theta=dec_o.rope_theta, eps=dec_o.eps, qkv_bias=True), max_ctx=256)
+    eng = E.CrabEngine(sd, cfg, cuda_dev, load_encoders=False)
+    ref_ids = g["generated_ids"]
+    n_new = ref_ids.shape[1]
+    with torch.no_grad():
+        _, ref_logits = O.greedy_generate(sd, g["inputs_embeds"], dec_o, n_new, teacher_tokens=ref_ids)
+    out, logits = eng.generate_from_embeds(g["inputs_embeds"].to(cuda_dev).to(torch.bfloat16), n_new, return_logits=True,
+                                           teacher_tokens=ref_ids.to(cuda_dev))
+    logits = logits.cpu()
+    e0, e1 = rel_l2(logits[0], g["prefill_last_logits"]), rel_l2(logits[1], g["step1_logits"])
+    print(f"qwen prefill logits rel_l2={e0:.3e}; step-1 rel_l2={e1:.3e}")
+    assert e0 < 4e-2 and e1 < 4e-2
+    err = (logits - ref_logits).abs().max().item()
+    top2 = ref_logits.topk(2, dim=-1).values
+    decisive = (top2[..., 0] - top2[..., 1]) > 4 * err
+    agree = logits.argmax(-1) == ref_logits.argmax(-1)
+    assert bool(agree[decisive].all())
+    free = eng.generate_from_embeds(g["inputs_embeds"].to(cuda_dev).to(torch.bfloat16), n_new).cpu()
+    print(f"qwen free-running match {(free == ref_ids).float().mean().item():.2f}")
+
+
+def test_full_width_decoder_layer_vs_oracle(cuda_dev):
+    """7B-dim layers (D=4096, F=11008, 32 heads x 128) at the bench's tile shapes, 2 layers, bs 3, S=200: prefill and two
+    decode steps against the CPU oracle on the same seeded weights."""
+    from crab_b200 import engine as E
+    from crab_b200.models.unified_arch import decoder_manifest
+    from oracle import synth
+
+    dcfg = E.DecoderConfig(layers=2, vocab=2048)
+    sd = synth.synth_state_dict(decoder_manifest(dcfg), 3)
+    dec_o = O.DecoderCfg(layers=2, vocab=2048)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    emb = torch.randn(3, 200, 4096, generator=g)
+    eng = E.CrabEngine(sd, E.CrabConfig(decoder=dcfg, max_ctx=256), cuda_dev, load_encoders=False)
+    with torch.no_grad():
+        ref_ids, ref_logits = O.greedy_generate(sd, emb.to(torch.bfloat16).float(), dec_o, 3)
+    out, logits = eng.generate_from_embeds(emb.to(cuda_dev).to(torch.bfloat16), 3, return_logits=True,
+                                           teacher_tokens=ref_ids.to(cuda_dev))
+    e = [rel_l2(logits[i], ref_logits[i]) for i in range(3)]
+    print("full-width logits rel_l2 per step:", ["%.3e" % v for v in e])
+    assert max(e) < 4e-2

@@ -115,3 +115,75 @@ def test_gemm_lora_z(cuda_dev):
     ref = (2.0 * r.unsqueeze(-1) * u.unsqueeze(-2)).reshape(M, G * 24)
     assert out.shape == (M, G * 24)
     _check(out, ref)
+
+
+@pytest.mark.parametrize("M", [1, 7, 32])
+@pytest.mark.parametrize("N,K,splits", [(256, 512, 0), (4096, 4128, 0), (12288, 4192, 3), (1000, 328, 2), (32024, 1024, 1),
+                                        (4096, 11040, 9)])
+def test_gemm_skinny(cuda_dev, M, N, K, splits):
+    from crab_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    ld = K + 24  # the decode activation buffers are wider than K
+    xbuf = torch.randn(M, ld, generator=g).to(torch.bfloat16).to(cuda_dev)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(cuda_dev)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    res = torch.randn(M, N, generator=g).to(torch.bfloat16).to(cuda_dev)
+    ref = xbuf[:, :K].float() @ w.float().t()
+    out = ops.gemm_skinny(xbuf, w, k=K, splits=splits)
+    _check(out, ref)
+    out2 = ops.gemm_skinny(xbuf, w, k=K, splits=splits)  # ticket counters must have been reset by the kernel
+    assert torch.equal(out, out2)
+    out = ops.gemm_skinny(xbuf, w, k=K, bias=bias, residual=res, splits=splits, out_dtype=torch.float32)
+    assert out.dtype == torch.float32
+    _check(out, ref + bias + res.float())
+    # in-place residual (the decoder's x += proj(...)): C aliases the residual
+    x_inplace = res.clone()
+    ops.gemm_skinny(xbuf, w, k=K, residual=x_inplace, out=x_inplace, splits=splits)
+    _check(x_inplace, ref + res.float())
+
+
+def test_gemm_skinny_swiglu_matches_prefill_kernel(cuda_dev):
+    from crab_b200 import ops
+
+    M, F, K = 32, 1024, 512
+    g = torch.Generator(device="cpu").manual_seed(2)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(cuda_dev)
+    wg = (torch.randn(F, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(cuda_dev)
+    wu = (torch.randn(F, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(cuda_dev)
+    packed = torch.stack([wg.view(F // 64, 64, K), wu.view(F // 64, 64, K)], dim=1).reshape(2 * F, K).contiguous()
+    ref = torch.nn.functional.silu(a.float() @ wg.float().t()) * (a.float() @ wu.float().t())
+    for splits in (1, 2, 0):
+        out = ops.gemm_skinny(a, packed, act=ops.ACT_SWIGLU, splits=splits)
+        assert out.shape == (M, F)
+        _check(out, ref)
+    _check(ops.gemm(a, packed, act=ops.ACT_SWIGLU), ref)
+
+
+@pytest.mark.parametrize("cols,groups,norm", [(4096, 3, True), (4096, 2, True), (4096, 1, False), (11008, 1, False), (256, 3, True),
+                                              (4096, 0, True)])
+def test_row_norm_loraz(cuda_dev, cols, groups, norm):
+    from crab_b200 import ops
+
+    rows = 9
+    g = torch.Generator(device="cpu").manual_seed(cols + groups)
+    x = (torch.randn(rows, cols, generator=g) * 1.5).to(torch.bfloat16).to(cuda_dev)
+    gamma = (1 + 0.1 * torch.randn(cols, generator=g)).to(cuda_dev)
+    ra = (torch.randn(max(groups, 1) * 11, cols, generator=g) / cols ** 0.5).to(torch.bfloat16).to(cuda_dev)
+    buf = torch.zeros(rows, cols + 96, dtype=torch.bfloat16, device=cuda_dev)
+    if norm:
+        ops.row_norm_loraz(x, gamma=gamma, eps=1e-6, y=buf[:, :cols], ra=ra if groups else None, groups=groups,
+                           z=buf[:, cols:] if groups else None, scale=2.0)
+        y_ref = ops.rmsnorm(x, gamma, 1e-6)
+        assert torch.equal(buf[:, :cols], y_ref)  # identical rounding to the prefill norm kernel
+        src = y_ref
+    else:
+        buf[:, :cols] = x
+        ops.row_norm_loraz(buf[:, :cols], ra=ra, groups=groups, z=buf[:, cols:], scale=2.0)
+        src = x
+    if groups:
+        t = (src.float() @ ra.float().t()).view(rows, groups, 11)
+        r = torch.softmax(t[..., :3], dim=-1)
+        ref = (2.0 * r.unsqueeze(-1) * t[..., 3:].unsqueeze(-2)).reshape(rows, groups * 24)
+        _check(buf[:, cols:cols + groups * 24], ref)
+        assert buf[:, cols + groups * 24:].abs().max().item() == 0

@@ -99,3 +99,25 @@ def test_hyper_lora_reduces_to_linear_when_B_is_zero():
         sd[f"l.lora_B{i}.weight"] = torch.zeros(16, 8)
     x = torch.randn(2, 5, 32)
     assert torch.allclose(O.hyper_lora_linear(x, sd, "l", cfg), x @ sd["l.weight"].t())
+
+
+def test_oracle_qwen_matches_reference():
+    """Qwen2 backbone (q/k/v bias, GQA, rope_theta from config) vs the reference's unified_qwen + peft_hyper."""
+    g = torch.load(GOLDEN / "qwen_small.pt", weights_only=False)
+    case = g["case"]
+    sd = O.strip_peft_prefix(synth.synth_state_dict(g["manifest"], case["weight_seed"]))
+    lc = case["llama_cfg"]
+    dec = O.DecoderCfg(hidden=lc["hidden_size"], inter=lc["intermediate_size"], layers=lc["num_hidden_layers"],
+                       heads=lc["num_attention_heads"], kv_heads=lc["num_key_value_heads"],
+                       head_dim=lc["hidden_size"] // lc["num_attention_heads"], vocab=lc["vocab_size"],
+                       rope_theta=lc["rope_theta"], eps=lc["rms_norm_eps"], qkv_bias=True)
+    with torch.no_grad():
+        h, cache, hiddens = O.decoder_forward(sd, g["inputs_embeds"], dec, collect_hidden=True)
+        for i, ref in enumerate(g["hidden_states"][:-1]):
+            _close(hiddens[i][:, -4:], ref)
+        _close(O.lm_head(sd, h[:, -1]), g["prefill_last_logits"])
+        first = g["generated_ids"][:, 0]
+        h1, cache = O.decoder_forward(sd, sd["model.embed_tokens.weight"][first].unsqueeze(1), dec, cache)
+        _close(O.lm_head(sd, h1[:, -1]), g["step1_logits"])
+        gen, _ = O.greedy_generate(sd, g["inputs_embeds"], dec, case["new_tokens"])
+    assert torch.equal(gen, g["generated_ids"])
