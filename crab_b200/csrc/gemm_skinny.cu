@@ -4,13 +4,21 @@
 // operands are swapped so the weights take the 128-row A slot of the tensor core and the batch takes the N slot:
 //     D[128 weight rows, 32 batch columns] += W_tile[128, 64] . X_tile[32, 64]^T      (tcgen05.mma M=128 N=32 K=16)
 // so no weight byte is fetched twice and the X tile (4 KB / k-block) is the only redundant traffic.
-// N/128 tiles cannot fill 148 SMs for the 4096-wide projections, so K is split across CTAs (split-K); every CTA parks
-// its fp32 partial tile in a workspace and the LAST CTA to finish a tile (atomic ticket) reduces the partials in
-// fixed split order — deterministic, unlike fp32 atomics — and applies the epilogue (bias, residual, SwiGLU, cast).
-// Two CTAs are resident per SM (5 x 20 KB stages each) so one CTA's prologue / fix-up overlaps the other's stream.
+//
+// Scheduling is persistent stream-K: the (tile, k-block) space is flattened and cut into one contiguous range per
+// CTA (one CTA per SM), so every SM streams the same number of bytes whatever N and K are.  A CTA's range crosses
+// at most a few tile boundaries; each piece ("segment") accumulates in TMEM (double-buffered so the epilogue of one
+// segment overlaps the stream of the next), is parked as an fp32 partial in an L2-resident workspace, and the LAST
+// contributor of a tile (atomic ticket) sums the partials in fixed order — deterministic, unlike fp32 atomics — and
+// applies the epilogue (bias, residual, SwiGLU, cast).  The TMA ring (5 x 20 KB stages) never drains between segments.
+// One CTA takes half an SM's shared memory on purpose: with PDL the NEXT kernel of the decode chain becomes resident
+// on the same SM while this one is still streaming, fills its own ring with weight tiles, and only then waits for its
+// producer — so launch latency, prologue and first-byte latency of every GEMM hide behind the previous kernel.
 //
 //   warp 0 : TMA producer (W 128x64 + X 32x64 per stage, SWIZZLE_128B)     warp 1 : MMA issuer + TMEM owner
 //   warps 2-5 : TMEM -> workspace, ticket, fix-up epilogue
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -19,12 +27,13 @@ namespace crab {
 static constexpr int SK_BM = 128;   // weight rows per tile
 static constexpr int SK_MB = 32;    // batch columns (UMMA N)
 static constexpr int SK_BK = 64;
-static constexpr int SK_STAGES = 5;
+static constexpr int SK_STAGES = 5;   // 100 KB: leaves room for the NEXT kernel's CTA on the same SM (PDL overlap)
 static constexpr int SK_W_BYTES = SK_BM * SK_BK * 2;
 static constexpr int SK_X_BYTES = SK_MB * SK_BK * 2;
 static constexpr int SK_STAGE_BYTES = SK_W_BYTES + SK_X_BYTES;
-static constexpr int SK_SMEM = SK_STAGES * SK_STAGE_BYTES + 1024 + 128;
+static constexpr int SK_SMEM = SK_STAGES * SK_STAGE_BYTES + 1024 + 256;
 static constexpr int SK_THREADS = 192;
+static constexpr int SK_MAX_SLOTS = 16;  // max contributors (CTAs) per tile (bounds the fix-up loop)
 
 struct SkinnyParams {
   void* C;
@@ -33,10 +42,24 @@ struct SkinnyParams {
   float* ws;
   int* counters;
   int M, N, K, ldc, ldr;
-  int act, out_dtype, splits;
+  int act, out_dtype;
+  const __nv_bfloat16* w_tiled;  // non-null: weights pre-packed as contiguous, pre-swizzled 16 KB (tile, k-block) blocks
+  int debug;  // diagnostic bit mask (env CRAB_SK_DEBUG): 1 = no X loads, 2 = no MMA, 4 = no epilogue/fix-up (wrong results!)
+  int tiles, kb_per_tile, max_segs;  // max_segs: workspace slots per CTA (segments a CTA range can touch)
+  long long total_kb;
 };
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// flattened k-block range of CTA c: [c*T/G, (c+1)*T/G)
+__device__ __forceinline__ long long sk_lo(long long c, long long T, long long G) { return c * T / G; }
+// the CTA whose range contains flattened k-block s
+__device__ __forceinline__ int sk_owner(long long s, long long T, long long G) {
+  long long c = s * G / T;
+  while (c + 1 < G && sk_lo(c + 1, T, G) <= s) ++c;
+  while (c > 0 && sk_lo(c, T, G) > s) --c;
+  return (int)c;
+}
 
 __global__ void __launch_bounds__(SK_THREADS, 2)
 gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
@@ -47,23 +70,23 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   const uint32_t bar_base = smem_base + SK_STAGES * SK_STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (SK_STAGES + s); };
-  const uint32_t tfull_bar = bar_base + 8u * (2 * SK_STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * SK_STAGES + 1);
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * SK_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SK_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SK_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
-  const int kb_total = (p.K + SK_BK - 1) / SK_BK;
-  const int kb0 = (int)((long long)split * kb_total / p.splits);
-  const int kb1 = (int)((long long)(split + 1) * kb_total / p.splits);
+  const long long T = p.total_kb, G = gridDim.x;
+  const int KB = p.kb_per_tile;
+  const long long lo = sk_lo(blockIdx.x, T, G), hi = sk_lo(blockIdx.x + 1, T, G);
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_w);
+    if (!p.w_tiled) tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < SK_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tfull_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 32); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -75,172 +98,262 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
     if (lane == 0) {
       // Weights never depend on an earlier kernel: fill the whole ring with W tiles BEFORE waiting for the producer
       // of X, so the weight stream is already in flight while the previous kernel drains.
-      const int npre = min(kb1 - kb0, SK_STAGES);
+      const int npre = (int)min((long long)SK_STAGES, hi - lo);
       for (int i = 0; i < npre; ++i) {
-        mbar_arrive_expect_tx(full_bar(i), SK_STAGE_BYTES);
-        tma_load_2d_hint(smem_base + i * SK_STAGE_BYTES, &tmap_w, full_bar(i), (kb0 + i) * SK_BK, tile * SK_BM, kEvictFirst);
+        const long long f = lo + i;
+        mbar_arrive_expect_tx(full_bar(i), (p.debug & 1) ? SK_W_BYTES : SK_STAGE_BYTES);
+        if (p.w_tiled) bulk_load_1d_hint(smem_base + i * SK_STAGE_BYTES, p.w_tiled + (size_t)f * (SK_BM * SK_BK), SK_W_BYTES, full_bar(i), kEvictFirst);
+        else tma_load_2d_hint(smem_base + i * SK_STAGE_BYTES, &tmap_w, full_bar(i), (int)(f % KB) * SK_BK, (int)(f / KB) * SK_BM, kEvictFirst);
       }
       pdl_wait();
-      for (int i = 0; i < npre; ++i)
-        tma_load_2d_hint(smem_base + i * SK_STAGE_BYTES + SK_W_BYTES, &tmap_x, full_bar(i), (kb0 + i) * SK_BK, 0, kEvictLast);
+      for (int i = 0; i < npre && !(p.debug & 1); ++i)
+        tma_load_2d_hint(smem_base + i * SK_STAGE_BYTES + SK_W_BYTES, &tmap_x, full_bar(i), (int)((lo + i) % KB) * SK_BK, 0, kEvictLast);
       uint32_t stage = 0, phase = 1;  // ring position after the prefill above (npre == SK_STAGES wraps to stage 0)
-      if (npre < SK_STAGES) { stage = npre; phase = 0; }
-      for (int kb = kb0 + npre; kb < kb1; ++kb) {
+      for (long long f = lo + npre; f < hi; ++f) {
         mbar_wait(empty_bar(stage), phase ^ 1);
-        mbar_arrive_expect_tx(full_bar(stage), SK_STAGE_BYTES);
+        mbar_arrive_expect_tx(full_bar(stage), (p.debug & 1) ? SK_W_BYTES : SK_STAGE_BYTES);
         const uint32_t sw = smem_base + stage * SK_STAGE_BYTES;
-        tma_load_2d_hint(sw, &tmap_w, full_bar(stage), kb * SK_BK, tile * SK_BM, kEvictFirst);  // weights: read once
-        tma_load_2d_hint(sw + SK_W_BYTES, &tmap_x, full_bar(stage), kb * SK_BK, 0, kEvictLast);  // X: shared by all CTAs
+        const int kb = (int)(f % KB), tile = (int)(f / KB);
+        if (p.w_tiled) bulk_load_1d_hint(sw, p.w_tiled + (size_t)f * (SK_BM * SK_BK), SK_W_BYTES, full_bar(stage), kEvictFirst);
+        else tma_load_2d_hint(sw, &tmap_w, full_bar(stage), kb * SK_BK, tile * SK_BM, kEvictFirst);   // weights: read once
+        if (!(p.debug & 1)) tma_load_2d_hint(sw + SK_W_BYTES, &tmap_x, full_bar(stage), kb * SK_BK, 0, kEvictLast);  // X: shared by all CTAs
         if (++stage == SK_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(SK_BM, SK_MB);
-      uint32_t stage = 0, phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      long long f = lo;
+      while (f < hi) {
+        const long long seg_end = min(hi, (f / KB + 1) * KB);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t sw = smem_base + stage * SK_STAGE_BYTES;
-        const uint64_t da = make_sdesc_sw128(sw);
-        const uint64_t db = make_sdesc_sw128(sw + SK_W_BYTES);
+        const uint32_t tmem_d = tmem_base + acc * SK_MB;
+        for (long long g = f; g < seg_end; ++g) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sw = smem_base + stage * SK_STAGE_BYTES;
+          const uint64_t da = make_sdesc_sw128(sw);
+          const uint64_t db = make_sdesc_sw128(sw + SK_W_BYTES);
+          if (p.debug & 2) {
+            mbar_arrive(empty_bar(stage));
+          } else {
 #pragma unroll
-        for (int k = 0; k < SK_BK / 16; ++k) umma_bf16_ss(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb > kb0) | (k > 0));
-        umma_commit(empty_bar(stage));
-        if (++stage == SK_STAGES) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < SK_BK / 16; ++k) umma_bf16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (g > f) | (k > 0));
+            umma_commit(empty_bar(stage));
+          }
+          if (++stage == SK_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (p.debug & 2) mbar_arrive(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        f = seg_end;
       }
-      umma_commit(tfull_bar);
     }
   } else {
-    // ---- park the partial tile: ws[(tile*splits + split)][row 0..127][b 0..31] ----
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    const int tt = (warp - 2) * 32 + lane;
     pdl_wait();  // before the first write to the shared workspace / read of residual
-    mbar_wait(tfull_bar, 0);
-    tc_fence_after();
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16), r);
-    tmem_ld_wait();
-    float* wrow = p.ws + (((size_t)tile * p.splits + split) * SK_BM + row) * SK_MB;
+    uint32_t acc = 0, acc_phase = 0;
+    long long f = lo;
+    while (f < hi) {
+      const int tile = (int)(f / KB);
+      const long long t0 = (long long)tile * KB;
+      const long long seg_end = min(hi, t0 + KB);
+      const int c_first = sk_owner(t0, T, G), c_last = sk_owner(t0 + KB - 1, T, G);
+      const int n_contrib = c_last - c_first + 1;
+      const int my_seg = tile - (int)(lo / KB);
+      // ---- park the partial tile: ws[cta][segment index within the CTA][row 0..127][b 0..31] ----
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * SK_MB, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator free: the MMA warp may start the next segment
+      if (p.debug & 4) { acc ^= 1; if (acc == 0) acc_phase ^= 1; f = seg_end; continue; }
+      float* wrow = p.ws + (((size_t)blockIdx.x * p.max_segs + my_seg) * SK_BM + row) * SK_MB;
 #pragma unroll
-    for (int g = 0; g < 8; ++g)
-      __stcg(reinterpret_cast<float4*>(wrow) + g, make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
-                                                              __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])));
-    __threadfence();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (warp == 2 && lane == 0) {
-      const int old = atomicAdd(p.counters + tile, 1);
-      s_last = (old == p.splits - 1);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (s_last) {
+      for (int g = 0; g < 8; ++g)
+        __stcg(reinterpret_cast<float4*>(wrow) + g, make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                                                                __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])));
       __threadfence();
-      const int tt = (warp - 2) * 32 + lane;
-      const float* wt = p.ws + (size_t)tile * p.splits * SK_BM * SK_MB;
-      if (p.act == CRAB_ACT_SWIGLU) {
-        // tile rows = [64 gate | 64 up]  ->  64 output columns
-        const int n = tile * 64 + tt;
-        if (tt < 64 && n < (p.N >> 1)) {
-          float g[32], u[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { g[j] = 0.f; u[j] = 0.f; }
-          for (int s = 0; s < p.splits; ++s) {
-            const float* pg = wt + ((size_t)s * SK_BM + tt) * SK_MB;
-            const float* pu = wt + ((size_t)s * SK_BM + tt + 64) * SK_MB;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 a = ldcg4(pg + 4 * q), b = ldcg4(pu + 4 * q);
-              g[4 * q] += a.x; g[4 * q + 1] += a.y; g[4 * q + 2] += a.z; g[4 * q + 3] += a.w;
-              u[4 * q] += b.x; u[4 * q + 1] += b.y; u[4 * q + 2] += b.z; u[4 * q + 3] += b.w;
-            }
-          }
-          __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C);
-#pragma unroll
-          for (int b = 0; b < 32; ++b)
-            if (b < p.M) c[(size_t)b * p.ldc + n] = __float2bfloat16_rn(g[b] / (1.0f + __expf(-g[b])) * u[b]);
-        }
-      } else {
-        const int n = tile * SK_BM + tt;
-        if (n < p.N) {
-          float a[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) a[j] = 0.f;
-          for (int s = 0; s < p.splits; ++s) {
-            const float* pa = wt + ((size_t)s * SK_BM + tt) * SK_MB;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 v = ldcg4(pa + 4 * q);
-              a[4 * q] += v.x; a[4 * q + 1] += v.y; a[4 * q + 2] += v.z; a[4 * q + 3] += v.w;
-            }
-          }
-          const float bias = p.bias ? p.bias[n] : 0.f;
-#pragma unroll
-          for (int b = 0; b < 32; ++b) {
-            if (b < p.M) {
-              float v = a[b] + bias;
-              if (p.residual) v += __bfloat162float(p.residual[(size_t)b * p.ldr + n]);
-              if (p.out_dtype == CRAB_BF16) reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(v);
-              else reinterpret_cast<float*>(p.C)[(size_t)b * p.ldc + n] = v;
-            }
-          }
-        }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tt == 0) {
+        const int old = atomicAdd(p.counters + tile, 1);
+        s_last = (old == n_contrib - 1);
       }
-      if (warp == 2 && lane == 0) p.counters[tile] = 0;  // ready for the next launch (stream order)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const bool last = s_last != 0;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone has read s_last before the next segment rewrites it
+      if (last) {
+        __threadfence();
+        if (p.act == CRAB_ACT_SWIGLU) {
+          // tile rows = [64 gate | 64 up]  ->  64 output columns
+          const int n = tile * 64 + tt;
+          if (tt < 64 && n < (p.N >> 1)) {
+            float g[32], u[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { g[j] = 0.f; u[j] = 0.f; }
+            for (int s = 0; s < n_contrib; ++s) {
+              const int cc = c_first + s;
+              const float* wt = p.ws + ((size_t)cc * p.max_segs + (tile - (int)(sk_lo(cc, T, G) / KB))) * SK_BM * SK_MB;
+              const float* pg = wt + (size_t)tt * SK_MB;
+              const float* pu = wt + (size_t)(tt + 64) * SK_MB;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 a = ldcg4(pg + 4 * q), b = ldcg4(pu + 4 * q);
+                g[4 * q] += a.x; g[4 * q + 1] += a.y; g[4 * q + 2] += a.z; g[4 * q + 3] += a.w;
+                u[4 * q] += b.x; u[4 * q + 1] += b.y; u[4 * q + 2] += b.z; u[4 * q + 3] += b.w;
+              }
+            }
+            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C);
+#pragma unroll
+            for (int b = 0; b < 32; ++b)
+              if (b < p.M) c[(size_t)b * p.ldc + n] = __float2bfloat16_rn(g[b] / (1.0f + __expf(-g[b])) * u[b]);
+          }
+        } else {
+          const int n = tile * SK_BM + tt;
+          if (n < p.N) {
+            float a[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = 0.f;
+            for (int s = 0; s < n_contrib; ++s) {
+              const int cc = c_first + s;
+              const float* pa = p.ws + (((size_t)cc * p.max_segs + (tile - (int)(sk_lo(cc, T, G) / KB))) * SK_BM + tt) * SK_MB;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 v = ldcg4(pa + 4 * q);
+                a[4 * q] += v.x; a[4 * q + 1] += v.y; a[4 * q + 2] += v.z; a[4 * q + 3] += v.w;
+              }
+            }
+            const float bias = p.bias ? p.bias[n] : 0.f;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+              if (b < p.M) {
+                float v = a[b] + bias;
+                if (p.residual) v += __bfloat162float(p.residual[(size_t)b * p.ldr + n]);
+                if (p.out_dtype == CRAB_BF16) reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(v);
+                else reinterpret_cast<float*>(p.C)[(size_t)b * p.ldc + n] = v;
+              }
+            }
+          }
+        }
+        if (tt == 0) p.counters[tile] = 0;  // ready for the next launch (stream order)
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+      f = seg_end;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
 }
 
-int choose_splits(int N, int K) {
-  const int tiles = (N + SK_BM - 1) / SK_BM;
-  const int kb = (K + SK_BK - 1) / SK_BK;
-  const int target = 2 * sm_count();
-  int s = (target + tiles / 2) / tiles;
-  if (s < 1) s = 1;
-  if (s > kb / 4) s = kb / 4 > 0 ? kb / 4 : 1;
-  if (s > 16) s = 16;
-  return s;
+// Pre-pack a row-major weight [N, ldw] into the streaming layout: block f = tile * KB + kb holds the 128 x 64 tile
+// exactly as the UMMA SWIZZLE_128B smem layout wants it (row r: 128 bytes, 16-byte chunk c stored at c ^ (r & 7)),
+// zero-padded past N / K.  One CTA's stream-K range is then ONE contiguous span of HBM.
+__global__ void pack_skinny_weight_kernel(const __nv_bfloat16* __restrict__ w, int N, int K, int ldw,
+                                          __nv_bfloat16* __restrict__ out, int kb_per_tile, long long total_chunks) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk per thread
+  if (i >= total_chunks) return;
+  const int cs = (int)(i & 7);                 // stored chunk position
+  const int r = (int)((i >> 3) & 127);         // row within tile
+  const long long f = i >> 10;                 // block index
+  const int kb = (int)(f % kb_per_tile), tile = (int)(f / kb_per_tile);
+  const int c = cs ^ (r & 7);                  // source chunk
+  const int row = tile * SK_BM + r, col = kb * SK_BK + c * 8;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (row < N) {
+    if (col + 8 <= K) v = *reinterpret_cast<const uint4*>(w + (size_t)row * ldw + col);
+    else if (col < K) {
+      __nv_bfloat16 t[8];
+      for (int e = 0; e < 8; ++e) t[e] = (col + e < K) ? w[(size_t)row * ldw + col + e] : __float2bfloat16_rn(0.f);
+      v = *reinterpret_cast<uint4*>(t);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + i * 8) = v;
+}
+
+// CTAs for (N, K): one per SM, but never so many that a CTA streams fewer than 8 k-blocks or a tile gets more than
+// SK_MAX_SLOTS contributors.
+int choose_ctas(int N, int K) {
+  const long long tiles = (N + SK_BM - 1) / SK_BM;
+  const long long kb = (K + SK_BK - 1) / SK_BK;
+  const long long T = tiles * kb;
+  long long g = sm_count();
+  if (g > T / 8) g = T / 8 > 0 ? T / 8 : 1;
+  return (int)g;
 }
 
 }  // namespace crab
 
 using namespace crab;
 
-extern "C" int crab_gemm_skinny_plan(int N, int K, int* splits, int64_t* workspace_bytes, int* n_counters) {
-  CRAB_REQUIRE(N > 0 && K > 0 && splits && workspace_bytes && n_counters, "crab_gemm_skinny_plan: bad args");
+extern "C" int crab_gemm_skinny_plan(int N, int K, int* ctas, int64_t* workspace_bytes, int* n_counters) {
+  CRAB_REQUIRE(N > 0 && K > 0 && ctas && workspace_bytes && n_counters, "crab_gemm_skinny_plan: bad args");
   const int tiles = (N + SK_BM - 1) / SK_BM;
-  *splits = choose_splits(N, K);
-  *workspace_bytes = (int64_t)tiles * (*splits) * SK_BM * SK_MB * 4;
+  *ctas = choose_ctas(N, K);
+  *workspace_bytes = (int64_t)(tiles + 2 * (*ctas)) * SK_BM * SK_MB * 4;
   *n_counters = tiles;
+  return CRAB_OK;
+}
+
+extern "C" int crab_skinny_packed_bytes(int N, int K, int64_t* bytes) {
+  CRAB_REQUIRE(N > 0 && K > 0 && bytes, "crab_skinny_packed_bytes: bad args");
+  *bytes = (int64_t)((N + SK_BM - 1) / SK_BM) * ((K + SK_BK - 1) / SK_BK) * SK_BM * SK_BK * 2;
+  return CRAB_OK;
+}
+
+extern "C" int crab_pack_skinny_weight(const void* W, int N, int K, int ldw, void* out, void* stream) {
+  CRAB_REQUIRE(W && out && N > 0 && K > 0 && ldw >= K && ldw % 8 == 0, "crab_pack_skinny_weight: bad args");
+  CRAB_REQUIRE(((uintptr_t)W % 16 == 0) && ((uintptr_t)out % 128 == 0), "crab_pack_skinny_weight: alignment (W 16 B, out 128 B)");
+  const int kb = (K + SK_BK - 1) / SK_BK;
+  const long long chunks = (long long)((N + SK_BM - 1) / SK_BM) * kb * SK_BM * 8;
+  pack_skinny_weight_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(W), N, K, ldw, reinterpret_cast<__nv_bfloat16*>(out), kb, chunks);
+  CRAB_CHECK_CUDA(cudaGetLastError());
   return CRAB_OK;
 }
 
 extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CRAB_REQUIRE(a && a->X && a->W && a->C && a->workspace && a->counters, "crab_gemm_skinny_bf16: null pointer");
+  CRAB_REQUIRE(a && a->X && (a->W || a->W_packed) && a->C && a->workspace && a->counters, "crab_gemm_skinny_bf16: null pointer");
   CRAB_REQUIRE(a->M > 0 && a->M <= SK_MB, "crab_gemm_skinny_bf16: M must be in 1..32 (got %d)", a->M);
-  CRAB_REQUIRE(a->N > 0 && a->K > 0 && a->ldx % 8 == 0 && a->ldw % 8 == 0 && a->ldx >= a->K && a->ldw >= a->K,
-               "crab_gemm_skinny_bf16: bad shape/strides N=%d K=%d ldx=%d ldw=%d", a->N, a->K, a->ldx, a->ldw);
-  CRAB_REQUIRE(((uintptr_t)a->X % 16 == 0) && ((uintptr_t)a->W % 16 == 0), "crab_gemm_skinny_bf16: X/W must be 16-byte aligned");
+  CRAB_REQUIRE(a->N > 0 && a->K > 0 && a->ldx % 8 == 0 && a->ldx >= a->K, "crab_gemm_skinny_bf16: bad shape/strides N=%d K=%d ldx=%d",
+               a->N, a->K, a->ldx);
+  if (a->W_packed) CRAB_REQUIRE((uintptr_t)a->W_packed % 128 == 0, "crab_gemm_skinny_bf16: W_packed must be 128-byte aligned");
+  else CRAB_REQUIRE(a->ldw % 8 == 0 && a->ldw >= a->K && ((uintptr_t)a->W % 16 == 0), "crab_gemm_skinny_bf16: W alignment / ldw=%d", a->ldw);
+  CRAB_REQUIRE((uintptr_t)a->X % 16 == 0, "crab_gemm_skinny_bf16: X must be 16-byte aligned");
   CRAB_REQUIRE(a->act == CRAB_ACT_NONE || a->act == CRAB_ACT_SWIGLU, "crab_gemm_skinny_bf16: act must be NONE or SWIGLU");
   if (a->act == CRAB_ACT_SWIGLU)
     CRAB_REQUIRE(a->N % 128 == 0 && !a->bias && !a->residual && a->out_dtype == CRAB_BF16, "crab_gemm_skinny_bf16: SWIGLU constraints");
   const int tiles = (a->N + SK_BM - 1) / SK_BM;
   const int kb = (a->K + SK_BK - 1) / SK_BK;
-  int splits = a->splits > 0 ? a->splits : choose_splits(a->N, a->K);
-  if (splits > kb) splits = kb;
-  if (splits > 16) splits = 16;
+  const long long T = (long long)tiles * kb;
+  long long ctas = a->splits > 0 ? a->splits : choose_ctas(a->N, a->K);  // `splits` = explicit CTA count (testing)
+  if (ctas > T) ctas = T;
+  // a tile of kb k-blocks may be shared by at most SK_MAX_SLOTS CTAs
+  const long long min_range = (kb + SK_MAX_SLOTS - 2) / (SK_MAX_SLOTS - 1);
+  if (T / ctas < min_range) ctas = T / min_range > 0 ? T / min_range : 1;
   CRAB_REQUIRE(a->n_counters >= tiles, "crab_gemm_skinny_bf16: need %d counters (got %d)", tiles, a->n_counters);
-  CRAB_REQUIRE(a->workspace_bytes >= (int64_t)tiles * splits * SK_BM * SK_MB * 4, "crab_gemm_skinny_bf16: workspace too small");
+  const long long range_max = (T + ctas - 1) / ctas;
+  const int max_segs = (int)((range_max + kb - 1) / kb) + 1;
+  const long long ws_need = ctas * max_segs * (long long)SK_BM * SK_MB * 4;
+  CRAB_REQUIRE(a->workspace_bytes >= ws_need, "crab_gemm_skinny_bf16: workspace too small (need %lld bytes)", ws_need);
   static bool attr_set = false;
   if (!attr_set) {
     CRAB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
     attr_set = true;
   }
   CUtensorMap tw, tx;
-  int rc = encode_tmap_bf16_2d(&tw, a->W, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldw, SK_BM, SK_BK);
+  int rc = 0;
+  if (a->W_packed) memset(&tw, 0, sizeof(tw));
+  else rc = encode_tmap_bf16_2d(&tw, a->W, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldw, SK_BM, SK_BK);
   if (rc != 0) return rc;
   rc = encode_tmap_bf16_2d(&tx, a->X, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->ldx, SK_MB, SK_BK);
   if (rc != 0) return rc;
@@ -248,7 +361,10 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
   p.C = a->C; p.bias = a->bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
   p.ws = a->workspace; p.counters = a->counters;
   p.M = a->M; p.N = a->N; p.K = a->K; p.ldc = a->ldc; p.ldr = a->ldr;
-  p.act = a->act; p.out_dtype = a->out_dtype; p.splits = splits;
-  CRAB_CHECK_CUDA(launch_pdl(gemm_skinny_tcgen05_kernel, dim3(tiles * splits), dim3(SK_THREADS), SK_SMEM, stream, tw, tx, p));
+  p.act = a->act; p.out_dtype = a->out_dtype;
+  p.w_tiled = reinterpret_cast<const __nv_bfloat16*>(a->W_packed);
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("CRAB_SK_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+  p.tiles = tiles; p.kb_per_tile = kb; p.total_kb = T; p.max_segs = max_segs;
+  CRAB_CHECK_CUDA(launch_pdl(gemm_skinny_tcgen05_kernel, dim3((unsigned)ctas), dim3(SK_THREADS), SK_SMEM, stream, tw, tx, p));
   return CRAB_OK;
 }

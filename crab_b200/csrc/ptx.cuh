@@ -89,6 +89,15 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t smem_dst, const void* 
       : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// 1-D bulk copy global -> shared (contiguous `bytes`, multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d_hint(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar,
+                                                  uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar), "l"(hint)
+      : "memory");
+}
 // L2 eviction-priority policies (same encodings CUTLASS uses for TMA::CacheHintSm90)
 static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 static constexpr uint64_t kEvictLast = 0x14F0000000000000ull;

@@ -149,12 +149,14 @@ class _QformerWeights:
 
 
 class CrabEngine:
-    def __init__(self, sd: SD, cfg: CrabConfig, device: Optional[torch.device] = None, load_encoders: bool = True):
+    def __init__(self, sd: SD, cfg: CrabConfig, device: Optional[torch.device] = None, load_encoders: bool = True,
+                 decode_packed: bool = True):
         if not torch.cuda.is_available():
             raise ops._l.CrabError("crab_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         ops.init(self.dev.index or 0)
         self.cfg = cfg
+        self.decode_packed = decode_packed
         sd = {(k[len("base_model.model."):] if k.startswith("base_model.model.") else k): v for k, v in sd.items()}
         self._pack_decoder(sd)
         self.has_encoders = load_encoders and ("model.vl_projector.visual_ln.weight" in sd)
@@ -195,6 +197,7 @@ class CrabEngine:
         lm = torch.zeros((self.vocab_pad, D), dtype=torch.bfloat16, device=dev)
         lm[:V] = _bf(sd["lm_head.weight"], dev)
         self.lm_head = lm
+        self.lm_head_p = ops.pack_skinny_weight(lm) if self.decode_packed else None
         self.scaling = c.lora_alpha / c.lora_r
         nl, r = c.lora_nums, c.lora_r
         zw = nl * r  # 24 z columns per linear
@@ -259,6 +262,14 @@ class CrabEngine:
             L["wd"] = wd
             L["ln1"] = _f32(sd[lp + "input_layernorm.weight"], dev)
             L["ln2"] = _f32(sd[lp + "post_attention_layernorm.weight"], dev)
+            if self.decode_packed:
+                # second copy of the decode-step weights in the streaming layout (contiguous pre-swizzled 16 KB tile
+                # blocks): the prefill GEMM wants row-major K-extended rows, the M<=32 stream wants sequential HBM
+                lo = self.lora
+                L["wqkv_p"] = ops.pack_skinny_weight(wq, k=D + (self.EXT_QKV if lo else 0))
+                L["wo_p"] = ops.pack_skinny_weight(wo, k=nq + (self.EXT_O if lo else 0))
+                L["wgu_p"] = ops.pack_skinny_weight(L["wgu"], k=D + (self.EXT_GU if lo else 0))
+                L["wd_p"] = ops.pack_skinny_weight(wd, k=F + (self.EXT_D if lo else 0))
             self.layers.append(L)
         self.rope = ops.rope_table(self.cfg.max_ctx, hd, c.rope_theta, dev)
 
@@ -592,7 +603,7 @@ class CrabEngine:
             if skinny:
                 ops.row_norm_loraz(x, gamma=L["ln1"], eps=c.eps, y=xn[:, :D], ra=L.get("ra_qkv"), groups=3 if self.lora else 0,
                                    z=xn[:, D:] if self.lora else None, scale=sc)
-                ops.gemm_skinny(xn, L["wqkv"], bias=L["bqkv"], out=qkv, k=D + (self.EXT_QKV if self.lora else 0))
+                ops.gemm_skinny(xn, L.get("wqkv_p", L["wqkv"]), bias=L["bqkv"], out=qkv, k=D + (self.EXT_QKV if self.lora else 0))
             else:
                 ops.rmsnorm(x, L["ln1"], c.eps, out=xn[:, :D])
                 if self.lora:
@@ -610,13 +621,13 @@ class CrabEngine:
             if skinny:
                 if self.lora:
                     ops.row_norm_loraz(at[:, :nq], ra=L["ra_o"], groups=1, z=at[:, nq:], scale=sc)
-                ops.gemm_skinny(at, L["wo"], residual=x, out=x, k=nq + (self.EXT_O if self.lora else 0))
+                ops.gemm_skinny(at, L.get("wo_p", L["wo"]), residual=x, out=x, k=nq + (self.EXT_O if self.lora else 0))
                 ops.row_norm_loraz(x, gamma=L["ln2"], eps=c.eps, y=xn[:, :D], ra=L.get("ra_gu"), groups=2 if self.lora else 0,
                                    z=xn[:, D:] if self.lora else None, scale=sc)
-                ops.gemm_skinny(xn, L["wgu"], act=ops.ACT_SWIGLU, out=hh[:, :F], k=D + (self.EXT_GU if self.lora else 0))
+                ops.gemm_skinny(xn, L.get("wgu_p", L["wgu"]), act=ops.ACT_SWIGLU, out=hh[:, :F], k=D + (self.EXT_GU if self.lora else 0))
                 if self.lora:
                     ops.row_norm_loraz(hh[:, :F], ra=L["ra_d"], groups=1, z=hh[:, F:], scale=sc)
-                ops.gemm_skinny(hh, L["wd"], residual=x, out=x, k=F + (self.EXT_D if self.lora else 0))
+                ops.gemm_skinny(hh, L.get("wd_p", L["wd"]), residual=x, out=x, k=F + (self.EXT_D if self.lora else 0))
             else:
                 if self.lora:
                     ops.gemm(at[:, :nq], L["ra_o"], act=ops.ACT_LORA_Z, out_scale=sc, out=at[:, nq:nq + 24])
@@ -635,7 +646,7 @@ class CrabEngine:
         c = self.cfg.decoder
         hn = ops.rmsnorm(x_last, self.final_norm, c.eps, out=self._buf("head_hn", tuple(x_last.shape)))
         if x_last.shape[0] <= 32:
-            ops.gemm_skinny(hn, self.lm_head, out=logits)
+            ops.gemm_skinny(hn, self.lm_head_p if self.lm_head_p is not None else self.lm_head, out=logits)
         else:
             ops.gemm(hn, self.lm_head, out=logits)
         ops.argmax(logits, self.vocab, out=next_ids)

@@ -350,23 +350,52 @@ def _skinny_scratch(device):
     return _skinny_bufs[key]
 
 
-def gemm_skinny(x: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+class PackedWeight:
+    """A decode weight in the streaming layout of crab_pack_skinny_weight (plus its logical shape)."""
+
+    __slots__ = ("data", "N", "K")
+
+    def __init__(self, data: torch.Tensor, N: int, K: int):
+        self.data, self.N, self.K = data, N, K
+
+
+def pack_skinny_weight(w: torch.Tensor, k: Optional[int] = None) -> PackedWeight:
+    """Row-major bf16 [N, >=K] -> contiguous pre-swizzled 16 KB (tile, k-block) blocks for gemm_skinny."""
+    _req_cuda(w)
+    assert w.dim() == 2 and w.dtype == torch.bfloat16 and w.stride(1) == 1
+    N, K = w.shape[0], (k if k is not None else w.shape[1])
+    nbytes = C.c_int64(0)
+    _l.check(_l.load().crab_skinny_packed_bytes(_i(N), _i(K), C.byref(nbytes)), "crab_skinny_packed_bytes")
+    out = torch.empty(nbytes.value // 2, device=w.device, dtype=torch.bfloat16)
+    assert out.data_ptr() % 128 == 0
+    _l.check(_l.load().crab_pack_skinny_weight(_vp(w), _i(N), _i(K), _i(w.stride(0)), _vp(out), _stream()), "crab_pack_skinny_weight")
+    count_launches(1)
+    return PackedWeight(out, N, K)
+
+
+def gemm_skinny(x: torch.Tensor, w, *, bias: Optional[torch.Tensor] = None,
                 residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
                 out_dtype: torch.dtype = torch.bfloat16, k: Optional[int] = None, n: Optional[int] = None,
                 splits: int = 0) -> torch.Tensor:
     """out[M, N'] = epilogue(x[M<=32, K] @ w[N, K]^T): the decode-step weight-streaming GEMM (swap-AB, split-K)."""
-    _req_cuda(x, w, bias, residual, out)
-    assert x.dim() == 2 and w.dim() == 2 and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    packed = isinstance(w, PackedWeight)
+    _req_cuda(x, w.data if packed else w, bias, residual, out)
+    assert x.dim() == 2 and x.dtype == torch.bfloat16
     M = x.shape[0]
-    K = k if k is not None else x.shape[1]
-    N = n if n is not None else w.shape[0]
+    if packed:
+        K, N = w.K, w.N
+        assert x.shape[1] >= K
+    else:
+        assert w.dim() == 2 and w.dtype == torch.bfloat16
+        K = k if k is not None else x.shape[1]
+        N = n if n is not None else w.shape[0]
     n_out = N // 2 if act == ACT_SWIGLU else N
     if out is None:
         out = torch.empty((M, n_out), device=x.device, dtype=out_dtype)
     ws, cnt = _skinny_scratch(x.device)
-    args = _l.SkinnyArgs(X=_ptr(x), W=_ptr(w), C=_ptr(out), bias=_ptr(bias), residual=_ptr(residual),
+    args = _l.SkinnyArgs(X=_ptr(x), W=None if packed else _ptr(w), W_packed=_ptr(w.data) if packed else None, C=_ptr(out), bias=_ptr(bias), residual=_ptr(residual),
                          workspace=_ptr(ws), counters=_ptr(cnt), workspace_bytes=ws.numel() * 4, n_counters=cnt.numel(),
-                         M=M, N=N, K=K, ldx=x.stride(0), ldw=w.stride(0), ldc=out.stride(0),
+                         M=M, N=N, K=K, ldx=x.stride(0), ldw=0 if packed else w.stride(0), ldc=out.stride(0),
                          ldr=(residual.stride(0) if residual is not None else 0), act=act,
                          out_dtype=(BF16 if out.dtype == torch.bfloat16 else F32), splits=splits)
     with _timed("gemm_skinny_tcgen05", 2.0 * M * N * K, 2.0 * (M * K + N * K) + out.element_size() * M * n_out):

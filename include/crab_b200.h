@@ -31,7 +31,7 @@ const char* crab_last_error(void);
 /* Library / device probe: returns CRAB_OK when device `dev` is compute capability 10.x. */
 int crab_init(int dev);
 int crab_version(void);
-/* Programmatic dependent launch for the decode-chain kernels (default on; env CRAB_PDL=0 disables). */
+/* Programmatic dependent launch for the decode-chain kernels (default off; env CRAB_PDL=1 or crab_set_pdl(1)). */
 int crab_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -160,7 +160,8 @@ int crab_add_scalar_i32(int* p, int v, void* stream);
  * ---------------------------------------------------------------------------------------------------------------- */
 typedef struct crab_skinny_args {
   const void* X;        /* bf16 [M, ldx], M <= 32 */
-  const void* W;        /* bf16 [N, ldw] */
+  const void* W;        /* bf16 [N, ldw] row-major (read through TMA), or NULL when W_packed is given */
+  const void* W_packed; /* same weight pre-packed by crab_pack_skinny_weight (contiguous 16 KB tile blocks) or NULL */
   void* C;              /* [M, ldc] bf16 or fp32 */
   const float* bias;    /* fp32 [N] or NULL */
   const void* residual; /* bf16 [M, ldr] or NULL */
@@ -171,12 +172,19 @@ typedef struct crab_skinny_args {
   int32_t M, N, K, ldx, ldw, ldc, ldr;
   int32_t act;          /* CRAB_ACT_NONE or CRAB_ACT_SWIGLU */
   int32_t out_dtype;
-  int32_t splits;       /* 0 = auto */
+  int32_t splits;       /* stream-K CTA count; 0 = one per SM */
 } crab_skinny_args;
-int crab_gemm_skinny_plan(int N, int K, int* splits, int64_t* workspace_bytes, int* n_counters);
+int crab_gemm_skinny_plan(int N, int K, int* ctas, int64_t* workspace_bytes, int* n_counters);
+/* Streaming layout for decode weights: block (tile, kb) = the 128x64 tile, pre-swizzled for the tensor core, 16 KB
+ * contiguous; `out` needs crab_skinny_packed_bytes(N, K) bytes, 128-byte aligned. */
+int crab_skinny_packed_bytes(int N, int K, int64_t* bytes);
+int crab_pack_skinny_weight(const void* W, int N, int K, int ldw, void* out, void* stream);
 int crab_gemm_skinny_bf16(const crab_skinny_args* args, void* stream);
 int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, float eps, void* y, int ldy, const void* ra,
                         int ldra, int groups, void* z, int ldz, float scale, int rows, int cols, void* stream);
+
+/* Diagnostic (not on the product path): pure HBM->smem ring streaming, used by tools/ to size the decode pipelines. */
+int crab_debug_stream(const void* src, int64_t bytes, int chunk_bytes, int stages, int ctas, void* sink, void* stream);
 
 #ifdef __cplusplus
 }
