@@ -44,28 +44,28 @@ struct SkinnyParams {
   int M, N, K, ldc, ldr;
   int act, out_dtype;
   const __nv_bfloat16* w_tiled;  // non-null: weights pre-packed as contiguous, pre-swizzled 16 KB (tile, k-block) blocks
+  unsigned long long* trace;  // diagnostic: per-CTA timestamps of the last segment's epilogue (env CRAB_SK_TRACE=1)
   int debug;  // diagnostic bit mask (env CRAB_SK_DEBUG): 1 = no X loads, 2 = no MMA, 4 = no epilogue/fix-up (wrong results!)
   int tiles, kb_per_tile, max_segs;  // max_segs: workspace slots per CTA (segments a CTA range can touch)
-  long long total_kb;
+  int total_kb;
+  int q, rem;  // balanced partition of total_kb over the grid: CTA c owns [c*q + min(c,rem), ...) — no 64-bit divisions on device
 };
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-// flattened k-block range of CTA c: [c*T/G, (c+1)*T/G)
-__device__ __forceinline__ long long sk_lo(long long c, long long T, long long G) { return c * T / G; }
+// flattened k-block range of CTA c: the first `rem` CTAs own q+1 blocks, the rest q  (q = T / G, rem = T % G)
+__device__ __forceinline__ int sk_lo(int c, int q, int rem) { return c * q + min(c, rem); }
 // the CTA whose range contains flattened k-block s
-__device__ __forceinline__ int sk_owner(long long s, long long T, long long G) {
-  long long c = s * G / T;
-  while (c + 1 < G && sk_lo(c + 1, T, G) <= s) ++c;
-  while (c > 0 && sk_lo(c, T, G) > s) --c;
-  return (int)c;
+__device__ __forceinline__ int sk_owner(int s, int q, int rem) {
+  const int big = rem * (q + 1);
+  return s < big ? (int)((unsigned)s / (unsigned)(q + 1)) : rem + (int)((unsigned)(s - big) / (unsigned)q);
 }
 
 __global__ void __launch_bounds__(SK_THREADS, 2)
 gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                            const SkinnyParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ int s_last;
+  __shared__ int s_last[2];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + SK_STAGES * SK_STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -75,9 +75,8 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   const uint32_t tmem_slot = bar_base + 8u * (2 * SK_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long T = p.total_kb, G = gridDim.x;
   const int KB = p.kb_per_tile;
-  const long long lo = sk_lo(blockIdx.x, T, G), hi = sk_lo(blockIdx.x + 1, T, G);
+  const int lo = sk_lo(blockIdx.x, p.q, p.rem), hi = sk_lo(blockIdx.x + 1, p.q, p.rem);
 
   if (warp == 0 && lane == 0) {
     if (!p.w_tiled) tma_prefetch_desc(&tmap_w);
@@ -98,25 +97,33 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
     if (lane == 0) {
       // Weights never depend on an earlier kernel: fill the whole ring with W tiles BEFORE waiting for the producer
       // of X, so the weight stream is already in flight while the previous kernel drains.
-      const int npre = (int)min((long long)SK_STAGES, hi - lo);
+      const int npre = min(SK_STAGES, hi - lo);
+      int tile = lo / KB, kb = lo - tile * KB;  // advanced incrementally: no division in the issue loop
+      const int tile0 = tile, kb0 = kb;
       for (int i = 0; i < npre; ++i) {
-        const long long f = lo + i;
+        const int f = lo + i;
         mbar_arrive_expect_tx(full_bar(i), (p.debug & 1) ? SK_W_BYTES : SK_STAGE_BYTES);
         if (p.w_tiled) bulk_load_1d_hint(smem_base + i * SK_STAGE_BYTES, p.w_tiled + (size_t)f * (SK_BM * SK_BK), SK_W_BYTES, full_bar(i), kEvictFirst);
-        else tma_load_2d_hint(smem_base + i * SK_STAGE_BYTES, &tmap_w, full_bar(i), (int)(f % KB) * SK_BK, (int)(f / KB) * SK_BM, kEvictFirst);
+        else tma_load_2d_hint(smem_base + i * SK_STAGE_BYTES, &tmap_w, full_bar(i), kb * SK_BK, tile * SK_BM, kEvictFirst);
+        if (++kb == KB) { kb = 0; ++tile; }
       }
       pdl_wait();
-      for (int i = 0; i < npre && !(p.debug & 1); ++i)
-        tma_load_2d_hint(smem_base + i * SK_STAGE_BYTES + SK_W_BYTES, &tmap_x, full_bar(i), (int)((lo + i) % KB) * SK_BK, 0, kEvictLast);
+      {
+        int kx = kb0, tx_ = tile0;
+        for (int i = 0; i < npre && !(p.debug & 1); ++i) {
+          tma_load_2d_hint(smem_base + i * SK_STAGE_BYTES + SK_W_BYTES, &tmap_x, full_bar(i), kx * SK_BK, 0, kEvictLast);
+          if (++kx == KB) { kx = 0; ++tx_; }
+        }
+      }
       uint32_t stage = 0, phase = 1;  // ring position after the prefill above (npre == SK_STAGES wraps to stage 0)
-      for (long long f = lo + npre; f < hi; ++f) {
+      for (int f = lo + npre; f < hi; ++f) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_arrive_expect_tx(full_bar(stage), (p.debug & 1) ? SK_W_BYTES : SK_STAGE_BYTES);
         const uint32_t sw = smem_base + stage * SK_STAGE_BYTES;
-        const int kb = (int)(f % KB), tile = (int)(f / KB);
         if (p.w_tiled) bulk_load_1d_hint(sw, p.w_tiled + (size_t)f * (SK_BM * SK_BK), SK_W_BYTES, full_bar(stage), kEvictFirst);
         else tma_load_2d_hint(sw, &tmap_w, full_bar(stage), kb * SK_BK, tile * SK_BM, kEvictFirst);   // weights: read once
         if (!(p.debug & 1)) tma_load_2d_hint(sw + SK_W_BYTES, &tmap_x, full_bar(stage), kb * SK_BK, 0, kEvictLast);  // X: shared by all CTAs
+        if (++kb == KB) { kb = 0; ++tile; }
         if (++stage == SK_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -124,13 +131,15 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(SK_BM, SK_MB);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      long long f = lo;
+      int f = lo;
+      int tile_end = (lo / KB + 1) * KB;
       while (f < hi) {
-        const long long seg_end = min(hi, (f / KB + 1) * KB);
+        const int seg_end = min(hi, tile_end);
+        tile_end += KB;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * SK_MB;
-        for (long long g = f; g < seg_end; ++g) {
+        for (int g = f; g < seg_end; ++g) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sw = smem_base + stage * SK_STAGE_BYTES;
@@ -152,21 +161,29 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
       }
     }
   } else {
+    // ===================== epilogue warps =====================
+    // Per segment: TMEM -> registers; a tile this CTA owns alone is finished straight from registers; a shared tile is
+    // parked in the workspace and the last contributor (ticket) reduces it.  Publication follows the semaphore
+    // pattern (stores; bar; ONE thread: fence + atomic; bar) instead of a fence in every thread.
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int tt = (warp - 2) * 32 + lane;
     pdl_wait();  // before the first write to the shared workspace / read of residual
     uint32_t acc = 0, acc_phase = 0;
-    long long f = lo;
+    int seg_parity = 0;
+    int f = lo;
+    const int first_tile = lo / KB;
+    int tile = first_tile;
     while (f < hi) {
-      const int tile = (int)(f / KB);
-      const long long t0 = (long long)tile * KB;
-      const long long seg_end = min(hi, t0 + KB);
-      const int c_first = sk_owner(t0, T, G), c_last = sk_owner(t0 + KB - 1, T, G);
+      const int t0 = tile * KB;
+      const int seg_end = min(hi, t0 + KB);
+      const int c_first = sk_owner(t0, p.q, p.rem), c_last = sk_owner(t0 + KB - 1, p.q, p.rem);
       const int n_contrib = c_last - c_first + 1;
-      const int my_seg = tile - (int)(lo / KB);
-      // ---- park the partial tile: ws[cta][segment index within the CTA][row 0..127][b 0..31] ----
+      const bool tr = (p.trace != nullptr) && tt == 0 && seg_end == hi;
+      unsigned long long* trp = p.trace ? p.trace + (size_t)blockIdx.x * 8 : nullptr;
+      if (tr) trp[0] = globaltimer_ns();
       mbar_wait(tfull_bar(acc), acc_phase);
+      if (tr) trp[1] = globaltimer_ns();
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * SK_MB, r);
@@ -174,79 +191,108 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator free: the MMA warp may start the next segment
-      if (p.debug & 4) { acc ^= 1; if (acc == 0) acc_phase ^= 1; f = seg_end; continue; }
-      float* wrow = p.ws + (((size_t)blockIdx.x * p.max_segs + my_seg) * SK_BM + row) * SK_MB;
+      if (p.debug & 4) { acc ^= 1; if (acc == 0) acc_phase ^= 1; f = seg_end; ++tile; continue; }
+      const bool swiglu = p.act == CRAB_ACT_SWIGLU;
+      bool reduce_from_ws = false;
+      if (n_contrib == 1 && !swiglu) {
+        // ---- sole owner: finish from registers (thread = weight row n, 32 batch values) ----
+        const int n = tile * SK_BM + row;
+        if (n < p.N) {
+          const float bias = p.bias ? p.bias[n] : 0.f;
+          float resv[32];
 #pragma unroll
-      for (int g = 0; g < 8; ++g)
-        __stcg(reinterpret_cast<float4*>(wrow) + g, make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
-                                                                __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])));
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (tt == 0) {
-        const int old = atomicAdd(p.counters + tile, 1);
-        s_last = (old == n_contrib - 1);
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const bool last = s_last != 0;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone has read s_last before the next segment rewrites it
-      if (last) {
-        __threadfence();
-        if (p.act == CRAB_ACT_SWIGLU) {
-          // tile rows = [64 gate | 64 up]  ->  64 output columns
-          const int n = tile * 64 + tt;
-          if (tt < 64 && n < (p.N >> 1)) {
-            float g[32], u[32];
+          for (int b = 0; b < 32; ++b)  // all residual loads first: C may alias the residual (in-place x += ...)
+            resv[b] = (p.residual != nullptr && b < p.M) ? __bfloat162float(p.residual[(size_t)b * p.ldr + n]) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { g[j] = 0.f; u[j] = 0.f; }
-            for (int s = 0; s < n_contrib; ++s) {
-              const int cc = c_first + s;
-              const float* wt = p.ws + ((size_t)cc * p.max_segs + (tile - (int)(sk_lo(cc, T, G) / KB))) * SK_BM * SK_MB;
-              const float* pg = wt + (size_t)tt * SK_MB;
-              const float* pu = wt + (size_t)(tt + 64) * SK_MB;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 a = ldcg4(pg + 4 * q), b = ldcg4(pu + 4 * q);
-                g[4 * q] += a.x; g[4 * q + 1] += a.y; g[4 * q + 2] += a.z; g[4 * q + 3] += a.w;
-                u[4 * q] += b.x; u[4 * q + 1] += b.y; u[4 * q + 2] += b.z; u[4 * q + 3] += b.w;
-              }
+          for (int b = 0; b < 32; ++b) {
+            if (b < p.M) {
+              const float v = __uint_as_float(r[b]) + bias + resv[b];
+              if (p.out_dtype == CRAB_BF16) reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(v);
+              else reinterpret_cast<float*>(p.C)[(size_t)b * p.ldc + n] = v;
             }
+          }
+        }
+      } else {
+        // ---- park the partial tile: ws[cta][segment index within the CTA][row 0..127][b 0..31] ----
+        const int my_seg = tile - first_tile;
+        float* wrow = p.ws + (((size_t)blockIdx.x * p.max_segs + my_seg) * SK_BM + row) * SK_MB;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (!(p.debug & 32)) __stcg(reinterpret_cast<float4*>(wrow) + g, make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                                                                  __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])));
+        if (tr) trp[2] = globaltimer_ns();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tr) trp[3] = globaltimer_ns();
+        if (tt == 0) {
+          int last = 1;
+          if (p.debug & 16) last = ((int)blockIdx.x == c_last);
+          else if (n_contrib > 1) {
+            __threadfence();  // release: cumulative over the CTA's partial stores ordered by the barrier above
+            last = (atomicAdd(p.counters + tile, 1) == n_contrib - 1);
+            if (last) { __threadfence(); p.counters[tile] = 0; }  // acquire; counter ready for the next launch
+          }
+          s_last[seg_parity] = last;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        reduce_from_ws = s_last[seg_parity] != 0;
+        seg_parity ^= 1;
+        if (tr) trp[4] = globaltimer_ns();
+      }
+      if (reduce_from_ws && !(p.debug & 8)) {
+        // contributor s is CTA c_first + s; its partial for this tile sits at segment index tile - first_tile(cta)
+        const int n_valid = swiglu ? ((tt < 64 && tile * 64 + tt < (p.N >> 1)) ? 1 : 0) : (tile * SK_BM + tt < p.N ? 1 : 0);
+        if (n_valid) {
+          float a[32], u[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { a[j] = 0.f; u[j] = 0.f; }
+          for (int s = 0; s < n_contrib; ++s) {
+            const int cc = c_first + s;
+            // only the first contributor can start before this tile; every later one starts inside it (segment 0)
+            const int seg_idx = (s == 0) ? tile - (int)((unsigned)sk_lo(cc, p.q, p.rem) / (unsigned)KB) : 0;
+            const float* wt = p.ws + ((size_t)cc * p.max_segs + seg_idx) * SK_BM * SK_MB;
+            const float* pa = wt + (size_t)tt * SK_MB;
+            float4 va[8], vu[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) va[q] = ldcg4(pa + 4 * q);
+            if (swiglu) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) vu[q] = ldcg4(pa + 64 * SK_MB + 4 * q);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              a[4 * q] += va[q].x; a[4 * q + 1] += va[q].y; a[4 * q + 2] += va[q].z; a[4 * q + 3] += va[q].w;
+              if (swiglu) { u[4 * q] += vu[q].x; u[4 * q + 1] += vu[q].y; u[4 * q + 2] += vu[q].z; u[4 * q + 3] += vu[q].w; }
+            }
+          }
+          if (tr) trp[5] = globaltimer_ns();
+          if (swiglu) {
+            const int n = tile * 64 + tt;
             __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C);
 #pragma unroll
             for (int b = 0; b < 32; ++b)
-              if (b < p.M) c[(size_t)b * p.ldc + n] = __float2bfloat16_rn(g[b] / (1.0f + __expf(-g[b])) * u[b]);
-          }
-        } else {
-          const int n = tile * SK_BM + tt;
-          if (n < p.N) {
-            float a[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) a[j] = 0.f;
-            for (int s = 0; s < n_contrib; ++s) {
-              const int cc = c_first + s;
-              const float* pa = p.ws + (((size_t)cc * p.max_segs + (tile - (int)(sk_lo(cc, T, G) / KB))) * SK_BM + tt) * SK_MB;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 v = ldcg4(pa + 4 * q);
-                a[4 * q] += v.x; a[4 * q + 1] += v.y; a[4 * q + 2] += v.z; a[4 * q + 3] += v.w;
-              }
-            }
+              if (b < p.M) c[(size_t)b * p.ldc + n] = __float2bfloat16_rn(a[b] / (1.0f + __expf(-a[b])) * u[b]);
+          } else {
+            const int n = tile * SK_BM + tt;
             const float bias = p.bias ? p.bias[n] : 0.f;
+#pragma unroll
+            for (int b = 0; b < 32; ++b)  // residual loads first (C may alias the residual); u[] is free here
+              u[b] = (p.residual != nullptr && b < p.M) ? __bfloat162float(p.residual[(size_t)b * p.ldr + n]) : 0.f;
 #pragma unroll
             for (int b = 0; b < 32; ++b) {
               if (b < p.M) {
-                float v = a[b] + bias;
-                if (p.residual) v += __bfloat162float(p.residual[(size_t)b * p.ldr + n]);
+                const float v = a[b] + bias + u[b];
                 if (p.out_dtype == CRAB_BF16) reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(v);
                 else reinterpret_cast<float*>(p.C)[(size_t)b * p.ldc + n] = v;
               }
             }
           }
         }
-        if (tt == 0) p.counters[tile] = 0;  // ready for the next launch (stream order)
       }
+      if (tr) trp[6] = globaltimer_ns();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
       f = seg_end;
+      ++tile;
     }
   }
   tc_fence_before();
@@ -279,6 +325,8 @@ __global__ void pack_skinny_weight_kernel(const __nv_bfloat16* __restrict__ w, i
   *reinterpret_cast<uint4*>(out + i * 8) = v;
 }
 
+static unsigned long long* g_trace = nullptr;  // diagnostic timestamps (CRAB_SK_TRACE=1)
+
 // CTAs for (N, K): one per SM, but never so many that a CTA streams fewer than 8 k-blocks or a tile gets more than
 // SK_MAX_SLOTS contributors.
 int choose_ctas(int N, int K) {
@@ -300,6 +348,15 @@ extern "C" int crab_gemm_skinny_plan(int N, int K, int* ctas, int64_t* workspace
   *ctas = choose_ctas(N, K);
   *workspace_bytes = (int64_t)(tiles + 2 * (*ctas)) * SK_BM * SK_MB * 4;
   *n_counters = tiles;
+  return CRAB_OK;
+}
+
+extern "C" int crab_debug_skinny_trace(unsigned long long* host_out, int n_ctas) {
+  // diagnostic: copy the per-CTA epilogue timestamps (8 per CTA) of the latest launch made with CRAB_SK_TRACE=1
+  using namespace crab;
+  CRAB_REQUIRE(g_trace != nullptr && host_out != nullptr && n_ctas > 0 && n_ctas <= 1024, "crab_debug_skinny_trace: tracing is off");
+  CRAB_CHECK_CUDA(cudaDeviceSynchronize());
+  CRAB_CHECK_CUDA(cudaMemcpy(host_out, g_trace, (size_t)n_ctas * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return CRAB_OK;
 }
 
@@ -363,8 +420,15 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
   p.M = a->M; p.N = a->N; p.K = a->K; p.ldc = a->ldc; p.ldr = a->ldr;
   p.act = a->act; p.out_dtype = a->out_dtype;
   p.w_tiled = reinterpret_cast<const __nv_bfloat16*>(a->W_packed);
+  {
+    static int want = -1;
+    if (want < 0) { const char* e = getenv("CRAB_SK_TRACE"); want = (e && e[0] == '1') ? 1 : 0; }
+    if (want && !g_trace) { cudaMalloc(&g_trace, 1024 * 8 * sizeof(unsigned long long)); cudaMemset(g_trace, 0, 1024 * 8 * sizeof(unsigned long long)); }
+    p.trace = want ? g_trace : nullptr;
+  }
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("CRAB_SK_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
-  p.tiles = tiles; p.kb_per_tile = kb; p.total_kb = T; p.max_segs = max_segs;
+  p.tiles = tiles; p.kb_per_tile = kb; p.total_kb = (int)T; p.max_segs = max_segs;
+  p.q = (int)(T / ctas); p.rem = (int)(T % ctas);
   CRAB_CHECK_CUDA(launch_pdl(gemm_skinny_tcgen05_kernel, dim3((unsigned)ctas), dim3(SK_THREADS), SK_SMEM, stream, tw, tx, p));
   return CRAB_OK;
 }

@@ -184,6 +184,7 @@ int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, float eps, v
                         int ldra, int groups, void* z, int ldz, float scale, int rows, int cols, void* stream);
 
 /* Diagnostic (not on the product path): pure HBM->smem ring streaming, used by tools/ to size the decode pipelines. */
+int crab_debug_skinny_trace(unsigned long long* host_out, int n_ctas);
 int crab_debug_stream(const void* src, int64_t bytes, int chunk_bytes, int stages, int ctas, void* sink, void* stream);
 
 #ifdef __cplusplus
