@@ -268,7 +268,7 @@ class CrabEngine:
                 lo = self.lora
                 L["wqkv_p"] = ops.pack_skinny_weight(wq, k=D + (self.EXT_QKV if lo else 0))
                 L["wo_p"] = ops.pack_skinny_weight(wo, k=nq + (self.EXT_O if lo else 0))
-                L["wgu_p"] = ops.pack_skinny_weight(L["wgu"], k=D + (self.EXT_GU if lo else 0))
+                L["wgu_p"] = ops.pack_skinny_weight(L["wgu"], k=D + (self.EXT_GU if lo else 0), swiglu=True)
                 L["wd_p"] = ops.pack_skinny_weight(wd, k=F + (self.EXT_D if lo else 0))
             self.layers.append(L)
         self.rope = ops.rope_table(self.cfg.max_ctx, hd, c.rope_theta, dev)
@@ -597,7 +597,7 @@ class CrabEngine:
         at = self._buf(tag + "_attn", (M, nq + self.EXT_O), zero=True)
         hh = self._buf(tag + "_h", (M, F + self.EXT_D), zero=True)
         ctx = self.cfg.max_ctx
-        skinny = (S == 1 and len_dev is not None and M <= 32)  # decode step: weight-streaming kernels
+        skinny = (S == 1 and len_dev is not None and M <= 32 and self.decode_packed)  # decode step: weight streaming
         sc = self.scaling
         for li, L in enumerate(self.layers):
             if skinny:
@@ -624,7 +624,7 @@ class CrabEngine:
                 ops.gemm_skinny(at, L.get("wo_p", L["wo"]), residual=x, out=x, k=nq + (self.EXT_O if self.lora else 0))
                 ops.row_norm_loraz(x, gamma=L["ln2"], eps=c.eps, y=xn[:, :D], ra=L.get("ra_gu"), groups=2 if self.lora else 0,
                                    z=xn[:, D:] if self.lora else None, scale=sc)
-                ops.gemm_skinny(xn, L.get("wgu_p", L["wgu"]), act=ops.ACT_SWIGLU, out=hh[:, :F], k=D + (self.EXT_GU if self.lora else 0))
+                ops.gemm_skinny(xn, L["wgu_p"], act=ops.ACT_SWIGLU, out=hh[:, :F])
                 if self.lora:
                     ops.row_norm_loraz(hh[:, :F], ra=L["ra_d"], groups=1, z=hh[:, F:], scale=sc)
                 ops.gemm_skinny(hh, L.get("wd_p", L["wd"]), residual=x, out=x, k=F + (self.EXT_D if self.lora else 0))

@@ -77,7 +77,7 @@ class AttnArgs(C.Structure):
 class SkinnyArgs(C.Structure):
     _fields_ = [
         ("X", C.c_void_p), ("W", C.c_void_p), ("W_packed", C.c_void_p), ("C", C.c_void_p), ("bias", C.c_void_p),
-        ("residual", C.c_void_p), ("workspace", C.c_void_p), ("counters", C.c_void_p), ("workspace_bytes", C.c_int64), ("n_counters", C.c_int32),
+        ("residual", C.c_void_p),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("ldx", C.c_int32), ("ldw", C.c_int32), ("ldc", C.c_int32),
         ("ldr", C.c_int32), ("act", C.c_int32), ("out_dtype", C.c_int32), ("splits", C.c_int32),
     ]

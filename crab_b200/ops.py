@@ -335,32 +335,18 @@ def add_scalar_i32(p: torch.Tensor, v: int):
 
 
 # ---- decode-step kernels ------------------------------------------------------------------------------------------
-_SKINNY_WS_BYTES = 32 << 20
-_SKINNY_COUNTERS = 2048
-_skinny_bufs = {}
-
-
-def _skinny_scratch(device):
-    """Split-K workspace + ticket counters, shared by all skinny GEMMs on a device (they run in stream order).
-    Allocated once so the pointers captured in CUDA graphs stay valid."""
-    key = (device.type, device.index)
-    if key not in _skinny_bufs:
-        _skinny_bufs[key] = (torch.empty(_SKINNY_WS_BYTES // 4, device=device, dtype=torch.float32),
-                             torch.zeros(_SKINNY_COUNTERS, device=device, dtype=torch.int32))
-    return _skinny_bufs[key]
-
-
 class PackedWeight:
     """A decode weight in the streaming layout of crab_pack_skinny_weight (plus its logical shape)."""
 
-    __slots__ = ("data", "N", "K")
+    __slots__ = ("data", "N", "K", "swiglu")
 
-    def __init__(self, data: torch.Tensor, N: int, K: int):
-        self.data, self.N, self.K = data, N, K
+    def __init__(self, data: torch.Tensor, N: int, K: int, swiglu: bool = False):
+        self.data, self.N, self.K, self.swiglu = data, N, K, swiglu
 
 
-def pack_skinny_weight(w: torch.Tensor, k: Optional[int] = None) -> PackedWeight:
-    """Row-major bf16 [N, >=K] -> contiguous pre-swizzled 16 KB (tile, k-block) blocks for gemm_skinny."""
+def pack_skinny_weight(w: torch.Tensor, k: Optional[int] = None, swiglu: bool = False) -> PackedWeight:
+    """Row-major bf16 [N, >=K] -> contiguous pre-swizzled 16 KB (tile, k-block) blocks for gemm_skinny.
+    swiglu=True: `w` is in the prefill layout ([64 gate | 64 up] row groups); rows are interleaved for the decode kernel."""
     _req_cuda(w)
     assert w.dim() == 2 and w.dtype == torch.bfloat16 and w.stride(1) == 1
     N, K = w.shape[0], (k if k is not None else w.shape[1])
@@ -368,9 +354,10 @@ def pack_skinny_weight(w: torch.Tensor, k: Optional[int] = None) -> PackedWeight
     _l.check(_l.load().crab_skinny_packed_bytes(_i(N), _i(K), C.byref(nbytes)), "crab_skinny_packed_bytes")
     out = torch.empty(nbytes.value // 2, device=w.device, dtype=torch.bfloat16)
     assert out.data_ptr() % 128 == 0
-    _l.check(_l.load().crab_pack_skinny_weight(_vp(w), _i(N), _i(K), _i(w.stride(0)), _vp(out), _stream()), "crab_pack_skinny_weight")
+    _l.check(_l.load().crab_pack_skinny_weight(_vp(w), _i(N), _i(K), _i(w.stride(0)), _vp(out), _i(1 if swiglu else 0), _stream()),
+             "crab_pack_skinny_weight")
     count_launches(1)
-    return PackedWeight(out, N, K)
+    return PackedWeight(out, N, K, swiglu)
 
 
 def gemm_skinny(x: torch.Tensor, w, *, bias: Optional[torch.Tensor] = None,
@@ -392,9 +379,10 @@ def gemm_skinny(x: torch.Tensor, w, *, bias: Optional[torch.Tensor] = None,
     n_out = N // 2 if act == ACT_SWIGLU else N
     if out is None:
         out = torch.empty((M, n_out), device=x.device, dtype=out_dtype)
-    ws, cnt = _skinny_scratch(x.device)
-    args = _l.SkinnyArgs(X=_ptr(x), W=None if packed else _ptr(w), W_packed=_ptr(w.data) if packed else None, C=_ptr(out), bias=_ptr(bias), residual=_ptr(residual),
-                         workspace=_ptr(ws), counters=_ptr(cnt), workspace_bytes=ws.numel() * 4, n_counters=cnt.numel(),
+    if act == ACT_SWIGLU:
+        assert packed and w.swiglu, "decode SwiGLU needs pack_skinny_weight(..., swiglu=True)"
+    args = _l.SkinnyArgs(X=_ptr(x), W=None if packed else _ptr(w), W_packed=_ptr(w.data) if packed else None, C=_ptr(out),
+                         bias=_ptr(bias), residual=_ptr(residual),
                          M=M, N=N, K=K, ldx=x.stride(0), ldw=0 if packed else w.stride(0), ldc=out.stride(0),
                          ldr=(residual.stride(0) if residual is not None else 0), act=act,
                          out_dtype=(BF16 if out.dtype == torch.bfloat16 else F32), splits=splits)

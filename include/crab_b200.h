@@ -152,39 +152,36 @@ int crab_add_scalar_i32(int* p, int v, void* stream);
 /* ------------------------------------------------------------------------------------------------------------------
  * Decode-step (M <= 32 rows) kernels
  * crab_gemm_skinny_bf16 replaces: the same nn.Linear / hyper-LoRA linears at q_len == 1 (HF generate's per-token
- *           forward, models/unified_llama.py:125-127): swap-AB tcgen05 weight streaming, split-K with a deterministic
- *           last-CTA reduction.  crab_gemm_skinny_plan returns the split count, workspace size and ticket-counter
- *           count for (N, K); `counters` must be zero before the first launch (the kernel re-zeroes them).
+ *           forward, models/unified_llama.py:125-127): swap-AB tcgen05 weight streaming; K is split across the CTAs
+ *           of a thread-block cluster and reduced through distributed shared memory (deterministic, no workspace).
+ *           crab_gemm_skinny_plan reports the K-split the library would pick for (N, K).
+ * crab_pack_skinny_weight: streaming layout for decode weights — block (tile, kb) = the 128x64 tile, pre-swizzled for
+ *           the tensor core, 16 KB contiguous; `out` needs crab_skinny_packed_bytes(N, K) bytes, 128-byte aligned.
+ *           swiglu_interleave=1 converts the prefill layout ([64 gate | 64 up] row groups) to interleaved rows
+ *           (2i = gate_i, 2i+1 = up_i), which CRAB_ACT_SWIGLU requires here.
  * crab_row_norm_loraz replaces: LlamaRMSNorm + lora_route / lora_A projections + fp32 router softmax for up to three
  *           linears sharing one input row (peft_hyper/tuners/lora.py:344-350).  gamma/y NULL = no norm (LoRA only).
  * ---------------------------------------------------------------------------------------------------------------- */
 typedef struct crab_skinny_args {
   const void* X;        /* bf16 [M, ldx], M <= 32 */
   const void* W;        /* bf16 [N, ldw] row-major (read through TMA), or NULL when W_packed is given */
-  const void* W_packed; /* same weight pre-packed by crab_pack_skinny_weight (contiguous 16 KB tile blocks) or NULL */
+  const void* W_packed; /* same weight pre-packed by crab_pack_skinny_weight, or NULL */
   void* C;              /* [M, ldc] bf16 or fp32 */
   const float* bias;    /* fp32 [N] or NULL */
-  const void* residual; /* bf16 [M, ldr] or NULL */
-  float* workspace;
-  int32_t* counters;
-  int64_t workspace_bytes;
-  int32_t n_counters;
+  const void* residual; /* bf16 [M, ldr] or NULL (may alias C) */
   int32_t M, N, K, ldx, ldw, ldc, ldr;
-  int32_t act;          /* CRAB_ACT_NONE or CRAB_ACT_SWIGLU */
+  int32_t act;          /* CRAB_ACT_NONE or CRAB_ACT_SWIGLU (needs W_packed with swiglu_interleave) */
   int32_t out_dtype;
-  int32_t splits;       /* stream-K CTA count; 0 = one per SM */
+  int32_t splits;       /* K-split = cluster size, 1..8; 0 = auto */
 } crab_skinny_args;
-int crab_gemm_skinny_plan(int N, int K, int* ctas, int64_t* workspace_bytes, int* n_counters);
-/* Streaming layout for decode weights: block (tile, kb) = the 128x64 tile, pre-swizzled for the tensor core, 16 KB
- * contiguous; `out` needs crab_skinny_packed_bytes(N, K) bytes, 128-byte aligned. */
+int crab_gemm_skinny_plan(int N, int K, int* splits, int64_t* workspace_bytes, int* n_counters);
 int crab_skinny_packed_bytes(int N, int K, int64_t* bytes);
-int crab_pack_skinny_weight(const void* W, int N, int K, int ldw, void* out, void* stream);
+int crab_pack_skinny_weight(const void* W, int N, int K, int ldw, void* out, int swiglu_interleave, void* stream);
 int crab_gemm_skinny_bf16(const crab_skinny_args* args, void* stream);
 int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, float eps, void* y, int ldy, const void* ra,
                         int ldra, int groups, void* z, int ldz, float scale, int rows, int cols, void* stream);
 
 /* Diagnostic (not on the product path): pure HBM->smem ring streaming, used by tools/ to size the decode pipelines. */
-int crab_debug_skinny_trace(unsigned long long* host_out, int n_ctas);
 int crab_debug_stream(const void* src, int64_t bytes, int chunk_bytes, int stages, int ctas, void* sink, void* stream);
 
 #ifdef __cplusplus

@@ -119,7 +119,7 @@ def test_gemm_lora_z(cuda_dev):
 
 @pytest.mark.parametrize("M", [1, 7, 32])
 @pytest.mark.parametrize("N,K,splits", [(256, 512, 0), (4096, 4128, 0), (12288, 4192, 3), (1000, 328, 2), (32024, 1024, 1),
-                                        (4096, 11040, 9), (4096, 11040, 0), (22016, 4160, 100), (12288, 4192, 0), (384, 4096, 40)])
+                                        (4096, 11040, 8), (4096, 11040, 5), (22016, 4160, 7), (12288, 4192, 0), (384, 4096, 6)])
 def test_gemm_skinny(cuda_dev, M, N, K, splits):
     from crab_b200 import ops
 
@@ -157,12 +157,11 @@ def test_gemm_skinny_swiglu_matches_prefill_kernel(cuda_dev):
     wu = (torch.randn(F, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(cuda_dev)
     packed = torch.stack([wg.view(F // 64, 64, K), wu.view(F // 64, 64, K)], dim=1).reshape(2 * F, K).contiguous()
     ref = torch.nn.functional.silu(a.float() @ wg.float().t()) * (a.float() @ wu.float().t())
-    pk = ops.pack_skinny_weight(packed)
-    for splits in (1, 2, 0, 7):  # `splits` = CTA count of the stream-K partition (0 = auto)
-        out = ops.gemm_skinny(a, packed, act=ops.ACT_SWIGLU, splits=splits)
+    pk = ops.pack_skinny_weight(packed, swiglu=True)  # prefill layout -> interleaved decode layout
+    for splits in (1, 2, 0, 3, 5, 7, 8):  # K-split = cluster size (0 = auto)
+        out = ops.gemm_skinny(a, pk, act=ops.ACT_SWIGLU, splits=splits)
         assert out.shape == (M, F)
         _check(out, ref)
-        assert torch.equal(ops.gemm_skinny(a, pk, act=ops.ACT_SWIGLU, splits=splits), out)
     _check(ops.gemm(a, packed, act=ops.ACT_SWIGLU), ref)
 
 

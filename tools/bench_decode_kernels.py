@@ -32,18 +32,8 @@ for name, N, K in [("qkv", 12288, 4192), ("o", 4096, 4128), ("gateup", 22016, 41
     x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
     out = torch.empty(M, N // 2 if name == "gateup" else N, device=dev, dtype=torch.bfloat16)
     act = ops.ACT_SWIGLU if name == "gateup" else ops.ACT_NONE
-    for splits in [0, 296]:  # CTA count of the stream-K partition (0 = one per SM)
-        def fn():
-            for r in range(3):
-                for W in Ws:
-                    ops.gemm_skinny(x, W, act=act, out=out, splits=splits)
-            return 3 * nW
-        us = time_graph(fn)
-        gbs = (N * K * 2 + M * K * 2) / us / 1e3
-        res[f"skinny_{name}_s{splits}"] = dict(us=round(us, 2), gbs=round(gbs, 1))
-        print(f"skinny {name:8s} N={N} K={K} splits={splits:2d}: {us:8.2f} us  {gbs:8.1f} GB/s", flush=True)
-    Wp = [ops.pack_skinny_weight(W) for W in Ws]
-    for splits in [0, 296]:
+    Wp = [ops.pack_skinny_weight(W, swiglu=(name == "gateup")) for W in Ws]
+    for splits in [0, 1, 2, 4, 8]:
         def fnp():
             for r in range(3):
                 for W in Wp:

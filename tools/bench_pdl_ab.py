@@ -25,7 +25,7 @@ M = 32
 print("CRAB_PDL =", os.environ.get("CRAB_PDL", "1"))
 for name, N, K in [("qkv", 12288, 4192), ("o", 4096, 4128), ("gateup", 22016, 4160), ("down", 4096, 11040)]:
     nW = max(2, math.ceil((600 << 20) / (N * K * 2)))
-    Ws = [ops.pack_skinny_weight(torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.02) for _ in range(nW)]
+    Ws = [ops.pack_skinny_weight(torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.02, swiglu=(name == "gateup")) for _ in range(nW)]
     x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
     out = torch.empty(M, N // 2 if name == "gateup" else N, device=dev, dtype=torch.bfloat16)
     act = ops.ACT_SWIGLU if name == "gateup" else ops.ACT_NONE
