@@ -50,12 +50,11 @@ struct FlashParams {
   const float* table;  // [H, Sq, Sk] or null   (bias = gate * table)
 };
 
-template <int HD>
+template <int HD, int MT>
 struct FlashCfg {
-  static constexpr int BM = 64, BN = 64, THREADS = 128;
-  static constexpr int CHUNKS = HD / 8;  // 16-byte chunks per row
+  static constexpr int BM = 64 * MT, BN = 64, THREADS = 128;  // MT m16-tiles of query rows per warp
   static constexpr int TILE_BYTES = 64 * HD * 2;
-  static constexpr int SMEM = TILE_BYTES * 5;  // Q + 2 x (K, V)
+  static constexpr int SMEM = TILE_BYTES * (MT + 4);  // Q (MT tiles) + 2 x (K, V)
 };
 
 // smem tile: row-major [64][HD] bf16, 16-byte chunk c of row r stored at chunk (c ^ (r & 7))
@@ -75,12 +74,13 @@ __device__ __forceinline__ void load_tile(uint32_t sbase, const __nv_bfloat16* g
   }
 }
 
-template <int HD>
+// Each warp owns MT x 16 query rows, so every K / V fragment fetched from shared memory (ldmatrix) feeds MT MMAs.
+template <int HD, int MT>
 __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
-  using Cfg = FlashCfg<HD>;
+  using Cfg = FlashCfg<HD, MT>;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem);
-  const uint32_t sK0 = sQ + Cfg::TILE_BYTES;
+  const uint32_t sK0 = sQ + MT * Cfg::TILE_BYTES;
   const uint32_t sV0 = sK0 + 2 * Cfg::TILE_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -96,23 +96,31 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
     n_tiles = min(n_tiles, last_key / Cfg::BN + 1);
   }
 
-  load_tile<HD>(sQ, qg, p.q_rs, q0, p.Sq);
+#pragma unroll
+  for (int t = 0; t < MT; ++t) load_tile<HD>(sQ + t * Cfg::TILE_BYTES, qg, p.q_rs, q0 + t * 64, p.Sq);
   load_tile<HD>(sK0, kg, p.k_rs, 0, p.Sk);
   load_tile<HD>(sV0, vg, p.v_rs, 0, p.Sk);
   cp_async_commit();
 
   constexpr int DT = HD / 8;  // output n8-tiles per row
-  float o_acc[DT][4];
+  float o_acc[MT][DT][4];
+  float m_run[MT][2], l_run[MT][2];
+  int r_lo[MT];               // global query row of c0/c1 for m-tile mt; c2/c3 are r_lo + 8
+  float gate_lo[MT], gate_hi[MT];
 #pragma unroll
-  for (int i = 0; i < DT; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
-  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-  const float sl2 = p.scale * 1.4426950408889634f;
-  const int r_lo = q0 + warp * 16 + (lane >> 2);  // global query row of c0/c1; c2/c3 are r_lo + 8
-  float gate_lo = 0.f, gate_hi = 0.f;
-  if (p.gate) {
-    if (r_lo < p.Sq) gate_lo = p.gate[((size_t)b * p.H + h) * p.Sq + r_lo];
-    if (r_lo + 8 < p.Sq) gate_hi = p.gate[((size_t)b * p.H + h) * p.Sq + r_lo + 8];
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int i = 0; i < DT; ++i) { o_acc[mt][i][0] = o_acc[mt][i][1] = o_acc[mt][i][2] = o_acc[mt][i][3] = 0.f; }
+    m_run[mt][0] = m_run[mt][1] = -INFINITY;
+    l_run[mt][0] = l_run[mt][1] = 0.f;
+    r_lo[mt] = q0 + (warp * MT + mt) * 16 + (lane >> 2);
+    gate_lo[mt] = gate_hi[mt] = 0.f;
+    if (p.gate) {
+      if (r_lo[mt] < p.Sq) gate_lo[mt] = p.gate[((size_t)b * p.H + h) * p.Sq + r_lo[mt]];
+      if (r_lo[mt] + 8 < p.Sq) gate_hi[mt] = p.gate[((size_t)b * p.H + h) * p.Sq + r_lo[mt] + 8];
+    }
   }
+  const float sl2 = p.scale * 1.4426950408889634f;
 
   for (int t = 0; t < n_tiles; ++t) {
     const int buf = t & 1;
@@ -127,18 +135,21 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
     __syncthreads();
     const uint32_t sK = sK0 + buf * Cfg::TILE_BYTES, sV = sV0 + buf * Cfg::TILE_BYTES;
 
-    // ---- S = Q K^T  (16 x 64 per warp) ----
-    float s[8][4];
+    // ---- S = Q K^T  (MT x 16 x 64 per warp) ----
+    float s[MT][8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[mt][i][0] = s[mt][i][1] = s[mt][i][2] = s[mt][i][3] = 0.f; }
 #pragma unroll
     for (int ks = 0; ks < HD / 16; ++ks) {
-      uint32_t a[4];
-      {
+      uint32_t a[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
         // A fragment (m16 x k16): matrices (rows 0-7,k0-7), (rows 8-15,k0-7), (rows 0-7,k8-15), (rows 8-15,k8-15)
-        const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int rr = (warp * MT + mt) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;  // row within the BM-row Q block
         const int c = ks * 2 + (lane >> 4);
-        ldsm_x4(tile_addr<HD>(sQ, r, c), a[0], a[1], a[2], a[3]);
+        ldsm_x4(tile_addr<HD>(sQ + (rr >> 6) * Cfg::TILE_BYTES, rr & 63, c), a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
       }
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
@@ -147,69 +158,78 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
         const int n = np * 16 + (lane & 7) + (lane >> 4) * 8;
         const int c = ks * 2 + ((lane >> 3) & 1);
         ldsm_x4(tile_addr<HD>(sK, n, c), b0, b1, b2, b3);
-        mma_bf16(s[np * 2], a, b0, b1);
-        mma_bf16(s[np * 2 + 1], a, b2, b3);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16(s[mt][np * 2], a[mt], b0, b1);
+          mma_bf16(s[mt][np * 2 + 1], a[mt], b2, b3);
+        }
       }
     }
 
     // ---- scale, bias, mask, online softmax (log2 domain) ----
     const int k0 = t * Cfg::BN;
-    float mx[2] = {m_run[0], m_run[1]};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int mt = 0; mt < MT; ++mt) {
+      float mx[2] = {m_run[mt][0], m_run[mt][1]};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int kj = k0 + nt * 8 + (lane & 3) * 2 + (e & 1);
-        const int hi = e >> 1;
-        const int qi = r_lo + hi * 8;
-        float v = s[nt][e] * sl2;
-        if (p.table != nullptr && qi < p.Sq && kj < p.Sk)
-          v += (hi ? gate_hi : gate_lo) * p.table[((size_t)h * p.Sq + qi) * p.Sk + kj] * 1.4426950408889634f;
-        const bool masked = (kj >= p.Sk) || (p.causal && kj > qi + off);
-        v = masked ? -INFINITY : v;
-        s[nt][e] = v;
-        mx[hi] = fmaxf(mx[hi], v);
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int kj = k0 + nt * 8 + (lane & 3) * 2 + (e & 1);
+          const int hi = e >> 1;
+          const int qi = r_lo[mt] + hi * 8;
+          float v = s[mt][nt][e] * sl2;
+          if (p.table != nullptr && qi < p.Sq && kj < p.Sk)
+            v += (hi ? gate_hi[mt] : gate_lo[mt]) * p.table[((size_t)h * p.Sq + qi) * p.Sk + kj] * 1.4426950408889634f;
+          const bool masked = (kj >= p.Sk) || (p.causal && kj > qi + off);
+          v = masked ? -INFINITY : v;
+          s[mt][nt][e] = v;
+          mx[hi] = fmaxf(mx[hi], v);
+        }
       }
-    }
 #pragma unroll
-    for (int hi = 0; hi < 2; ++hi) {
-      mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 1));
-      mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 2));
-    }
-    float corr[2], msafe[2];
-#pragma unroll
-    for (int hi = 0; hi < 2; ++hi) {
-      msafe[hi] = (mx[hi] == -INFINITY) ? 0.f : mx[hi];
-      corr[hi] = exp2f(m_run[hi] - msafe[hi]);
-      m_run[hi] = mx[hi];
-      l_run[hi] *= corr[hi];
-    }
-    float rs[2] = {0.f, 0.f};
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float pv = exp2f(s[nt][e] - msafe[e >> 1]);
-        s[nt][e] = pv;
-        rs[e >> 1] += pv;
+      for (int hi = 0; hi < 2; ++hi) {
+        mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 1));
+        mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 2));
       }
-    }
-    l_run[0] += rs[0];
-    l_run[1] += rs[1];
+      float corr[2], msafe[2];
 #pragma unroll
-    for (int i = 0; i < DT; ++i) {
-      o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
-      o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+      for (int hi = 0; hi < 2; ++hi) {
+        msafe[hi] = (mx[hi] == -INFINITY) ? 0.f : mx[hi];
+        corr[hi] = exp2f(m_run[mt][hi] - msafe[hi]);
+        m_run[mt][hi] = mx[hi];
+        l_run[mt][hi] *= corr[hi];
+      }
+      float rs[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pv = exp2f(s[mt][nt][e] - msafe[e >> 1]);
+          s[mt][nt][e] = pv;
+          rs[e >> 1] += pv;
+        }
+      }
+      l_run[mt][0] += rs[0];
+      l_run[mt][1] += rs[1];
+#pragma unroll
+      for (int i = 0; i < DT; ++i) {
+        o_acc[mt][i][0] *= corr[0]; o_acc[mt][i][1] *= corr[0];
+        o_acc[mt][i][2] *= corr[1]; o_acc[mt][i][3] *= corr[1];
+      }
     }
 
     // ---- O += P V ----
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
-      uint32_t a[4];
-      a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-      a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-      a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      uint32_t a[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        a[mt][0] = pack_bf16x2(s[mt][2 * kk][0], s[mt][2 * kk][1]);
+        a[mt][1] = pack_bf16x2(s[mt][2 * kk][2], s[mt][2 * kk][3]);
+        a[mt][2] = pack_bf16x2(s[mt][2 * kk + 1][0], s[mt][2 * kk + 1][1]);
+        a[mt][3] = pack_bf16x2(s[mt][2 * kk + 1][2], s[mt][2 * kk + 1][3]);
+      }
 #pragma unroll
       for (int dp = 0; dp < DT / 2; ++dp) {
         uint32_t b0, b1, b2, b3;
@@ -217,29 +237,35 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
         const int key = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int c = dp * 2 + (lane >> 4);
         ldsm_x4_t(tile_addr<HD>(sV, key, c), b0, b1, b2, b3);
-        mma_bf16(o_acc[dp * 2], a, b0, b1);
-        mma_bf16(o_acc[dp * 2 + 1], a, b2, b3);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16(o_acc[mt][dp * 2], a[mt], b0, b1);
+          mma_bf16(o_acc[mt][dp * 2 + 1], a[mt], b2, b3);
+        }
       }
     }
     __syncthreads();
   }
 
   // ---- finalise ----
-#pragma unroll
-  for (int hi = 0; hi < 2; ++hi) {
-    l_run[hi] += __shfl_xor_sync(0xffffffffu, l_run[hi], 1);
-    l_run[hi] += __shfl_xor_sync(0xffffffffu, l_run[hi], 2);
-  }
-  const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
-  const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
   __nv_bfloat16* og = p.o + b * p.o_bs + h * p.o_hs;
 #pragma unroll
-  for (int i = 0; i < DT; ++i) {
-    const int col = i * 8 + (lane & 3) * 2;
-    if (r_lo < p.Sq)
-      *reinterpret_cast<uint32_t*>(og + (long long)r_lo * p.o_rs + col) = pack_bf16x2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
-    if (r_lo + 8 < p.Sq)
-      *reinterpret_cast<uint32_t*>(og + (long long)(r_lo + 8) * p.o_rs + col) = pack_bf16x2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      l_run[mt][hi] += __shfl_xor_sync(0xffffffffu, l_run[mt][hi], 1);
+      l_run[mt][hi] += __shfl_xor_sync(0xffffffffu, l_run[mt][hi], 2);
+    }
+    const float inv0 = l_run[mt][0] > 0.f ? 1.f / l_run[mt][0] : 0.f;
+    const float inv1 = l_run[mt][1] > 0.f ? 1.f / l_run[mt][1] : 0.f;
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+      const int col = i * 8 + (lane & 3) * 2;
+      if (r_lo[mt] < p.Sq)
+        *reinterpret_cast<uint32_t*>(og + (long long)r_lo[mt] * p.o_rs + col) = pack_bf16x2(o_acc[mt][i][0] * inv0, o_acc[mt][i][1] * inv0);
+      if (r_lo[mt] + 8 < p.Sq)
+        *reinterpret_cast<uint32_t*>(og + (long long)(r_lo[mt] + 8) * p.o_rs + col) = pack_bf16x2(o_acc[mt][i][2] * inv1, o_acc[mt][i][3] * inv1);
+    }
   }
 }
 
@@ -416,17 +442,27 @@ extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
   p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
   p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.Sq = a->Sq; p.Sk = a->Sk;
   p.scale = a->scale; p.causal = a->causal; p.gate = a->gate; p.table = a->bias_table;
-  dim3 grid((a->Sq + 63) / 64, a->H, a->B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->head_dim == 64) {
-    static bool set = false;
-    if (!set) { CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlashCfg<64>::SMEM)); set = true; }
-    flash_attn_kernel<64><<<grid, 128, FlashCfg<64>::SMEM, st>>>(p);
-  } else {
-    static bool set = false;
-    if (!set) { CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlashCfg<128>::SMEM)); set = true; }
-    flash_attn_kernel<128><<<grid, 128, FlashCfg<128>::SMEM, st>>>(p);
+  // 32 query rows per warp (MT = 2) when there are enough rows to fill 128-row blocks; short sequences (Q-Former's 32
+  // queries, BEATs' 48 tokens) keep 64-row blocks.
+  const bool big = a->Sq > 64;
+#define CRAB_FLASH_LAUNCH(HD_, MT_)                                                                                        \
+  {                                                                                                                        \
+    static bool set = false;                                                                                               \
+    if (!set) {                                                                                                            \
+      CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                           FlashCfg<HD_, MT_>::SMEM));                                                     \
+      set = true;                                                                                                          \
+    }                                                                                                                      \
+    dim3 grid((a->Sq + FlashCfg<HD_, MT_>::BM - 1) / FlashCfg<HD_, MT_>::BM, a->H, a->B);                                  \
+    flash_attn_kernel<HD_, MT_><<<grid, 128, FlashCfg<HD_, MT_>::SMEM, st>>>(p);                                           \
   }
+  if (a->head_dim == 64) {
+    if (big) CRAB_FLASH_LAUNCH(64, 2) else CRAB_FLASH_LAUNCH(64, 1)
+  } else {
+    if (big) CRAB_FLASH_LAUNCH(128, 2) else CRAB_FLASH_LAUNCH(128, 1)
+  }
+#undef CRAB_FLASH_LAUNCH
   CRAB_CHECK_CUDA(cudaGetLastError());
   return CRAB_OK;
 }
