@@ -167,30 +167,46 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
     }
 
     // ---- scale, bias, mask, online softmax (log2 domain) ----
+    // Interior tiles (no key past Sk, nothing above the causal diagonal, no bias) take the fast path: the raw scores stay
+    // in registers and the scale is folded into the exponent's FFMA; only edge / diagonal / biased tiles pay for the
+    // per-element index arithmetic.
     const int k0 = t * Cfg::BN;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      float mx[2] = {m_run[mt][0], m_run[mt][1]};
+      const int q_min = q0 + (warp * MT + mt) * 16;  // smallest query row of this m-tile (warp-uniform)
+      const bool general = (p.table != nullptr) || (k0 + Cfg::BN > p.Sk) || (p.causal && (k0 + Cfg::BN - 1 > q_min + off));
+      float mx[2] = {-INFINITY, -INFINITY};
+      if (general) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int kj = k0 + nt * 8 + (lane & 3) * 2 + (e & 1);
-          const int hi = e >> 1;
-          const int qi = r_lo[mt] + hi * 8;
-          float v = s[mt][nt][e] * sl2;
-          if (p.table != nullptr && qi < p.Sq && kj < p.Sk)
-            v += (hi ? gate_hi[mt] : gate_lo[mt]) * p.table[((size_t)h * p.Sq + qi) * p.Sk + kj] * 1.4426950408889634f;
-          const bool masked = (kj >= p.Sk) || (p.causal && kj > qi + off);
-          v = masked ? -INFINITY : v;
-          s[mt][nt][e] = v;
-          mx[hi] = fmaxf(mx[hi], v);
+          for (int e = 0; e < 4; ++e) {
+            const int kj = k0 + nt * 8 + (lane & 3) * 2 + (e & 1);
+            const int hi = e >> 1;
+            const int qi = r_lo[mt] + hi * 8;
+            float v = s[mt][nt][e] * sl2;
+            if (p.table != nullptr && qi < p.Sq && kj < p.Sk)
+              v += (hi ? gate_hi[mt] : gate_lo[mt]) * p.table[((size_t)h * p.Sq + qi) * p.Sk + kj] * 1.4426950408889634f;
+            const bool masked = (kj >= p.Sk) || (p.causal && kj > qi + off);
+            v = masked ? -INFINITY : v;
+            s[mt][nt][e] = v;
+            mx[hi] = fmaxf(mx[hi], v);
+          }
         }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          mx[0] = fmaxf(mx[0], fmaxf(s[mt][nt][0], s[mt][nt][1]));
+          mx[1] = fmaxf(mx[1], fmaxf(s[mt][nt][2], s[mt][nt][3]));
+        }
+        mx[0] *= sl2;  // sl2 > 0: max commutes with the scale
+        mx[1] *= sl2;
       }
 #pragma unroll
       for (int hi = 0; hi < 2; ++hi) {
         mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 1));
         mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 2));
+        mx[hi] = fmaxf(mx[hi], m_run[mt][hi]);
       }
       float corr[2], msafe[2];
 #pragma unroll
@@ -201,13 +217,25 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
         l_run[mt][hi] *= corr[hi];
       }
       float rs[2] = {0.f, 0.f};
+      if (general) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float pv = exp2f(s[mt][nt][e] - msafe[e >> 1]);
-          s[mt][nt][e] = pv;
-          rs[e >> 1] += pv;
+          for (int e = 0; e < 4; ++e) {
+            const float pv = exp2f(s[mt][nt][e] - msafe[e >> 1]);
+            s[mt][nt][e] = pv;
+            rs[e >> 1] += pv;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float pv = exp2f(fmaf(s[mt][nt][e], sl2, -msafe[e >> 1]));
+            s[mt][nt][e] = pv;
+            rs[e >> 1] += pv;
+          }
         }
       }
       l_run[mt][0] += rs[0];
