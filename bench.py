@@ -35,6 +35,15 @@ sys.path.insert(0, str(ROOT))
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
+def load_traffic():
+    """dram__bytes_read+write per launch from the committed ncu --set full capture (profiles/ncu_traffic.json)."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        return json.loads(p.read_text())
+    except Exception:
+        return {}
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -427,6 +436,33 @@ def main():
                     "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / max(d["launches"], 1)}
         roof["peak_source"] = peaks_src
         roof["share_of_step"] = shares[top] / ms_step
+        traffic = load_traffic()
+        tkey = top[len("decode:"):] if top.startswith("decode:") else top
+        if tkey in traffic:
+            roof["traffic"] = traffic[tkey]["traffic_bytes_per_launch"]
+            roof["traffic_note"] = f"ncu dram bytes of one launch, {traffic[tkey]['shape']} ({traffic.get('_source', '')})"
+        # the other kernels that matter, same arithmetic (per kernel class, averaged over its launches in the step)
+        def _roof(tag, dct, scale=1.0, bound="tensor"):
+            d_ = dct.get(tag)
+            if not d_ or d_["ms"] <= 0:
+                return None
+            t_ms = d_["ms"] * scale
+            if bound == "tensor":
+                a_ = d_["flops"] / (t_ms * 1e-3) / 1e12
+                return {"bound": "tensor", "achieved": a_, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": a_ / peaks["bf16_tflops_sustained"], "ms_per_step": t_ms}
+            a_ = d_["bytes"] / (t_ms * 1e-3) / 1e9
+            return {"bound": "hbm", "achieved": a_, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a_ / peaks["hbm_gbs"],
+                    "ms_per_step": t_ms}
+        dscale = graph_step_ms / max(dec_eager_ms, 1e-9)
+        kd_step = {k: dict(v, ms=v["ms"] * (args.new_tokens - 1), bytes=v["bytes"] * (args.new_tokens - 1)) for k, v in kd.items()}
+        if "crab_attn_decode" in kd_step:
+            kd_step["crab_attn_decode"]["bytes"] = kv_bytes * (args.new_tokens - 1)
+        rooflines = {
+            "prefill_gemm_tcgen05<256>": _roof("gemm_bf16_tcgen05<256>", kt),
+            "decode_gemm_skinny_tcgen05": _roof("gemm_skinny_tcgen05", kd_step, dscale, "hbm"),
+            "decode_attention": _roof("crab_attn_decode", kd_step, dscale, "hbm"),
+        }
         gemm_ms = sum(d["ms"] for k, d in kt.items() if k.startswith("gemm"))
         gemm_fl = sum(d["flops"] for k, d in kt.items() if k.startswith("gemm"))
         phases = {
@@ -459,7 +495,7 @@ def main():
             "config": workload_config(args), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "crab_b200.models.unified_llama.UnifiedForCausalLM.generate", "ids_equal_resident_run": e2e_same},
-            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "phases": phases,
+            "gpu_launches": int(launches), "roofline": roof, "rooflines": rooflines, "cpu_baseline": cpu, "phases": phases,
             "deterministic_across_steps": deterministic, "weights": "random-init (seeded), generated on device",
             "load_s": round(t_load, 1),
         }
