@@ -473,7 +473,7 @@ extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // 32 query rows per warp (MT = 2) when there are enough rows to fill 128-row blocks; short sequences (Q-Former's 32
   // queries, BEATs' 48 tokens) keep 64-row blocks.
-  const bool big = a->Sq > 64;
+  const bool big = a->Sq >= 512;  // N=257 (CLIP) wastes less with 64-row blocks (5 x 64 vs 3 x 128 row slots)
 #define CRAB_FLASH_LAUNCH(HD_, MT_)                                                                                        \
   {                                                                                                                        \
     static bool set = false;                                                                                               \

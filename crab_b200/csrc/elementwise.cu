@@ -401,6 +401,19 @@ __global__ void __launch_bounds__(256) row_loraz_kernel(const __nv_bfloat16* __r
       for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
     }
   }
+  // The router/A rows do not depend on the norm: for short rows fetch them now so the loads fly during the reduction.
+  constexpr bool PRE = (VPT <= 2);
+  const __nv_bfloat16* rg = (groups > 0) ? ra + (size_t)grp * 11 * ldra : nullptr;
+  uint4 rq[PRE ? VPT : 1][11];
+  if (PRE && groups > 0) {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int vi = threadIdx.x + i * 256;
+#pragma unroll
+      for (int o = 0; o < 11; ++o)
+        rq[PRE ? i : 0][o] = (vi < nvec) ? __ldg(reinterpret_cast<const uint4*>(rg + (size_t)o * ldra) + vi) : make_uint4(0, 0, 0, 0);
+    }
+  }
   if (NORM) {
     const float rstd = rsqrtf(block_sum(ss, sh) / cols + eps);
 #pragma unroll
@@ -418,7 +431,6 @@ __global__ void __launch_bounds__(256) row_loraz_kernel(const __nv_bfloat16* __r
     }
   }
   if (groups == 0) return;
-  const __nv_bfloat16* rg = ra + (size_t)grp * 11 * ldra;
   float acc[11];
 #pragma unroll
   for (int o = 0; o < 11; ++o) acc[o] = 0.f;
@@ -428,7 +440,8 @@ __global__ void __launch_bounds__(256) row_loraz_kernel(const __nv_bfloat16* __r
     if (vi < nvec) {
       uint4 q[11];
 #pragma unroll
-      for (int o = 0; o < 11; ++o) q[o] = __ldg(reinterpret_cast<const uint4*>(rg + (size_t)o * ldra) + vi);  // 11 loads in flight
+      for (int o = 0; o < 11; ++o)
+        q[o] = PRE ? rq[PRE ? i : 0][o] : __ldg(reinterpret_cast<const uint4*>(rg + (size_t)o * ldra) + vi);  // 11 loads in flight
 #pragma unroll
       for (int o = 0; o < 11; ++o) {
         float rf[8];

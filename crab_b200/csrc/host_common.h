@@ -35,8 +35,8 @@ int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint6
 
 int sm_count();
 
-// 1 = launch the decode-chain kernels with the programmatic-stream-serialization attribute (env CRAB_PDL=1 or
-// crab_set_pdl(1); default off: the A/B in profiles/ shows the chain is faster without it for now).
+// Programmatic dependent launch level (env CRAB_PDL or crab_set_pdl): 0 = off (default: the A/B in profiles/ shows the
+// chain is faster without it for now), 1 = every decode-chain kernel, 2 = the light kernels only (not the streaming GEMM).
 int pdl_enabled();
 
 template <typename... KArgs, typename... Args>

@@ -31,8 +31,8 @@ const char* crab_last_error(void);
 /* Library / device probe: returns CRAB_OK when device `dev` is compute capability 10.x. */
 int crab_init(int dev);
 int crab_version(void);
-/* Programmatic dependent launch for the decode-chain kernels (default off; env CRAB_PDL=1 or crab_set_pdl(1)). */
-int crab_set_pdl(int on);
+/* Programmatic dependent launch for the decode-chain kernels: 0 off (default), 1 all, 2 light kernels only (env CRAB_PDL). */
+int crab_set_pdl(int level);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Dense linear:  C[M,N] = epilogue( A[M,K] . B[N,K]^T )       (tcgen05 + TMEM + TMA, persistent, warp-specialised)
