@@ -518,15 +518,15 @@ extern "C" int crab_attn_decode(const void* q, int ldq, const void* k_cache, con
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
 #define CRAB_DECODE_CASE(HD_, G_) \
-  if (head_dim == HD_ && G == G_) { e = launch_pdl(attn_decode_kernel<HD_, G_>, grid, dim3(128), 0, st, p); } else
+  if (head_dim == HD_ && G == G_) { e = launch_pdl(PDL_ATTN, attn_decode_kernel<HD_, G_>, grid, dim3(128), 0, st, p); } else
   CRAB_DECODE_CASE(128, 1) CRAB_DECODE_CASE(128, 2) CRAB_DECODE_CASE(128, 4) CRAB_DECODE_CASE(128, 7)
   CRAB_DECODE_CASE(128, 8) CRAB_DECODE_CASE(64, 1)
   { return set_error(CRAB_ERR_INVALID, "crab_attn_decode: unsupported head_dim=%d group=%d", head_dim, G); }
 #undef CRAB_DECODE_CASE
   CRAB_CHECK_CUDA(e);
   if (nsplit > 1) {
-    if (head_dim == 128) e = launch_pdl(attn_decode_combine_kernel<128>, dim3(B * H), dim3(128), 0, st, (const float*)workspace, p.o, ldo, H, nsplit);
-    else e = launch_pdl(attn_decode_combine_kernel<64>, dim3(B * H), dim3(64), 0, st, (const float*)workspace, p.o, ldo, H, nsplit);
+    if (head_dim == 128) e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<128>, dim3(B * H), dim3(128), 0, st, (const float*)workspace, p.o, ldo, H, nsplit);
+    else e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<64>, dim3(B * H), dim3(64), 0, st, (const float*)workspace, p.o, ldo, H, nsplit);
     CRAB_CHECK_CUDA(e);
   }
   return CRAB_OK;

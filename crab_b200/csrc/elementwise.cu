@@ -105,11 +105,11 @@ static int launch_norm(const void* x, int ldx, const float* gamma, const float* 
   auto xx = reinterpret_cast<const __nv_bfloat16*>(x);
   auto yy = reinterpret_cast<__nv_bfloat16*>(y);
   cudaError_t e;
-  if (nvec <= 128) e = launch_pdl(norm_kernel<RMS, 1>, dim3(rows), dim3(128), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
-  else if (nvec <= 256) e = launch_pdl(norm_kernel<RMS, 1>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
-  else if (nvec <= 512) e = launch_pdl(norm_kernel<RMS, 2>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
-  else if (nvec <= 1024) e = launch_pdl(norm_kernel<RMS, 4>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
-  else e = launch_pdl(norm_kernel<RMS, 8>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  if (nvec <= 128) e = launch_pdl(PDL_LIGHT, norm_kernel<RMS, 1>, dim3(rows), dim3(128), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else if (nvec <= 256) e = launch_pdl(PDL_LIGHT, norm_kernel<RMS, 1>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else if (nvec <= 512) e = launch_pdl(PDL_LIGHT, norm_kernel<RMS, 2>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else if (nvec <= 1024) e = launch_pdl(PDL_LIGHT, norm_kernel<RMS, 4>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
+  else e = launch_pdl(PDL_LIGHT, norm_kernel<RMS, 8>, dim3(rows), dim3(256), 0, st, xx, ldx, gamma, beta, yy, ldy, rows, cols, eps);
   CRAB_CHECK_CUDA(e);
   return CRAB_OK;
 }
@@ -379,7 +379,6 @@ __global__ void __launch_bounds__(256) row_loraz_kernel(const __nv_bfloat16* __r
   // grid = (rows, max(groups, 1)): block (row, g) owns the 11 outputs of linear g; the norm is recomputed per block
   // (8 KB row read) and written by the g == 0 block only.
   pdl_trigger();
-  pdl_wait();
   __shared__ float sh[32];
   __shared__ float red[8][11];
   __shared__ float tot[11];
@@ -387,6 +386,21 @@ __global__ void __launch_bounds__(256) row_loraz_kernel(const __nv_bfloat16* __r
   const int nvec = cols >> 3;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const __nv_bfloat16* xr = x + (size_t)row * ldx;
+  // The router/A rows are weights (no dependence on the previous kernel): for short rows fetch them BEFORE the PDL wait
+  // so the loads fly while the producer of x drains, and during the norm reduction.
+  constexpr bool PRE = (VPT <= 2);
+  const __nv_bfloat16* rg = (groups > 0) ? ra + (size_t)grp * 11 * ldra : nullptr;
+  uint4 rq[PRE ? VPT : 1][11];
+  if (PRE && groups > 0) {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int vi = threadIdx.x + i * 256;
+#pragma unroll
+      for (int o = 0; o < 11; ++o)
+        rq[PRE ? i : 0][o] = (vi < nvec) ? __ldg(reinterpret_cast<const uint4*>(rg + (size_t)o * ldra) + vi) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  pdl_wait();
   float v[VPT][8];
   float ss = 0.f;
 #pragma unroll
@@ -399,19 +413,6 @@ __global__ void __launch_bounds__(256) row_loraz_kernel(const __nv_bfloat16* __r
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
-    }
-  }
-  // The router/A rows do not depend on the norm: for short rows fetch them now so the loads fly during the reduction.
-  constexpr bool PRE = (VPT <= 2);
-  const __nv_bfloat16* rg = (groups > 0) ? ra + (size_t)grp * 11 * ldra : nullptr;
-  uint4 rq[PRE ? VPT : 1][11];
-  if (PRE && groups > 0) {
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      const int vi = threadIdx.x + i * 256;
-#pragma unroll
-      for (int o = 0; o < 11; ++o)
-        rq[PRE ? i : 0][o] = (vi < nvec) ? __ldg(reinterpret_cast<const uint4*>(rg + (size_t)o * ldra) + vi) : make_uint4(0, 0, 0, 0);
     }
   }
   if (NORM) {
@@ -519,9 +520,9 @@ extern "C" int crab_rope_kv_append(void* qkv, int ldq, const float* cos_sin, voi
   auto kc = reinterpret_cast<__nv_bfloat16*>(k_cache);
   auto vc = reinterpret_cast<__nv_bfloat16*>(v_cache);
   if (head_dim == 128)
-    CRAB_CHECK_CUDA(launch_pdl(rope_kv_kernel<128>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, q, ldq, cos_sin, kc, vc, B, S, H, KV, ctx_max, past_dev, past_host));
+    CRAB_CHECK_CUDA(launch_pdl(PDL_ROPE, rope_kv_kernel<128>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, q, ldq, cos_sin, kc, vc, B, S, H, KV, ctx_max, past_dev, past_host));
   else
-    CRAB_CHECK_CUDA(launch_pdl(rope_kv_kernel<64>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, q, ldq, cos_sin, kc, vc, B, S, H, KV, ctx_max, past_dev, past_host));
+    CRAB_CHECK_CUDA(launch_pdl(PDL_ROPE, rope_kv_kernel<64>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, q, ldq, cos_sin, kc, vc, B, S, H, KV, ctx_max, past_dev, past_host));
   return CRAB_OK;
 }
 
@@ -530,7 +531,7 @@ extern "C" int crab_gather_rows(const void* src, int lds, const int64_t* src_row
   CRAB_REQUIRE(src && dst, "crab_gather_rows: null pointer");
   CRAB_REQUIRE(cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "crab_gather_rows: cols/ld must be multiples of 8");
   if (n <= 0) return CRAB_OK;
-  CRAB_CHECK_CUDA(launch_pdl(gather_rows_kernel, dim3(n), dim3(128), 0, (cudaStream_t)stream,
+  CRAB_CHECK_CUDA(launch_pdl(PDL_LIGHT, gather_rows_kernel, dim3(n), dim3(128), 0, (cudaStream_t)stream,
                              reinterpret_cast<const __nv_bfloat16*>(src), lds, src_rows,
                              reinterpret_cast<__nv_bfloat16*>(dst), ldd, dst_rows, n, cols));
   return CRAB_OK;
@@ -604,7 +605,7 @@ extern "C" int crab_beats_posconv_finish(const void* x, const void* conv_g, cons
 extern "C" int crab_argmax(const float* logits, int ld, int rows, int V, int64_t* out, void* stream) {
   CRAB_REQUIRE(logits && out && V > 0, "crab_argmax: bad args");
   if (rows <= 0) return CRAB_OK;
-  CRAB_CHECK_CUDA(launch_pdl(argmax_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, logits, ld, V, out));
+  CRAB_CHECK_CUDA(launch_pdl(PDL_LIGHT, argmax_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, logits, ld, V, out));
   return CRAB_OK;
 }
 
@@ -630,8 +631,8 @@ extern "C" int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, f
 #define CRAB_ROW_CASE(V)                                                                                              \
   if (vpt <= V) {                                                                                                     \
     const dim3 grid(rows, groups > 0 ? groups : 1);                                                                   \
-    if (gamma) e = launch_pdl(row_loraz_kernel<true, V>, grid, dim3(256), 0, st, xx, ldx, gamma, eps, yy, ldy, rr, ldra, groups, zz, ldz, scale, cols); \
-    else e = launch_pdl(row_loraz_kernel<false, V>, grid, dim3(256), 0, st, xx, ldx, gamma, eps, yy, ldy, rr, ldra, groups, zz, ldz, scale, cols);      \
+    if (gamma) e = launch_pdl(PDL_ROW, row_loraz_kernel<true, V>, grid, dim3(256), 0, st, xx, ldx, gamma, eps, yy, ldy, rr, ldra, groups, zz, ldz, scale, cols); \
+    else e = launch_pdl(PDL_ROW, row_loraz_kernel<false, V>, grid, dim3(256), 0, st, xx, ldx, gamma, eps, yy, ldy, rr, ldra, groups, zz, ldz, scale, cols);      \
   } else
   CRAB_ROW_CASE(2) CRAB_ROW_CASE(4) CRAB_ROW_CASE(8) { return set_error(CRAB_ERR_INVALID, "crab_row_norm_loraz: cols too large"); }
 #undef CRAB_ROW_CASE
@@ -641,6 +642,6 @@ extern "C" int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, f
 
 extern "C" int crab_add_scalar_i32(int* p, int v, void* stream) {
   CRAB_REQUIRE(p != nullptr, "crab_add_scalar_i32: null pointer");
-  CRAB_CHECK_CUDA(launch_pdl(add_scalar_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, p, v));
+  CRAB_CHECK_CUDA(launch_pdl(PDL_LIGHT, add_scalar_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, p, v));
   return CRAB_OK;
 }

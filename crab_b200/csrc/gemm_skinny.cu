@@ -369,7 +369,7 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
     at[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl_enabled() == 1) {  // level 2 = light kernels only: the streaming GEMM stays a normal launch
+  if (pdl_mask() & PDL_GEMM) {
     at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

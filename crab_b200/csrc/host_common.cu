@@ -31,10 +31,10 @@ int sm_count() {
 }
 
 static int g_pdl = -1;
-int pdl_enabled() {
+int pdl_mask() {
   if (g_pdl < 0) {
     const char* e = getenv("CRAB_PDL");
-    g_pdl = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 0;  // 0 off (default, profiles/r01_pdl_ab.txt), 1 all, 2 light kernels only
+    g_pdl = (e != nullptr) ? (atoi(e) & 31) : 0;
   }
   return g_pdl;
 }
@@ -80,8 +80,8 @@ extern "C" const char* crab_last_error(void) { return crab::last_error_buf(); }
 
 extern "C" int crab_version(void) { return 1; }
 
-extern "C" int crab_set_pdl(int level) {
-  crab::g_pdl = level < 0 ? 0 : (level > 2 ? 2 : level);
+extern "C" int crab_set_pdl(int mask) {
+  crab::g_pdl = mask & 31;
   return CRAB_OK;
 }
 

@@ -35,12 +35,16 @@ int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint6
 
 int sm_count();
 
-// Programmatic dependent launch level (env CRAB_PDL or crab_set_pdl): 0 = off (default: the A/B in profiles/ shows the
-// chain is faster without it for now), 1 = every decode-chain kernel, 2 = the light kernels only (not the streaming GEMM).
-int pdl_enabled();
+// Programmatic dependent launch (env CRAB_PDL or crab_set_pdl): a bit mask over kernel classes.  A kernel whose class
+// bit is set is launched with cudaLaunchAttributeProgrammaticStreamSerialization, i.e. its CTAs may become resident as
+// soon as every CTA of the PREVIOUS kernel in the stream has executed griddepcontrol.launch_dependents (all decode-chain
+// kernels do so at their top) and block in griddepcontrol.wait until that kernel has completed.  The mask is read at
+// launch time, so the host can change it between two launches (the engine does, see engine._decoder_layers).
+enum PdlClass { PDL_GEMM = 1, PDL_ROW = 2, PDL_ROPE = 4, PDL_ATTN = 8, PDL_LIGHT = 16 };
+int pdl_mask();
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -50,7 +54,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_mask() & cls) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -13,6 +13,7 @@ Reference call stack being replaced:
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -21,6 +22,7 @@ import torch
 from . import ops
 
 SD = Dict[str, torch.Tensor]
+DEFAULT_PDL_PLAN = "0,0"
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -165,6 +167,10 @@ class CrabEngine:
             self._pack_beats(sd)
             self._pack_bridges(sd)
         self._bufs: Dict[Tuple, torch.Tensor] = {}
+        # Programmatic dependent launch over the decode chain: (mask for the chain, mask for the kernel that follows the
+        # decode attention).  Env CRAB_PDL_PLAN="chain,after_attn" overrides; see profiles/r02_pdl_plans.txt for the A/B.
+        plan = os.environ.get("CRAB_PDL_PLAN", DEFAULT_PDL_PLAN).split(",")
+        self.pdl_chain, self.pdl_after_attn = int(plan[0]), int(plan[-1])
         self._graph = None
         self._graph_bs = None
         self._use_graph = False
@@ -619,9 +625,17 @@ class CrabEngine:
                                v_strides=(KV * ctx * hd, hd, ctx * hd), o_strides=(S * (nq + self.EXT_O), nq + self.EXT_O, hd),
                                scale=1 / math.sqrt(hd), causal=True)
             if skinny:
+                # the kernel right after the decode attention is launched under its own PDL mask: early-resident
+                # streaming-GEMM CTAs must not squat on the SMs while the 1024-CTA attention kernel still runs
+                if self.pdl_after_attn != self.pdl_chain:
+                    ops.set_pdl(self.pdl_after_attn)
                 if self.lora:
                     ops.row_norm_loraz(at[:, :nq], ra=L["ra_o"], groups=1, z=at[:, nq:], scale=sc)
+                    if self.pdl_after_attn != self.pdl_chain:
+                        ops.set_pdl(self.pdl_chain)
                 ops.gemm_skinny(at, L.get("wo_p", L["wo"]), residual=x, out=x, k=nq + (self.EXT_O if self.lora else 0))
+                if self.pdl_after_attn != self.pdl_chain:
+                    ops.set_pdl(self.pdl_chain)
                 ops.row_norm_loraz(x, gamma=L["ln2"], eps=c.eps, y=xn[:, :D], ra=L.get("ra_gu"), groups=2 if self.lora else 0,
                                    z=xn[:, D:] if self.lora else None, scale=sc)
                 ops.gemm_skinny(xn, L["wgu_p"], act=ops.ACT_SWIGLU, out=hh[:, :F])
@@ -673,11 +687,15 @@ class CrabEngine:
     def _decode_body(self, B: int, nsplit: int, ws):
         D = self.cfg.decoder.hidden
         x = self._buf("dec_x", (B, D))
-        ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)  # embed_tokens of the previous arg-max
-        self._decoder_layers(x, B, 1, past=0, past_dev=self.past_dev, len_dev=self.len_dev, nsplit=nsplit, ws=ws, tag="dec")
-        self._head(x, self.logits, self.next_ids)
-        ops.add_scalar_i32(self.past_dev, 1)
-        ops.add_scalar_i32(self.len_dev, 1)
+        ops.set_pdl(self.pdl_chain)
+        try:
+            ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)  # embed_tokens of the previous arg-max
+            self._decoder_layers(x, B, 1, past=0, past_dev=self.past_dev, len_dev=self.len_dev, nsplit=nsplit, ws=ws, tag="dec")
+            self._head(x, self.logits, self.next_ids)
+            ops.add_scalar_i32(self.past_dev, 1)
+            ops.add_scalar_i32(self.len_dev, 1)
+        finally:
+            ops.set_pdl(0)  # prefill / encoder launches are never PDL launches
 
     def begin_decode(self, B: int, use_graph: bool = True):
         """Prepare the decode loop after a prefill.  With `use_graph`, one decode step (all layers + head + arg-max +

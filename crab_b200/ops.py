@@ -14,6 +14,17 @@ from . import lib as _l
 _launches = 0
 
 
+PDL_GEMM, PDL_ROW, PDL_ROPE, PDL_ATTN, PDL_LIGHT = 1, 2, 4, 8, 16
+_pdl_mask = None
+
+
+def set_pdl(mask: int) -> None:
+    """Programmatic-dependent-launch mask over kernel classes (include/crab_b200.h: crab_set_pdl); read at launch time."""
+    global _pdl_mask
+    _l.check(_l.load().crab_set_pdl(C.c_int(int(mask) & 31)), "crab_set_pdl")
+    _pdl_mask = int(mask) & 31
+
+
 def launch_count() -> int:
     """Number of crab_b200 CUDA kernels launched (or replayed from a captured graph) so far in this process."""
     return _launches

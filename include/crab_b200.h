@@ -31,8 +31,10 @@ const char* crab_last_error(void);
 /* Library / device probe: returns CRAB_OK when device `dev` is compute capability 10.x. */
 int crab_init(int dev);
 int crab_version(void);
-/* Programmatic dependent launch for the decode-chain kernels: 0 off (default), 1 all, 2 light kernels only (env CRAB_PDL). */
-int crab_set_pdl(int level);
+/* Programmatic dependent launch for the decode-chain kernels: bit mask over kernel classes (env CRAB_PDL gives the
+ * initial value, default 0): 1 = weight-streaming GEMM, 2 = row norm/LoRA pre-pass, 4 = RoPE + KV append,
+ * 8 = decode attention, 16 = the other light kernels (norm, gather, arg-max, counters).  Read at launch time. */
+int crab_set_pdl(int mask);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Dense linear:  C[M,N] = epilogue( A[M,K] . B[N,K]^T )       (tcgen05 + TMEM + TMA, persistent, warp-specialised)
