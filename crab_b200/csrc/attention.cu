@@ -308,6 +308,7 @@ struct DecodeParams {
   int B, H, KVH, ctx_max, nsplit;
   const int* len_dev; int len_host;           // number of valid keys
   float scale;
+  int late_trigger;                           // PDL: release the dependent kernel after the streaming loop, not at the top
 };
 
 template <int HD, int G>
@@ -317,7 +318,10 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
   constexpr int NSUB = 4 * KPW;      // independent softmax states per block
   __shared__ float sh_m[NSUB][G], sh_l[NSUB][G];
   __shared__ float sh_acc[NSUB][G][HD];
-  pdl_trigger();
+  // With an early trigger the next kernels of a PDL chain (ultimately the streaming GEMM, 100 KB smem / 32 K registers per
+  // CTA) become resident while this grid still streams the cache and squat on its SM slots; a late trigger releases them
+  // only when every CTA is past its loop, which still hides their launch latency behind the combine/tail.
+  if (!p.late_trigger) pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / LPK, li = lane % LPK;
@@ -392,6 +396,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
       }
     }
   }
+  if (p.late_trigger) pdl_trigger();
   // combine the NSUB partial states
   const int sidx = warp * KPW + sub;
 #pragma unroll
@@ -514,6 +519,7 @@ extern "C" int crab_attn_decode(const void* q, int ldq, const void* k_cache, con
   p.q = (const __nv_bfloat16*)q; p.ldq = ldq; p.kc = (const __nv_bfloat16*)k_cache; p.vc = (const __nv_bfloat16*)v_cache;
   p.o = (__nv_bfloat16*)o; p.ldo = ldo; p.ws = workspace; p.B = B; p.H = H; p.KVH = KVH; p.ctx_max = ctx_max;
   p.nsplit = nsplit; p.len_dev = len_dev; p.len_host = len_host; p.scale = scale;
+  p.late_trigger = (pdl_mask() & PDL_ATTN_LATE) ? 1 : 0;
   dim3 grid(B * KVH, nsplit);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;

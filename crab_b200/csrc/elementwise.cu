@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(256) row_loraz_kernel(const __nv_bfloat16* __r
   for (int i = 0; i < VPT; ++i) {
     const int vi = threadIdx.x + i * 256;
     if (vi < nvec) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + vi), v[i]);
+      unpack8(ld_dep_u4(reinterpret_cast<const uint4*>(xr) + vi), v[i]);  // x comes from the previous kernel: ordered load
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
     } else {

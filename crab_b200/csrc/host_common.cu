@@ -34,7 +34,7 @@ static int g_pdl = -1;
 int pdl_mask() {
   if (g_pdl < 0) {
     const char* e = getenv("CRAB_PDL");
-    g_pdl = (e != nullptr) ? (atoi(e) & 31) : 0;
+    g_pdl = (e != nullptr) ? (atoi(e) & 63) : 0;
   }
   return g_pdl;
 }
@@ -81,7 +81,7 @@ extern "C" const char* crab_last_error(void) { return crab::last_error_buf(); }
 extern "C" int crab_version(void) { return 1; }
 
 extern "C" int crab_set_pdl(int mask) {
-  crab::g_pdl = mask & 31;
+  crab::g_pdl = mask & 63;
   return CRAB_OK;
 }
 

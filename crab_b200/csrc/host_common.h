@@ -40,7 +40,7 @@ int sm_count();
 // soon as every CTA of the PREVIOUS kernel in the stream has executed griddepcontrol.launch_dependents (all decode-chain
 // kernels do so at their top) and block in griddepcontrol.wait until that kernel has completed.  The mask is read at
 // launch time, so the host can change it between two launches (the engine does, see engine._decoder_layers).
-enum PdlClass { PDL_GEMM = 1, PDL_ROW = 2, PDL_ROPE = 4, PDL_ATTN = 8, PDL_LIGHT = 16 };
+enum PdlClass { PDL_GEMM = 1, PDL_ROW = 2, PDL_ROPE = 4, PDL_ATTN = 8, PDL_LIGHT = 16, PDL_ATTN_LATE = 32 /* modifier */ };
 int pdl_mask();
 
 template <typename... KArgs, typename... Args>

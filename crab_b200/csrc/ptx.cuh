@@ -189,6 +189,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // kernel writes, so completion is transitive along the chain.  Both are no-ops for a normal launch.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// 16-byte load of data ANOTHER kernel of the PDL chain produced.  `__ldg` / `const __restrict__` loads compile to
+// LDG.CONSTANT, which the compiler treats as invariant and hoists above griddepcontrol.wait (seen in SASS: every load of
+// the row kernel landed before ACQBULK once anything else preceded the wait) — a read-before-write race against the
+// producer.  This one is ordered: volatile + memory clobber keep it after the wait.
+__device__ __forceinline__ uint4 ld_dep_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------

@@ -55,6 +55,8 @@ class ClipConfig:
     patch: int = 14
     image: int = 224
     eps: float = 1e-5
+    image_mean: Tuple[float, float, float] = (0.48145466, 0.4578275, 0.40821073)  # CLIPImageProcessor (OpenAI CLIP)
+    image_std: Tuple[float, float, float] = (0.26862954, 0.26130258, 0.27577711)
 
 
 @dataclass
@@ -383,13 +385,18 @@ class CrabEngine:
     # forward pieces
     # ==========================================================================================================
     def clip_forward(self, pixels: torch.Tensor) -> torch.Tensor:
-        """pixels fp32 (n,3,H,W) on device -> hidden_states[select_layers[-1]] as bf16 [n*tokens, D] (CLS kept)."""
+        """pixels fp32 (n,3,H,W) — or uint8 frames (n,H,W,3) straight from the video decoder — on device ->
+        hidden_states[select_layers[-1]] as bf16 [n*tokens, D] (CLS kept)."""
         c = self.cfg.clip
         n = pixels.shape[0]
-        g = pixels.shape[2] // c.patch
+        g = (pixels.shape[1] if pixels.dtype == torch.uint8 else pixels.shape[2]) // c.patch
         tokens = g * g + 1
         D = c.hidden
-        patches = ops.patchify(pixels, c.patch, self.clip_kpad)
+        if pixels.dtype == torch.uint8:
+            # raw decoded frames (n, H, W, 3): CLIPImageProcessor's rescale + normalise fused into the im2col
+            patches = ops.patchify_u8(pixels, c.patch, self.clip_kpad, c.image_mean, c.image_std)
+        else:
+            patches = ops.patchify(pixels, c.patch, self.clip_kpad)
         pe = ops.gemm(patches, self.clip_patch_w)
         x = ops.clip_embed_ln(pe, self.clip_cls, self.clip_pos, *self.clip_pre_ln, n, tokens, D, c.eps)
         M = n * tokens
@@ -448,7 +455,7 @@ class CrabEngine:
         VLProjector; models/unified_arch.py:144-149, models/multimodal_encoder.py:119-144)."""
         c = self.cfg.clip
         n = pixels.shape[0]
-        tokens = (pixels.shape[2] // c.patch) ** 2 + 1
+        tokens = ((pixels.shape[1] if pixels.dtype == torch.uint8 else pixels.shape[2]) // c.patch) ** 2 + 1
         x = self.clip_forward(pixels)
         f = ops.layernorm(x, *self.visual_ln, 1e-5)  # CLS rows are normalised too but never read
         qo = self._qformer(self.vq, self.v_query, f, n, tokens - 1, 1, tokens)
@@ -568,10 +575,12 @@ class CrabEngine:
         out: List[Optional[torch.Tensor]] = [None] * len(items)
         groups: Dict[Tuple, List[int]] = {}
         for i, x in enumerate(items):
-            groups.setdefault(tuple(x.shape[1:]), []).append(i)
+            groups.setdefault((x.dtype == torch.uint8,) + tuple(x.shape[1:]), []).append(i)
         nq = self.cfg.n_query
         for shape, idxs in groups.items():
-            xs = torch.cat([items[i].to(self.dev, dtype=torch.float32, non_blocking=True) for i in idxs], 0).contiguous()
+            u8 = all(items[i].dtype == torch.uint8 for i in idxs)  # raw frames stay uint8 (fused normalise + im2col)
+            xs = torch.cat([items[i].to(self.dev, dtype=torch.uint8 if u8 else torch.float32, non_blocking=True)
+                            for i in idxs], 0).contiguous()
             y = fn(xs)
             r = 0
             for i in idxs:

@@ -14,15 +14,15 @@ from . import lib as _l
 _launches = 0
 
 
-PDL_GEMM, PDL_ROW, PDL_ROPE, PDL_ATTN, PDL_LIGHT = 1, 2, 4, 8, 16
+PDL_GEMM, PDL_ROW, PDL_ROPE, PDL_ATTN, PDL_LIGHT, PDL_ATTN_LATE = 1, 2, 4, 8, 16, 32
 _pdl_mask = None
 
 
 def set_pdl(mask: int) -> None:
     """Programmatic-dependent-launch mask over kernel classes (include/crab_b200.h: crab_set_pdl); read at launch time."""
     global _pdl_mask
-    _l.check(_l.load().crab_set_pdl(C.c_int(int(mask) & 31)), "crab_set_pdl")
-    _pdl_mask = int(mask) & 31
+    _l.check(_l.load().crab_set_pdl(C.c_int(int(mask) & 63)), "crab_set_pdl")
+    _pdl_mask = int(mask) & 63
 
 
 def launch_count() -> int:
@@ -279,6 +279,63 @@ def patchify(images: torch.Tensor, patch: int, ld_out: int) -> torch.Tensor:
     with _timed("crab_patchify"):
         _l.check(_l.load().crab_patchify(_vp(images), _vp(out), _i(ld_out), _i(n), _i(c), _i(h), _i(w), _i(patch), _stream()),
                  "crab_patchify")
+    count_launches(1)
+    return out
+
+
+def patchify_u8(images: torch.Tensor, patch: int, ld_out: int, mean, std, rescale: float = 1.0 / 255.0) -> torch.Tensor:
+    """uint8 (n, H, W, 3) frames -> bf16 patch rows of ((u * rescale - mean) / std), same row/column order as `patchify`."""
+    _req_cuda(images)
+    if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[-1] != 3 or not images.is_contiguous():
+        raise _l.CrabError("patchify_u8 wants a contiguous uint8 (n, H, W, 3) tensor")
+    n, h, w, _ = images.shape
+    rows = n * (h // patch) * (w // patch)
+    out = torch.empty((rows, ld_out), device=images.device, dtype=torch.bfloat16)
+    m3, s3 = (C.c_float * 3)(*map(float, mean)), (C.c_float * 3)(*map(float, std))
+    with _timed("crab_patchify_u8"):
+        _l.check(_l.load().crab_patchify_u8(_vp(images), _vp(out), _i(ld_out), _i(n), _i(h), _i(w), _i(patch), m3, s3,
+                                            C.c_float(rescale), _stream()), "crab_patchify_u8")
+    count_launches(1)
+    return out
+
+
+def normalize_u8(images: torch.Tensor, mean, std, rescale: float = 1.0 / 255.0) -> torch.Tensor:
+    """uint8 (n, H, W, 3) -> fp32 (n, 3, H, W) `pixel_values` ((u * rescale - mean) / std)."""
+    _req_cuda(images)
+    if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[-1] != 3 or not images.is_contiguous():
+        raise _l.CrabError("normalize_u8 wants a contiguous uint8 (n, H, W, 3) tensor")
+    n, h, w, _ = images.shape
+    out = torch.empty((n, 3, h, w), device=images.device, dtype=torch.float32)
+    m3, s3 = (C.c_float * 3)(*map(float, mean)), (C.c_float * 3)(*map(float, std))
+    with _timed("crab_normalize_u8"):
+        _l.check(_l.load().crab_normalize_u8(_vp(images), _vp(out), _i(n), _i(h), _i(w), m3, s3, C.c_float(rescale), _stream()),
+                 "crab_normalize_u8")
+    count_launches(1)
+    return out
+
+
+def fbank_num_frames(n_samples: int) -> int:
+    n = C.c_int(0)
+    _l.check(_l.load().crab_fbank_num_frames(_i(n_samples), C.byref(n)), "crab_fbank_num_frames")
+    return n.value
+
+
+def kaldi_fbank(wave: torch.Tensor, window: torch.Tensor, twiddle: torch.Tensor, mel_start: torch.Tensor, mel_off: torch.Tensor,
+                mel_w: torch.Tensor, in_scale: float, mean: float, std2: float) -> torch.Tensor:
+    """fp32 waveforms (n_seg, n_samples) in [-1, 1] -> fp32 (n_seg, n_frames, n_mel) normalised Kaldi log-mel features."""
+    _req_cuda(wave, window, twiddle, mel_start, mel_off, mel_w)
+    assert twiddle.dtype == torch.float32 and tuple(twiddle.shape) == (256, 2) and twiddle.is_contiguous()
+    if wave.dtype != torch.float32 or wave.dim() != 2 or wave.stride(1) != 1:
+        raise _l.CrabError("kaldi_fbank wants fp32 (n_seg, n_samples) waveforms with unit inner stride")
+    assert window.dtype == torch.float32 and mel_w.dtype == torch.float32 and mel_start.dtype == torch.int32 and mel_off.dtype == torch.int32
+    n_seg, n_samples = wave.shape
+    n_mel = mel_start.numel()
+    frames = fbank_num_frames(n_samples)
+    out = torch.empty((n_seg, frames, n_mel), device=wave.device, dtype=torch.float32)
+    with _timed("crab_kaldi_fbank"):
+        _l.check(_l.load().crab_kaldi_fbank(_vp(wave), C.c_int64(wave.stride(0)), _i(n_seg), _i(n_samples), _vp(window),
+                                            _vp(twiddle), _vp(mel_start), _vp(mel_off), _vp(mel_w), _i(n_mel), C.c_float(in_scale),
+                                            C.c_float(mean), C.c_float(std2), _vp(out), _stream()), "crab_kaldi_fbank")
     count_launches(1)
     return out
 

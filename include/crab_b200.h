@@ -33,7 +33,8 @@ int crab_init(int dev);
 int crab_version(void);
 /* Programmatic dependent launch for the decode-chain kernels: bit mask over kernel classes (env CRAB_PDL gives the
  * initial value, default 0): 1 = weight-streaming GEMM, 2 = row norm/LoRA pre-pass, 4 = RoPE + KV append,
- * 8 = decode attention, 16 = the other light kernels (norm, gather, arg-max, counters).  Read at launch time. */
+ * 8 = decode attention, 16 = the other light kernels (norm, gather, arg-max, counters); modifier 32 = the decode
+ * attention releases its dependents after its streaming loop instead of at its top.  Read at launch time. */
 int crab_set_pdl(int mask);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -182,6 +183,29 @@ int crab_pack_skinny_weight(const void* W, int N, int K, int ldw, void* out, int
 int crab_gemm_skinny_bf16(const crab_skinny_args* args, void* stream);
 int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, float eps, void* y, int ldy, const void* ra,
                         int ldra, int groups, void* z, int ldz, float scale, int rows, int cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Front-end preprocessing (the step immediately before the path)
+ * crab_kaldi_fbank replaces: dataset/audio_processor.py:29-41 `preprocess` = torchaudio.compliance.kaldi.fbank(
+ *           waveform * 2**15, num_mel_bins=128, sample_frequency=16000, frame_length=25, frame_shift=10) [defaults:
+ *           dither 0, remove_dc_offset, preemphasis 0.97, povey window, round_to_power_of_two, snip_edges, use_power,
+ *           use_log_fbank] followed by (fbank - mean) / (2 * std).  wave: fp32 [n_seg, wave_stride] (n_samples valid);
+ *           window [400]; twiddle [256][2] = (cos, -sin)(2 pi k / 512); the mel filters are passed as sparse rows (mel_start[n_mel], mel_off[n_mel+1], mel_w[nnz]) built
+ *           by the host from the Kaldi formula; out: fp32 [n_seg, n_frames, n_mel], n_frames from crab_fbank_num_frames.
+ *           `std2` is the full divisor (2 * 6.55582 in the reference).
+ * crab_patchify_u8 replaces: CLIPImageProcessor rescale + normalize (dataset/quick_start_dataset.py:303-315 calls
+ *           `video_processor.preprocess(frames)` on 224x224 decoded frames, for which resize / centre-crop are
+ *           identities) fused with crab_patchify: uint8 [n, H, W, 3] -> bf16 patch rows.
+ * crab_normalize_u8: same arithmetic to the reference's fp32 `pixel_values` [n, 3, H, W].
+ * ---------------------------------------------------------------------------------------------------------------- */
+int crab_kaldi_fbank(const float* wave, int64_t wave_stride, int n_seg, int n_samples, const float* window,
+                     const float* twiddle, const int* mel_start, const int* mel_off, const float* mel_w, int n_mel, float in_scale,
+                     float mean, float std2, float* out, void* stream);
+int crab_fbank_num_frames(int n_samples, int* n_frames);
+int crab_patchify_u8(const void* images_hwc, void* out, int ld_out, int n_img, int H, int W, int patch,
+                     const float* mean3, const float* std3, float rescale, void* stream);
+int crab_normalize_u8(const void* images_hwc, float* out_nchw, int n_img, int H, int W, const float* mean3,
+                      const float* std3, float rescale, void* stream);
 
 /* Diagnostic (not on the product path): pure HBM->smem ring streaming, used by tools/ to size the decode pipelines. */
 int crab_debug_stream(const void* src, int64_t bytes, int chunk_bytes, int stages, int ctas, void* sink, void* stream);

@@ -24,7 +24,7 @@ ap.add_argument("--bs", type=int, default=32)
 ap.add_argument("--S", type=int, default=1086)
 ap.add_argument("--new", type=int, default=128)
 ap.add_argument("--reps", type=int, default=2)
-ap.add_argument("--plans", nargs="*", default=["0,0", "1,1", "3,1", "19,17", "31,29", "31,31", "0,0"])
+ap.add_argument("--plans", nargs="*", default=["0,0", "1,1", "3,1", "35,35", "19,17", "31,29", "31,31", "63,63", "0,0"])
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
