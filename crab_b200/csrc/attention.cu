@@ -14,6 +14,8 @@
 
 namespace crab {
 
+int flash_attn_tcgen05_try(const crab_attn_args* a, cudaStream_t st);  // flash_tcgen05.cu
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;  // src-size 0 => zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
@@ -309,15 +311,34 @@ struct DecodeParams {
   const int* len_dev; int len_host;           // number of valid keys
   float scale;
   int late_trigger;                           // PDL: release the dependent kernel after the streaming loop, not at the top
+  // ---- FUSE variant: q points at the RAW qkv row [q (H*HD) | k (KVH*HD) | v (KVH*HD)] straight from the qkv GEMM ----
+  const float* cos_sin;                       // [max_pos, HD] = [cos(half) | sin(half)] per position
+  const int* past_dev;                        // position of the new token; number of valid keys = past + 1
+  __nv_bfloat16* kc_w; __nv_bfloat16* vc_w;   // the same caches, writable: the new K (rotated) / V row is appended here
+  const __nv_bfloat16* ra; int ldra;          // optional o_proj hyper-LoRA pre-pass: [R (3); A (8)] rows over H*HD columns
+  __nv_bfloat16* z; int ldz;                  // [B, >= 24] z columns (the K-extension of the o_proj GEMM)
+  float lora_scale;
+  float* lora_ws;                             // [B, KVH, 11] per-head-group partial dots
+  int* lora_cnt;                              // [B] arrival counters, zero on entry and left zero
 };
 
-template <int HD, int G>
+// FUSE = the decode step's RoPE + KV-cache append (+ the o_proj hyper-LoRA pre-pass) folded into the attention kernel:
+// the block rotates its own q heads and the new k row in registers (models/modeling_llama.py:204-236), appends k / v to
+// the cache, treats the new key as one more key of the stream, and — when `ra` is given — finishes with the 11 router /
+// A dot products of its heads' output; the last block of a batch row (arrival counter) sums them over the heads in
+// fixed order, applies the fp32 router softmax and writes the 24 z columns (peft_hyper/tuners/lora.py:344-350).
+// Two launches per layer (rope_kv_kernel, row_loraz_kernel) disappear from the decode chain.
+template <int HD, int G, bool FUSE>
 __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) {
   constexpr int LPK = HD / 8;        // lanes per key (16 for hd=128, 8 for hd=64)
   constexpr int KPW = 32 / LPK;      // keys per warp-load
   constexpr int NSUB = 4 * KPW;      // independent softmax states per block
   __shared__ float sh_m[NSUB][G], sh_l[NSUB][G];
   __shared__ float sh_acc[NSUB][G][HD];
+  __shared__ float sh_red[4][11];
+  __shared__ float sh_tot[11];
+  __shared__ int sh_ticket;
+  __shared__ uint4 sh_new[2][LPK];
   // With an early trigger the next kernels of a PDL chain (ultimately the streaming GEMM, 100 KB smem / 32 K registers per
   // CTA) become resident while this grid still streams the cache and squat on its SM slots; a late trigger releases them
   // only when every CTA is past its loop, which still hides their launch latency behind the combine/tail.
@@ -327,21 +348,78 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
   const int sub = lane / LPK, li = lane % LPK;
   const int b = blockIdx.x / p.KVH, kvh = blockIdx.x % p.KVH;
   const int split = blockIdx.y;
-  const int len = p.len_dev ? *p.len_dev : p.len_host;
+  const int past = FUSE ? *p.past_dev : 0;
+  const int len = FUSE ? past + 1 : (p.len_dev ? *p.len_dev : p.len_host);
   const int per = (len + p.nsplit - 1) / p.nsplit;
   const int k_begin = split * per, k_end = min(len, k_begin + per);
   const float sl2 = p.scale * 1.4426950408889634f;
 
+  // FUSE: rotary factors of this lane's 8 dims at position `past` (lanes of the low half pair with lane ^ LPK/2)
+  constexpr int HL = LPK / 2;
+  const bool is_hi = li >= HL;
+  float rc[8], rs[8];
+  if (FUSE) {
+    const float* cp = p.cos_sin + (size_t)past * HD + (li % HL) * 8;
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(cp)), c1 = __ldg(reinterpret_cast<const float4*>(cp) + 1);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(cp + HD / 2)), s1 = __ldg(reinterpret_cast<const float4*>(cp + HD / 2) + 1);
+    rc[0] = c0.x; rc[1] = c0.y; rc[2] = c0.z; rc[3] = c0.w; rc[4] = c1.x; rc[5] = c1.y; rc[6] = c1.z; rc[7] = c1.w;
+    rs[0] = s0.x; rs[1] = s0.y; rs[2] = s0.z; rs[3] = s0.w; rs[4] = s1.x; rs[5] = s1.y; rs[6] = s1.z; rs[7] = s1.w;
+    if (!is_hi) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rs[j] = -rs[j];  // low half: x c - partner s;  high half: x c + partner s
+    }
+  }
+  auto rope8 = [&](const uint4& raw, float* out) {  // rotate, then round to bf16 exactly where the unfused path stored bf16
+    float t[8];
+    t[0] = bf16lo(raw.x); t[1] = bf16hi(raw.x); t[2] = bf16lo(raw.y); t[3] = bf16hi(raw.y);
+    t[4] = bf16lo(raw.z); t[5] = bf16hi(raw.z); t[6] = bf16lo(raw.w); t[7] = bf16hi(raw.w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float other = __shfl_xor_sync(0xffffffffu, t[j], HL);
+      out[j] = __bfloat162float(__float2bfloat16_rn(t[j] * rc[j] + other * rs[j]));
+    }
+  };
+
   float qf[G][8];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    uint4 qq = *reinterpret_cast<const uint4*>(p.q + (size_t)b * p.ldq + (size_t)(kvh * G + g) * HD + li * 8);
+    const __nv_bfloat16* qp = p.q + (size_t)b * p.ldq + (size_t)(kvh * G + g) * HD + li * 8;
     float t[8];
-    t[0] = bf16lo(qq.x); t[1] = bf16hi(qq.x); t[2] = bf16lo(qq.y); t[3] = bf16hi(qq.y);
-    t[4] = bf16lo(qq.z); t[5] = bf16hi(qq.z); t[6] = bf16lo(qq.w); t[7] = bf16hi(qq.w);
+    if (FUSE) {
+      rope8(ld_dep_u4(qp), t);
+    } else {
+      const uint4 qq = *reinterpret_cast<const uint4*>(qp);
+      t[0] = bf16lo(qq.x); t[1] = bf16hi(qq.x); t[2] = bf16lo(qq.y); t[3] = bf16hi(qq.y);
+      t[4] = bf16lo(qq.z); t[5] = bf16hi(qq.z); t[6] = bf16lo(qq.w); t[7] = bf16hi(qq.w);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) qf[g][j] = t[j] * sl2;
   }
+  // FUSE: warp 0 rotates the new key row of this kv head, parks it (and the new value row) in shared memory for the
+  // tail below, and — in the block whose key range holds position `past` — appends both to the cache.  Nobody reads that
+  // cache row in this launch: the stream below stops at `past` and the tail folds the new key in from shared memory, so
+  // the streaming loop is instruction-for-instruction the unfused one.
+  const bool owns_new = FUSE && past >= k_begin && past < k_end;
+  if (FUSE && warp == 0 && owns_new) {
+    const __nv_bfloat16* kp = p.q + (size_t)b * p.ldq + (size_t)(p.H + kvh) * HD + li * 8;
+    float kr[8];
+    rope8(ld_dep_u4(kp), kr);
+    uint4 knew;
+    knew.x = pack_bf16x2(kr[0], kr[1]); knew.y = pack_bf16x2(kr[2], kr[3]);
+    knew.z = pack_bf16x2(kr[4], kr[5]); knew.w = pack_bf16x2(kr[6], kr[7]);
+    const uint4 vnew = ld_dep_u4(kp + (size_t)p.KVH * HD);
+    if (sub == 0) {
+      sh_new[0][li] = knew;
+      sh_new[1][li] = vnew;
+      if (past < p.ctx_max) {
+        const size_t row = (((size_t)b * p.KVH + kvh) * p.ctx_max + past) * HD + li * 8;
+        *reinterpret_cast<uint4*>(p.kc_w + row) = knew;
+        *reinterpret_cast<uint4*>(p.vc_w + row) = vnew;
+      }
+    }
+    __syncwarp();
+  }
+  const int k_stream_end = FUSE ? min(k_end, past) : k_end;  // keys read from the cache
   float m[G], l[G], acc[G][8];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
@@ -354,13 +432,13 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
   constexpr int U = 4;
   // this (warp, sub) walks keys k_begin + (warp*KPW + sub) + i * NSUB.  The loop bound depends on the warp only, so
   // every lane of a warp runs the same number of iterations (the shuffles below need the full warp).
-  for (int kb = k_begin + warp * KPW; kb < k_end; kb += NSUB * U) {
+  for (int kb = k_begin + warp * KPW; kb < k_stream_end; kb += NSUB * U) {
     const int k0 = kb + sub;
     uint4 kq[U], vq[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int key = k0 + u * NSUB;
-      if (key < k_end) {
+      if (key < k_stream_end) {
         kq[u] = __ldg(reinterpret_cast<const uint4*>(kbase + (size_t)key * HD) + li);
         vq[u] = __ldg(reinterpret_cast<const uint4*>(vbase + (size_t)key * HD) + li);
       } else {
@@ -371,7 +449,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int key = k0 + u * NSUB;
-      const bool valid = key < k_end;  // uniform across the LPK lanes of this key
+      const bool valid = key < k_stream_end;  // uniform across the LPK lanes of this key
       float kf[8], vf[8];
       kf[0] = bf16lo(kq[u].x); kf[1] = bf16hi(kq[u].x); kf[2] = bf16lo(kq[u].y); kf[3] = bf16hi(kq[u].y);
       kf[4] = bf16lo(kq[u].z); kf[5] = bf16hi(kq[u].z); kf[6] = bf16lo(kq[u].w); kf[7] = bf16hi(kq[u].w);
@@ -396,6 +474,32 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
       }
     }
   }
+  if (FUSE && warp == 0 && owns_new) {
+    // the new key, from shared memory, joins the (warp 0, sub 0) softmax state
+    const uint4 kq1 = sh_new[0][li], vq1 = sh_new[1][li];
+    float kf[8], vf[8];
+    kf[0] = bf16lo(kq1.x); kf[1] = bf16hi(kq1.x); kf[2] = bf16lo(kq1.y); kf[3] = bf16hi(kq1.y);
+    kf[4] = bf16lo(kq1.z); kf[5] = bf16hi(kq1.z); kf[6] = bf16lo(kq1.w); kf[7] = bf16hi(kq1.w);
+    vf[0] = bf16lo(vq1.x); vf[1] = bf16hi(vq1.x); vf[2] = bf16lo(vq1.y); vf[3] = bf16hi(vq1.y);
+    vf[4] = bf16lo(vq1.z); vf[5] = bf16hi(vq1.z); vf[6] = bf16lo(vq1.w); vf[7] = bf16hi(vq1.w);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float sc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sc += qf[g][j] * kf[j];
+#pragma unroll
+      for (int o = LPK / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+      if (sub == 0) {
+        const float mn = fmaxf(m[g], sc);
+        const float c = exp2f(m[g] - mn);
+        const float pe = exp2f(sc - mn);
+        m[g] = mn;
+        l[g] = l[g] * c + pe;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[g][j] = acc[g][j] * c + pe * vf[j];
+      }
+    }
+  }
   if (p.late_trigger) pdl_trigger();
   // combine the NSUB partial states
   const int sidx = warp * KPW + sub;
@@ -406,6 +510,10 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
     for (int j = 0; j < 8; ++j) sh_acc[sidx][g][li * 8 + j] = acc[g][j];
   }
   __syncthreads();
+  const bool lora = FUSE && p.ra != nullptr;
+  float t11[11];
+#pragma unroll
+  for (int j = 0; j < 11; ++j) t11[j] = 0.f;
   for (int idx = threadIdx.x; idx < G * HD; idx += 128) {
     const int g = idx / HD, d = idx % HD;
     float mm = -INFINITY;
@@ -422,11 +530,54 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
     }
     const int hq = kvh * G + g;
     if (p.nsplit == 1) {
-      p.o[(size_t)b * p.ldo + (size_t)hq * HD + d] = __float2bfloat16_rn(ll > 0.f ? aa / ll : 0.f);
+      const __nv_bfloat16 ob = __float2bfloat16_rn(ll > 0.f ? aa / ll : 0.f);
+      p.o[(size_t)b * p.ldo + (size_t)hq * HD + d] = ob;
+      if (lora) {
+        const float of = __bfloat162float(ob);
+        const __nv_bfloat16* rp = p.ra + (size_t)hq * HD + d;
+#pragma unroll
+        for (int j = 0; j < 11; ++j) t11[j] += of * __bfloat162float(rp[(size_t)j * p.ldra]);
+      }
     } else {
       float* w = p.ws + (((size_t)b * p.H + hq) * p.nsplit + split) * (HD + 2);
       w[d] = aa;
       if (d == 0) { w[HD] = mm; w[HD + 1] = ll; }
+    }
+  }
+  if (lora) {
+    // block partial of the 11 dots -> workspace; the last block of this batch row reduces over the kv heads in order
+#pragma unroll
+    for (int j = 0; j < 11; ++j) {
+      const float v = warp_sum(t11[j]);
+      if (lane == 0) sh_red[warp][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 11) {
+      const float v = sh_red[0][threadIdx.x] + sh_red[1][threadIdx.x] + sh_red[2][threadIdx.x] + sh_red[3][threadIdx.x];
+      p.lora_ws[((size_t)b * p.KVH + kvh) * 11 + threadIdx.x] = v;
+      __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sh_ticket = atomicAdd(p.lora_cnt + b, 1);
+    __syncthreads();
+    if (sh_ticket == p.KVH - 1) {
+      __threadfence();
+      if (threadIdx.x < 11) {
+        const volatile float* wsp = p.lora_ws + (size_t)b * p.KVH * 11 + threadIdx.x;
+        float t = 0.f;
+        for (int h2 = 0; h2 < p.KVH; ++h2) t += wsp[(size_t)h2 * 11];
+        sh_tot[threadIdx.x] = t;
+      }
+      __syncthreads();
+      if (threadIdx.x < 24) {
+        const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+        const float l0 = sh_tot[0], l1 = sh_tot[1], l2 = sh_tot[2];
+        const float mx = fmaxf(l0, fmaxf(l1, l2));
+        const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx), e2 = __expf(l2 - mx);
+        const float ri = (i == 0 ? e0 : (i == 1 ? e1 : e2)) / (e0 + e1 + e2);
+        p.z[(size_t)b * p.ldz + threadIdx.x] = __float2bfloat16_rn(p.lora_scale * ri * sh_tot[3 + j]);
+      }
+      if (threadIdx.x == 0) p.lora_cnt[b] = 0;  // ready for the next launch (next layer / next step)
     }
   }
 }
@@ -476,6 +627,11 @@ extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
   p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.Sq = a->Sq; p.Sk = a->Sk;
   p.scale = a->scale; p.causal = a->causal; p.gate = a->gate; p.table = a->bias_table;
   cudaStream_t st = (cudaStream_t)stream;
+  {  // head_dim 128 without a bias table and with TMA-describable strides: the tcgen05 / TMEM kernel (flash_tcgen05.cu)
+    const int rc = flash_attn_tcgen05_try(a, st);
+    if (rc == 0) return CRAB_OK;
+    if (rc < -1) return rc;
+  }
   // 32 query rows per warp (MT = 2) when there are enough rows to fill 128-row blocks; short sequences (Q-Former's 32
   // queries, BEATs' 48 tokens) keep 64-row blocks.
   const bool big = a->Sq >= 512;  // N=257 (CLIP) wastes less with 64-row blocks (5 x 64 vs 3 x 128 row slots)
@@ -520,11 +676,13 @@ extern "C" int crab_attn_decode(const void* q, int ldq, const void* k_cache, con
   p.o = (__nv_bfloat16*)o; p.ldo = ldo; p.ws = workspace; p.B = B; p.H = H; p.KVH = KVH; p.ctx_max = ctx_max;
   p.nsplit = nsplit; p.len_dev = len_dev; p.len_host = len_host; p.scale = scale;
   p.late_trigger = (pdl_mask() & PDL_ATTN_LATE) ? 1 : 0;
+  p.cos_sin = nullptr; p.past_dev = nullptr; p.kc_w = nullptr; p.vc_w = nullptr; p.ra = nullptr; p.ldra = 0; p.z = nullptr;
+  p.ldz = 0; p.lora_scale = 0.f; p.lora_ws = nullptr; p.lora_cnt = nullptr;
   dim3 grid(B * KVH, nsplit);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
 #define CRAB_DECODE_CASE(HD_, G_) \
-  if (head_dim == HD_ && G == G_) { e = launch_pdl(PDL_ATTN, attn_decode_kernel<HD_, G_>, grid, dim3(128), 0, st, p); } else
+  if (head_dim == HD_ && G == G_) { e = launch_pdl(PDL_ATTN, attn_decode_kernel<HD_, G_, false>, grid, dim3(128), 0, st, p); } else
   CRAB_DECODE_CASE(128, 1) CRAB_DECODE_CASE(128, 2) CRAB_DECODE_CASE(128, 4) CRAB_DECODE_CASE(128, 7)
   CRAB_DECODE_CASE(128, 8) CRAB_DECODE_CASE(64, 1)
   { return set_error(CRAB_ERR_INVALID, "crab_attn_decode: unsupported head_dim=%d group=%d", head_dim, G); }
@@ -533,6 +691,45 @@ extern "C" int crab_attn_decode(const void* q, int ldq, const void* k_cache, con
   if (nsplit > 1) {
     if (head_dim == 128) e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<128>, dim3(B * H), dim3(128), 0, st, (const float*)workspace, p.o, ldo, H, nsplit);
     else e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<64>, dim3(B * H), dim3(64), 0, st, (const float*)workspace, p.o, ldo, H, nsplit);
+    CRAB_CHECK_CUDA(e);
+  }
+  return CRAB_OK;
+}
+
+extern "C" int crab_attn_decode_fused(const crab_decode_fused_args* a, void* stream) {
+  CRAB_REQUIRE(a && a->qkv && a->cos_sin && a->k_cache && a->v_cache && a->o && a->past_dev, "crab_attn_decode_fused: null pointer");
+  CRAB_REQUIRE(a->head_dim == 128 || a->head_dim == 64, "crab_attn_decode_fused: head_dim must be 64 or 128");
+  CRAB_REQUIRE(a->B > 0 && a->H > 0 && a->KVH > 0 && a->H % a->KVH == 0, "crab_attn_decode_fused: bad heads");
+  CRAB_REQUIRE(a->nsplit >= 1 && (a->nsplit == 1 || a->workspace != nullptr), "crab_attn_decode_fused: nsplit>1 needs a workspace");
+  CRAB_REQUIRE(a->ldq % 8 == 0 && ((uintptr_t)a->qkv % 16 == 0) && ((uintptr_t)a->cos_sin % 16 == 0), "crab_attn_decode_fused: alignment");
+  CRAB_REQUIRE(a->ldq >= (a->H + 2 * a->KVH) * a->head_dim, "crab_attn_decode_fused: ldq smaller than the [q|k|v] row");
+  if (a->lora_ra) {
+    CRAB_REQUIRE(a->nsplit == 1, "crab_attn_decode_fused: the LoRA pre-pass needs nsplit == 1");
+    CRAB_REQUIRE(a->lora_z && a->lora_ws && a->lora_counters && a->ld_ra >= a->H * a->head_dim && a->ld_z >= 24,
+                 "crab_attn_decode_fused: LoRA pre-pass needs z, workspace [B*KVH*11] floats and counters [B] ints");
+  }
+  const int G = a->H / a->KVH;
+  DecodeParams p;
+  p.q = (const __nv_bfloat16*)a->qkv; p.ldq = a->ldq; p.kc = (const __nv_bfloat16*)a->k_cache; p.vc = (const __nv_bfloat16*)a->v_cache;
+  p.o = (__nv_bfloat16*)a->o; p.ldo = a->ldo; p.ws = a->workspace; p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.ctx_max = a->ctx_max;
+  p.nsplit = a->nsplit; p.len_dev = nullptr; p.len_host = 0; p.scale = a->scale;
+  p.late_trigger = (pdl_mask() & PDL_ATTN_LATE) ? 1 : 0;
+  p.cos_sin = a->cos_sin; p.past_dev = a->past_dev; p.kc_w = (__nv_bfloat16*)a->k_cache; p.vc_w = (__nv_bfloat16*)a->v_cache;
+  p.ra = (const __nv_bfloat16*)a->lora_ra; p.ldra = a->ld_ra; p.z = (__nv_bfloat16*)a->lora_z; p.ldz = a->ld_z;
+  p.lora_scale = a->lora_scale; p.lora_ws = a->lora_ws; p.lora_cnt = a->lora_counters;
+  dim3 grid(a->B * a->KVH, a->nsplit);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+#define CRAB_DECODE_CASE(HD_, G_) \
+  if (a->head_dim == HD_ && G == G_) { e = launch_pdl(PDL_ATTN, attn_decode_kernel<HD_, G_, true>, grid, dim3(128), 0, st, p); } else
+  CRAB_DECODE_CASE(128, 1) CRAB_DECODE_CASE(128, 2) CRAB_DECODE_CASE(128, 4) CRAB_DECODE_CASE(128, 7)
+  CRAB_DECODE_CASE(128, 8) CRAB_DECODE_CASE(64, 1)
+  { return set_error(CRAB_ERR_INVALID, "crab_attn_decode_fused: unsupported head_dim=%d group=%d", a->head_dim, G); }
+#undef CRAB_DECODE_CASE
+  CRAB_CHECK_CUDA(e);
+  if (a->nsplit > 1) {
+    if (a->head_dim == 128) e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<128>, dim3(a->B * a->H), dim3(128), 0, st, (const float*)a->workspace, p.o, a->ldo, a->H, a->nsplit);
+    else e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<64>, dim3(a->B * a->H), dim3(64), 0, st, (const float*)a->workspace, p.o, a->ldo, a->H, a->nsplit);
     CRAB_CHECK_CUDA(e);
   }
   return CRAB_OK;

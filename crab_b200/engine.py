@@ -173,6 +173,8 @@ class CrabEngine:
         # decode attention).  Env CRAB_PDL_PLAN="chain,after_attn" overrides; see profiles/r02_pdl_plans.txt for the A/B.
         plan = os.environ.get("CRAB_PDL_PLAN", DEFAULT_PDL_PLAN).split(",")
         self.pdl_chain, self.pdl_after_attn = int(plan[0]), int(plan[-1])
+        # decode step: RoPE + KV append + o_proj LoRA pre-pass inside the attention kernel (8 launches per layer, not 10)
+        self.fuse_decode_attn = os.environ.get("CRAB_DECODE_FUSE", "1") != "0"
         self._graph = None
         self._graph_bs = None
         self._use_graph = False
@@ -624,8 +626,21 @@ class CrabEngine:
                 if self.lora:
                     ops.gemm(xn[:, :D], L["ra_qkv"], act=ops.ACT_LORA_Z, out_scale=sc, out=xn[:, D:D + 72])
                 ops.gemm(xn, L["wqkv"], bias=L["bqkv"], out=qkv, k=D + (self.EXT_QKV if self.lora else 0))
-            ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, S, H, KV, hd, past=past, past_dev=past_dev)
-            if S == 1 and len_dev is not None:
+            fused = skinny and self.fuse_decode_attn
+            if fused:
+                # one launch: RoPE on q / new k, cache append, attention over past + 1 keys, and (nsplit == 1) the o_proj
+                # LoRA pre-pass whose z columns land in at[:, nq:]
+                lo = self.lora and nsplit == 1
+                ops.attn_decode_fused(qkv, self.rope, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV,
+                                      head_dim=hd, scale=1 / math.sqrt(hd), past_dev=past_dev, nsplit=nsplit, workspace=ws,
+                                      ra=L["ra_o"] if lo else None, z=at[:, nq:] if lo else None, lora_scale=sc,
+                                      lora_ws=self._buf("dec_lora_ws", (B * KV * 11,), torch.float32) if lo else None,
+                                      lora_counters=self._buf("dec_lora_cnt", (B,), torch.int32, zero=True) if lo else None)
+            else:
+                ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, S, H, KV, hd, past=past, past_dev=past_dev)
+            if fused:
+                pass
+            elif S == 1 and len_dev is not None:
                 ops.attn_decode(qkv, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV, head_dim=hd,
                                 scale=1 / math.sqrt(hd), len_dev=len_dev, nsplit=nsplit, workspace=ws)
             else:
@@ -638,7 +653,7 @@ class CrabEngine:
                 # streaming-GEMM CTAs must not squat on the SMs while the 1024-CTA attention kernel still runs
                 if self.pdl_after_attn != self.pdl_chain:
                     ops.set_pdl(self.pdl_after_attn)
-                if self.lora:
+                if self.lora and not (fused and nsplit == 1):
                     ops.row_norm_loraz(at[:, :nq], ra=L["ra_o"], groups=1, z=at[:, nq:], scale=sc)
                     if self.pdl_after_attn != self.pdl_chain:
                         ops.set_pdl(self.pdl_chain)

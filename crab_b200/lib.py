@@ -81,3 +81,14 @@ class SkinnyArgs(C.Structure):
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("ldx", C.c_int32), ("ldw", C.c_int32), ("ldc", C.c_int32),
         ("ldr", C.c_int32), ("act", C.c_int32), ("out_dtype", C.c_int32), ("splits", C.c_int32),
     ]
+
+
+class DecodeFusedArgs(C.Structure):
+    _fields_ = [
+        ("qkv", C.c_void_p), ("ldq", C.c_int32), ("cos_sin", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
+        ("o", C.c_void_p), ("ldo", C.c_int32), ("workspace", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("KVH", C.c_int32), ("head_dim", C.c_int32), ("ctx_max", C.c_int32),
+        ("nsplit", C.c_int32), ("past_dev", C.c_void_p), ("scale", C.c_float),
+        ("lora_ra", C.c_void_p), ("ld_ra", C.c_int32), ("lora_z", C.c_void_p), ("ld_z", C.c_int32),
+        ("lora_scale", C.c_float), ("lora_ws", C.c_void_p), ("lora_counters", C.c_void_p),
+    ]

@@ -247,6 +247,34 @@ def attn_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, o
     return out
 
 
+def attn_decode_fused(qkv: torch.Tensor, rope: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out: torch.Tensor, *,
+                      B: int, H: int, KVH: int, head_dim: int, scale: float, past_dev: torch.Tensor, nsplit: int = 1,
+                      workspace: Optional[torch.Tensor] = None, ra: Optional[torch.Tensor] = None,
+                      z: Optional[torch.Tensor] = None, lora_scale: float = 0.0, lora_ws: Optional[torch.Tensor] = None,
+                      lora_counters: Optional[torch.Tensor] = None):
+    """Decode-step attention with RoPE + KV append (+ the o_proj hyper-LoRA pre-pass) fused in: `qkv` is the RAW output
+    of the qkv projection; the caches are appended at *past_dev; z (24 columns) is written when `ra` is given."""
+    _req_cuda(qkv, rope, k_cache, v_cache, out, past_dev, workspace, ra, z, lora_ws, lora_counters)
+    assert qkv.dim() == 2 and out.dim() == 2 and qkv.stride(1) == 1 and out.stride(1) == 1
+    assert past_dev.dtype == torch.int32 and rope.dtype == torch.float32
+    if nsplit > 1 and workspace is None:
+        workspace = torch.empty(B * H * nsplit * (head_dim + 2), device=qkv.device, dtype=torch.float32)
+    if ra is not None:
+        assert z is not None and lora_ws is not None and lora_counters is not None
+        assert lora_ws.dtype == torch.float32 and lora_ws.numel() >= B * KVH * 11
+        assert lora_counters.dtype == torch.int32 and lora_counters.numel() >= B and ra.stride(1) == 1 and z.stride(1) == 1
+    a = _l.DecodeFusedArgs(
+        qkv=qkv.data_ptr(), ldq=qkv.stride(0), cos_sin=rope.data_ptr(), k_cache=k_cache.data_ptr(), v_cache=v_cache.data_ptr(),
+        o=out.data_ptr(), ldo=out.stride(0), workspace=_ptr(workspace), B=B, H=H, KVH=KVH, head_dim=head_dim,
+        ctx_max=k_cache.shape[2], nsplit=nsplit, past_dev=past_dev.data_ptr(), scale=scale,
+        lora_ra=_ptr(ra), ld_ra=ra.stride(0) if ra is not None else 0, lora_z=_ptr(z), ld_z=z.stride(0) if z is not None else 0,
+        lora_scale=lora_scale, lora_ws=_ptr(lora_ws), lora_counters=_ptr(lora_counters))
+    with _timed("crab_attn_decode_fused"):
+        _l.check(_l.load().crab_attn_decode_fused(C.byref(a), _stream()), "crab_attn_decode_fused")
+    count_launches(2 if nsplit > 1 else 1)
+    return out
+
+
 def gather_rows(src: torch.Tensor, dst: torch.Tensor, n: int, cols: int, src_rows: Optional[torch.Tensor] = None,
                 dst_rows: Optional[torch.Tensor] = None):
     _req_cuda(src, dst, src_rows, dst_rows)

@@ -125,6 +125,29 @@ int crab_attn_decode(const void* q, int ldq, const void* k_cache, const void* v_
                      float* workspace, int B, int H, int KVH, int head_dim, int ctx_max, int nsplit,
                      const int* len_dev, int len_host, float scale, void* stream);
 
+/* crab_attn_decode_fused replaces, in ONE launch per layer of the decode step: apply_rotary_pos_emb on the new q / k
+ *           (models/modeling_llama.py:204-236), the DynamicCache append, the q_len == 1 attention, and — when lora_ra is
+ *           given — the o_proj hyper-LoRA router / A projections with the fp32 router softmax
+ *           (peft_hyper/tuners/lora.py:344-350), whose 24 z values land in lora_z (the o_proj GEMM's K-extension).
+ *           qkv: RAW [B, ldq] rows [q | k | v] from the qkv projection; cos_sin from crab_rope_table; *past_dev = position
+ *           of the new token (valid keys = past + 1).  lora_ws: B*KVH*11 floats; lora_counters: B ints, zero on entry
+ *           (left zero).  The LoRA pre-pass needs nsplit == 1. */
+typedef struct crab_decode_fused_args {
+  const void* qkv; int32_t ldq;
+  const float* cos_sin;
+  void* k_cache; void* v_cache;           /* bf16 [B, KVH, ctx_max, head_dim] */
+  void* o; int32_t ldo;                   /* bf16 [B, ldo] */
+  float* workspace;                       /* split-KV partials (nsplit > 1) or NULL */
+  int32_t B, H, KVH, head_dim, ctx_max, nsplit;
+  const int* past_dev;
+  float scale;
+  const void* lora_ra; int32_t ld_ra;     /* bf16 [11, ld_ra] or NULL */
+  void* lora_z; int32_t ld_z;             /* bf16 [B, ld_z] */
+  float lora_scale;
+  float* lora_ws; int* lora_counters;
+} crab_decode_fused_args;
+int crab_attn_decode_fused(const crab_decode_fused_args* args, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Gathers, casts, patchify, CLIP embeddings, BEATs helpers, arg-max
  * crab_gather_rows replaces: embed_tokens lookups and the torch.cat / left-pad splice of

@@ -89,6 +89,12 @@ def _attn_ref(q, k, v, scale, causal=False, bias=None):
     (2, 4, 4, 200, 200, 128, True),      # LLaMA prefill
     (2, 8, 2, 150, 150, 128, True),      # Qwen2 GQA prefill
     (1, 2, 2, 70, 133, 128, True),       # chunked prefill (Sk > Sq)
+    # head_dim 128 with >= 128 queries runs on the tcgen05 / TMEM kernel (flash_tcgen05.cu)
+    (1, 2, 2, 128, 128, 128, True),      # exactly one q tile, two key tiles
+    (2, 4, 4, 1086, 1086, 128, True),    # the benchmark's sequence length: 9 q tiles, ragged last tile
+    (1, 4, 2, 300, 555, 128, True),      # chunked prefill with GQA (Sk > Sq)
+    (2, 2, 2, 257, 257, 128, False),     # non-causal, key tail masked by length only
+    (1, 2, 1, 640, 640, 128, False),
 ])
 def test_flash_attn(cuda_dev, B, H, KVH, Sq, Sk, hd, causal):
     from crab_b200 import ops
@@ -146,6 +152,56 @@ def test_attn_decode(cuda_dev, B, H, KVH, hd, length, nsplit):
     torch.cuda.synchronize()
     ref = _attn_ref(q[:, : H * hd].view(B, 1, H, hd).transpose(1, 2), kc[:, :, :length], vc[:, :, :length], hd ** -0.5)
     _close(o.view(B, H, hd), ref[:, :, 0], 2e-2)
+
+
+@pytest.mark.parametrize("B,H,KVH,hd,past,nsplit,lora", [(4, 8, 8, 128, 300, 1, True), (32, 32, 32, 128, 1100, 1, True),
+                                                          (3, 28, 4, 128, 517, 1, True), (2, 8, 8, 128, 1213, 4, False),
+                                                          (2, 4, 4, 128, 0, 1, True), (2, 4, 4, 64, 77, 1, False),
+                                                          (1, 28, 4, 128, 1000, 8, False)])
+def test_attn_decode_fused_equals_the_three_kernel_sequence(cuda_dev, B, H, KVH, hd, past, nsplit, lora):
+    """RoPE + KV append + decode attention (+ o_proj LoRA pre-pass) in one launch vs rope_kv_append -> attn_decode ->
+    row_norm_loraz: caches bit-identical, attention output and z within fp32 summation-order noise; repeated launches
+    (the arrival counters must come back to zero) give identical results."""
+    from crab_b200 import ops
+
+    ctx = 1280
+    g = _g(B * 7 + H + past)
+    nq = H * hd
+    qkv = torch.randn(B, (H + 2 * KVH) * hd, generator=g).to(torch.bfloat16).to(cuda_dev)
+    kc = torch.randn(B, KVH, ctx, hd, generator=g).to(torch.bfloat16).to(cuda_dev)
+    vc = torch.randn(B, KVH, ctx, hd, generator=g).to(torch.bfloat16).to(cuda_dev)
+    ra = (torch.randn(11, nq, generator=g) / math.sqrt(nq)).to(torch.bfloat16).to(cuda_dev)
+    rope = ops.rope_table(ctx, hd, 10000.0, cuda_dev)
+    pd = torch.tensor([past], dtype=torch.int32, device=cuda_dev)
+    ld = torch.tensor([past + 1], dtype=torch.int32, device=cuda_dev)
+    # reference sequence
+    q1, k1, v1 = qkv.clone(), kc.clone(), vc.clone()
+    o1 = torch.zeros(B, nq + 32, dtype=torch.bfloat16, device=cuda_dev)
+    ops.rope_kv_append(q1, rope, k1, v1, B, 1, H, KVH, hd, past=0, past_dev=pd)
+    ops.attn_decode(q1, k1, v1, o1[:, :nq], B=B, H=H, KVH=KVH, head_dim=hd, scale=hd ** -0.5, len_dev=ld, nsplit=nsplit)
+    if lora:
+        ops.row_norm_loraz(o1[:, :nq], ra=ra, groups=1, z=o1[:, nq:], scale=2.0)
+    # fused
+    k2, v2 = kc.clone(), vc.clone()
+    o2 = torch.zeros(B, nq + 32, dtype=torch.bfloat16, device=cuda_dev)
+    ws = torch.empty(B * KVH * 11, dtype=torch.float32, device=cuda_dev)
+    cnt = torch.zeros(B, dtype=torch.int32, device=cuda_dev)
+    for rep in range(2):
+        if rep == 1:
+            o2.zero_()
+        ops.attn_decode_fused(qkv, rope, k2, v2, o2[:, :nq], B=B, H=H, KVH=KVH, head_dim=hd, scale=hd ** -0.5, past_dev=pd,
+                              nsplit=nsplit, ra=ra if lora else None, z=o2[:, nq:] if lora else None, lora_scale=2.0,
+                              lora_ws=ws if lora else None, lora_counters=cnt if lora else None)
+        torch.cuda.synchronize()
+        assert torch.equal(k2, k1) and torch.equal(v2, v1)
+        _close(o2[:, :nq], o1[:, :nq], 1e-2)  # the new key joins a different partial softmax state: same math, other order
+        if rep == 0:
+            first = o2.clone()
+        assert torch.equal(o2, first)
+        assert int(cnt.abs().sum()) == 0
+        if lora:
+            _close(o2[:, nq:nq + 24], o1[:, nq:nq + 24], 2e-2)
+            assert o2[:, nq + 24:].abs().max().item() == 0
 
 
 def test_gather_cast_patchify_argmax(cuda_dev):
