@@ -38,8 +38,22 @@ ln = torch.tensor([1150], dtype=torch.int32, device=dev)
 qd = torch.randn(B, 3 * D, device=dev, dtype=torch.bfloat16)
 od = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
 ops.attn_decode(qd, kc, vc, od, B=B, H=H, KVH=H, head_dim=hd, scale=hd ** -0.5, len_dev=ln)
+# 4b. the decode step's fused kernel: RoPE + KV append + attention + o_proj LoRA pre-pass
+rope = ops.rope_table(1216, hd, 10000.0, dev)
+pd = torch.tensor([1149], dtype=torch.int32, device=dev)
+ra_o = torch.randn(11, D + 32, device=dev, dtype=torch.bfloat16) * 0.02
+at = torch.zeros(B, D + 32, device=dev, dtype=torch.bfloat16)
+ops.attn_decode_fused(qd, rope, kc, vc, at[:, :D], B=B, H=H, KVH=H, head_dim=hd, scale=hd ** -0.5, past_dev=pd,
+                      ra=ra_o[:, :D], z=at[:, D:], lora_scale=2.0, lora_ws=torch.empty(B * H * 11, device=dev),
+                      lora_counters=torch.zeros(B, dtype=torch.int32, device=dev))
 gamma = torch.ones(D, device=dev)
 ra = torch.randn(33, D, device=dev, dtype=torch.bfloat16) * 0.02
 ops.row_norm_loraz(xo, gamma=gamma, eps=1e-6, y=x[:, :D], ra=ra, groups=3, z=x[:, D:], scale=2.0)
+# 5. front-end: Kaldi fbank for 32 samples x 10 one-second segments, fused uint8 normalise + patchify
+from crab_b200.dataset import audio_processor as A
+wave = 0.2 * torch.randn(320, 16000, device=dev)
+A.preprocess(wave)
+frames = torch.randint(0, 256, (256, 224, 224, 3), device=dev, dtype=torch.uint8)
+ops.patchify_u8(frames, 14, 592, (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))
 torch.cuda.synchronize()
 print("ok")

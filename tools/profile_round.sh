@@ -6,7 +6,7 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:"gemm_bf16_tcgen05|gemm_skinny|flash_attn|attn_decode|row_loraz" -f -o gpurun_out/${TAG}_kernels \
+    -k regex:"gemm_bf16_tcgen05|gemm_skinny|flash_attn|attn_decode|row_loraz|fbank|patchify_u8" -f -o gpurun_out/${TAG}_kernels \
     python tools/profile_kernels.py > gpurun_out/${TAG}_ncu.log 2>&1
 if [ "$2" == "--with-launch-list" ]; then
   timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
