@@ -1,6 +1,8 @@
 // HBM-bound glue kernels of the hot path: norms, RoPE + KV-cache append, gathers/splices, patchify, CLIP embedding
 // assembly, BEATs gate / pos-conv packing, arg-max.  All use 16-byte vector loads, fp32 math and warp-shuffle
 // reductions; one row per warp or per block, grids sized by rows.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -475,6 +477,139 @@ __global__ void __launch_bounds__(256) row_loraz_kernel(const __nv_bfloat16* __r
   }
 }
 
+// Cluster version for the decode step: the columns of one (row, linear) are split over the P CTAs of a thread-block
+// cluster, so a 32-row batch fills 256-384 CTAs instead of 32-96 and every CTA's dependent-load chain is P times shorter.
+// Two exchanges through distributed shared memory: (1) the partial sums of squares go to every peer (each CTA needs rstd
+// to normalise its slice), (2) the 11 partial dots go to rank 0, which applies the router softmax and writes z.  Partials
+// are always summed in rank order: deterministic.  128 threads, VPT x 8 columns per thread.
+__device__ __forceinline__ uint32_t rl_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void rl_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void rl_st_remote(const void* local_smem, uint32_t rank, float v) {
+  uint32_t a = smem_u32(local_smem), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(r), "f"(v) : "memory");
+}
+
+template <bool NORM, int VPT>
+__global__ void __launch_bounds__(128) row_loraz_cluster_kernel(const __nv_bfloat16* x, int ldx, const float* __restrict__ gamma,
+                                                                float eps, __nv_bfloat16* y, int ldy,
+                                                                const __nv_bfloat16* __restrict__ ra, int ldra, int groups,
+                                                                __nv_bfloat16* z, int ldz, float scale, int cols, int P) {
+  pdl_trigger();
+  __shared__ float sh[32];
+  __shared__ float ss_part[8];        // [rank] partial sums of squares (written by every peer)
+  __shared__ float dot_part[8][11];   // [rank][11] partial dots (rank 0 only)
+  __shared__ float red[4][11];
+  __shared__ float tot[11];
+  const int row = blockIdx.x, grp = blockIdx.y;
+  const int rank = (int)rl_cluster_rank();
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int nvec_slice = (cols >> 3) / P;          // host guarantees divisibility
+  const int v0 = rank * nvec_slice;
+  const __nv_bfloat16* rg = (groups > 0) ? ra + (size_t)grp * 11 * ldra : nullptr;
+  // weights first (they do not depend on the previous kernel): 11 router/A vectors and gamma for this thread's columns
+  constexpr bool PRE = (VPT <= 2);  // wider slices fetch the router/A vectors inside the dot loop (register budget)
+  uint4 rq[PRE ? VPT : 1][11];
+  float4 gq[VPT][2];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vi = threadIdx.x + i * 128;
+    const bool ok = vi < nvec_slice;
+    if (PRE && groups > 0) {
+#pragma unroll
+      for (int o = 0; o < 11; ++o)
+        rq[PRE ? i : 0][o] = ok ? __ldg(reinterpret_cast<const uint4*>(rg + (size_t)o * ldra) + v0 + vi) : make_uint4(0, 0, 0, 0);
+    }
+    if (NORM) {
+      gq[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * (v0 + vi)) : make_float4(0, 0, 0, 0);
+      gq[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * (v0 + vi) + 1) : make_float4(0, 0, 0, 0);
+    }
+  }
+  pdl_wait();
+  float v[VPT][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vi = threadIdx.x + i * 128;
+    if (vi < nvec_slice) {
+      unpack8(ld_dep_u4(reinterpret_cast<const uint4*>(x + (size_t)row * ldx) + v0 + vi), v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+  if (NORM) {
+    const float part = block_sum(ss, sh);
+    if (threadIdx.x < P) rl_st_remote(&ss_part[rank], (uint32_t)threadIdx.x, part);
+    rl_cluster_sync();
+    float total = 0.f;
+    for (int r = 0; r < P; ++r) total += ss_part[r];
+    const float rstd = rsqrtf(total / cols + eps);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int vi = threadIdx.x + i * 128;
+      if (vi < nvec_slice) {
+        const float g[8] = {gq[i][0].x, gq[i][0].y, gq[i][0].z, gq[i][0].w, gq[i][1].x, gq[i][1].y, gq[i][1].z, gq[i][1].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // same two roundings as norm_kernel<RMS>
+          v[i][j] = __bfloat162float(__float2bfloat16_rn(g[j] * __bfloat162float(__float2bfloat16_rn(v[i][j] * rstd))));
+        if (grp == 0) *(reinterpret_cast<uint4*>(y + (size_t)row * ldy) + v0 + vi) = pack8(v[i]);
+      }
+    }
+  }
+  if (groups == 0) return;  // uniform over the cluster: nobody waits on a barrier below
+  float acc[11];
+#pragma unroll
+  for (int o = 0; o < 11; ++o) acc[o] = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vi = threadIdx.x + i * 128;
+    uint4 q11[11];
+#pragma unroll
+    for (int o = 0; o < 11; ++o)
+      q11[o] = PRE ? rq[PRE ? i : 0][o]
+                   : (vi < nvec_slice ? __ldg(reinterpret_cast<const uint4*>(rg + (size_t)o * ldra) + v0 + vi) : make_uint4(0, 0, 0, 0));
+#pragma unroll
+    for (int o = 0; o < 11; ++o) {
+      float rf[8];
+      unpack8(q11[o], rf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[o] += v[i][j] * rf[j];
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 11; ++o) {
+    acc[o] = warp_sum(acc[o]);
+    if (l == 0) red[w][o] = acc[o];
+  }
+  __syncthreads();
+  if (threadIdx.x < 11) rl_st_remote(&dot_part[rank][threadIdx.x], 0u, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+  rl_cluster_sync();
+  if (rank != 0) return;
+  if (threadIdx.x < 11) {
+    float t = 0.f;
+    for (int r = 0; r < P; ++r) t += dot_part[r][threadIdx.x];
+    tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 24) {
+    const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+    const float l0 = tot[0], l1 = tot[1], l2 = tot[2];
+    const float mx = fmaxf(l0, fmaxf(l1, l2));
+    const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx), e2 = __expf(l2 - mx);
+    const float ri = (i == 0 ? e0 : (i == 1 ? e1 : e2)) / (e0 + e1 + e2);
+    z[(size_t)row * ldz + grp * 24 + threadIdx.x] = __float2bfloat16_rn(scale * ri * tot[3 + j]);
+  }
+}
+
 // device-side scalar increment (decode position counter inside a CUDA graph)
 __global__ void add_scalar_kernel(int* p, int v) {
   pdl_trigger();
@@ -614,7 +749,7 @@ extern "C" int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, f
                                    const void* ra, int ldra, int groups, void* z, int ldz, float scale, int rows,
                                    int cols, void* stream) {
   CRAB_REQUIRE(x != nullptr, "crab_row_norm_loraz: null x");
-  CRAB_REQUIRE(cols % 8 == 0 && ldx % 8 == 0 && cols <= 8 * 256 * 8, "crab_row_norm_loraz: cols=%d unsupported", cols);
+  CRAB_REQUIRE(cols % 8 == 0 && ldx % 8 == 0 && cols <= 8 * 512 * 8, "crab_row_norm_loraz: cols=%d unsupported", cols);
   CRAB_REQUIRE(groups >= 0 && groups <= 3, "crab_row_norm_loraz: groups must be 0..3");
   CRAB_REQUIRE(groups == 0 || (ra && z && ldra % 8 == 0), "crab_row_norm_loraz: ra/z needed when groups > 0");
   CRAB_REQUIRE((gamma == nullptr) == (y == nullptr), "crab_row_norm_loraz: gamma and y go together");
@@ -622,6 +757,46 @@ extern "C" int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, f
   if (rows <= 0) return CRAB_OK;
   const int nvec = cols / 8;
   const int vpt = (nvec + 255) / 256;
+  {
+    // decode batches: split the columns of each row over a cluster of P CTAs (largest P <= 8 that divides the row into
+    // slices of at most 256 vectors, preferring >= 64 vectors per CTA)
+    static int use_cluster = -1;
+    if (use_cluster < 0) { const char* e = getenv("CRAB_ROW_CLUSTER"); use_cluster = (e && e[0] == '0') ? 0 : 1; }
+    int P = 0, V = 2;
+    if (use_cluster && rows <= 64 && nvec >= 256) {
+      for (int c = 8; c >= 2 && P == 0; c >>= 1)
+        if (nvec % c == 0 && nvec / c <= 256 && nvec / c >= 64) P = c;
+      if (P == 8 && nvec % 4 == 0 && nvec / 4 <= 128) P = 4;  // 128 vectors per CTA keeps every thread busy with one vector
+      if (P == 0 && nvec % 8 == 0 && nvec / 8 <= 512) { P = 8; V = 4; }  // very wide rows (Qwen2-7B's 18944-column MLP)
+    }
+    if (P > 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)rows, (unsigned)(groups > 0 ? groups : 1), (unsigned)P);
+      cfg.blockDim = dim3(128);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)P;
+      int na = 1;
+      if (pdl_mask() & PDL_ROW) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+      }
+      cfg.attrs = at;
+      cfg.numAttrs = na;
+      auto xx2 = reinterpret_cast<const __nv_bfloat16*>(x);
+      auto yy2 = reinterpret_cast<__nv_bfloat16*>(y);
+      auto rr2 = reinterpret_cast<const __nv_bfloat16*>(ra);
+      auto zz2 = reinterpret_cast<__nv_bfloat16*>(z);
+      if (gamma && V == 2) CRAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, row_loraz_cluster_kernel<true, 2>, xx2, ldx, gamma, eps, yy2, ldy, rr2, ldra, groups, zz2, ldz, scale, cols, P));
+      else if (gamma) CRAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, row_loraz_cluster_kernel<true, 4>, xx2, ldx, gamma, eps, yy2, ldy, rr2, ldra, groups, zz2, ldz, scale, cols, P));
+      else if (V == 2) CRAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, row_loraz_cluster_kernel<false, 2>, xx2, ldx, gamma, eps, yy2, ldy, rr2, ldra, groups, zz2, ldz, scale, cols, P));
+      else CRAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, row_loraz_cluster_kernel<false, 4>, xx2, ldx, gamma, eps, yy2, ldy, rr2, ldra, groups, zz2, ldz, scale, cols, P));
+      return CRAB_OK;
+    }
+  }
   auto xx = reinterpret_cast<const __nv_bfloat16*>(x);
   auto yy = reinterpret_cast<__nv_bfloat16*>(y);
   auto rr = reinterpret_cast<const __nv_bfloat16*>(ra);

@@ -166,6 +166,7 @@ def test_gemm_skinny_swiglu_matches_prefill_kernel(cuda_dev):
 
 
 @pytest.mark.parametrize("cols,groups,norm", [(4096, 3, True), (4096, 2, True), (4096, 1, False), (11008, 1, False), (256, 3, True),
+                                              (3584, 3, True), (18944, 1, False),
                                               (4096, 0, True)])
 def test_row_norm_loraz(cuda_dev, cols, groups, norm):
     from crab_b200 import ops
