@@ -25,6 +25,11 @@ def set_pdl(mask: int) -> None:
     _pdl_mask = int(mask) & 63
 
 
+def set_gemm_2cta(mode: int) -> None:
+    """CTA-pair GEMM policy: 0 never, 1 auto, 2 always when the 256-wide tile is used (include/crab_b200.h)."""
+    _l.check(_l.load().crab_set_gemm_2cta(C.c_int(int(mode))), "crab_set_gemm_2cta")
+
+
 def launch_count() -> int:
     """Number of crab_b200 CUDA kernels launched (or replayed from a captured graph) so far in this process."""
     return _launches

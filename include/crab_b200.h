@@ -72,6 +72,9 @@ typedef struct crab_gemm_args {
 } crab_gemm_args;
 
 int crab_gemm_bf16(const crab_gemm_args* args, void* stream);
+/* CTA-pair (tcgen05 cta_group::2, 256 x 256 tile on two SMs) policy for crab_gemm_bf16: 0 never, 1 auto (default: K >= 2048,
+ * M >= 16384, >= 4 waves of pairs), 2 whenever block_n resolves to 256 (env CRAB_GEMM_2CTA gives the initial value). */
+int crab_set_gemm_2cta(int mode);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Norms

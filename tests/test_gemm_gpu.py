@@ -100,6 +100,60 @@ def test_gemm_swiglu(cuda_dev):
         _check(out, ref)
 
 
+@pytest.fixture
+def force_pair(cuda_dev):
+    """Route every block_n=256 GEMM with >= 2 tiles through the cta_group::2 CTA-pair kernel for the duration of a test."""
+    from crab_b200 import ops
+
+    ops.set_gemm_2cta(2)
+    yield
+    ops.set_gemm_2cta(1)
+
+
+@pytest.mark.parametrize("M,N,K,max_ctas", [(512, 512, 64, 0), (700, 776, 520, 0), (1500, 776, 520, 6), (4173, 1304, 1000, 0),
+                                             (257, 1024, 4192, 0), (16640, 520, 2080, 0)])
+def test_gemm_cta_pair_plain(cuda_dev, force_pair, M, N, K, max_ctas):
+    """cta_group::2: ragged M / N / K tails, odd tile counts per pair, smem ring wrap-around with few pairs, and (last
+    case) a shape the auto policy itself sends to the pair kernel."""
+    from crab_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(cuda_dev)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(cuda_dev)
+    out = ops.gemm(a, w, block_n=256, max_ctas=max_ctas)
+    torch.cuda.synchronize()
+    _check(out, _ref(a, w))
+    ops.set_gemm_2cta(0)
+    single = ops.gemm(a, w, block_n=256, max_ctas=max_ctas)
+    assert torch.equal(out, single)  # same k order, same fp32 accumulation: bit-identical to the single-CTA kernel
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_gemm_cta_pair_epilogues(cuda_dev, force_pair, act, out_dtype):
+    from crab_b200 import ops
+
+    M, N, K = 515, 776, 328
+    g = torch.Generator(device="cpu").manual_seed(11 + act)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(cuda_dev)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(cuda_dev)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    res = torch.randn(M, N, generator=g).to(torch.bfloat16).to(cuda_dev)
+    out = ops.gemm(a, w, bias=bias, residual=res, res_scale=2.2, act=act, out_dtype=out_dtype, out_scale=0.5, block_n=256)
+    torch.cuda.synchronize()
+    _check(out, _ref(a, w, bias, res, 2.2, act, 0.5))
+    # in-place residual (x += ...) and the SwiGLU pair epilogue
+    x = res.clone()
+    ops.gemm(a, w, residual=x, out=x, block_n=256)
+    _check(x, _ref(a, w, None, res, 1.0, 0, 1.0))
+    F = 384
+    wg = (torch.randn(F, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(cuda_dev)
+    wu = (torch.randn(F, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(cuda_dev)
+    packed = torch.stack([wg.view(F // 64, 64, K), wu.view(F // 64, 64, K)], dim=1).reshape(2 * F, K).contiguous()
+    sw = ops.gemm(a, packed, act=ops.ACT_SWIGLU, block_n=256)
+    _check(sw, torch.nn.functional.silu(a.float() @ wg.float().t()) * (a.float() @ wu.float().t()))
+
+
 def test_gemm_lora_z(cuda_dev):
     from crab_b200 import ops
 
