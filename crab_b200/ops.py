@@ -230,7 +230,11 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
                     o_bs=o_strides[0], o_rs=o_strides[1], o_hs=o_strides[2],
                     B=B, H=H, KVH=KVH, Sq=Sq, Sk=Sk, head_dim=head_dim, scale=scale, causal=int(causal),
                     gate=_ptr(gate), bias_table=_ptr(bias_table))
-    with _timed("crab_flash_attn"):
+    # algorithmic work: 4*Sq*Sk*hd per (b, h), the visible half under a causal mask; hd-128 problems with >= 128 queries and no
+    # bias run on the tcgen05 / TMEM kernel (flash_tcgen05.cu), the rest on the mma.sync kernel
+    tag = "crab_flash_attn_tcgen05<128>" if (head_dim == 128 and gate is None and Sq >= 128) else f"crab_flash_attn<{head_dim}>"
+    fl = 4.0 * B * H * Sq * Sk * head_dim * ((Sk - Sq / 2.0) / Sk if causal else 1.0)
+    with _timed(tag, fl, 2.0 * (B * H * Sq * head_dim * 2 + 2 * B * KVH * Sk * head_dim)):
         _l.check(_l.load().crab_flash_attn(C.byref(a), _stream()), "crab_flash_attn")
     count_launches(1)
     return out
