@@ -50,6 +50,7 @@ struct FlashParams {
   int causal;
   const float* gate;   // [B, H, Sq] or null
   const float* table;  // [H, Sq, Sk] or null   (bias = gate * table)
+  const int* sk_dev;   // null, or the number of keys in device memory (overrides Sk)
 };
 
 template <int HD, int MT>
@@ -91,17 +92,18 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
   const __nv_bfloat16* qg = p.q + b * p.q_bs + h * p.q_hs;
   const __nv_bfloat16* kg = p.k + b * p.k_bs + kvh * p.k_hs;
   const __nv_bfloat16* vg = p.v + b * p.v_bs + kvh * p.v_hs;
-  const int off = p.Sk - p.Sq;  // causal: key j visible to query i iff j <= i + off
-  int n_tiles = (p.Sk + Cfg::BN - 1) / Cfg::BN;
+  const int Sk = p.sk_dev ? *p.sk_dev : p.Sk;
+  const int off = Sk - p.Sq;  // causal: key j visible to query i iff j <= i + off
+  int n_tiles = (Sk + Cfg::BN - 1) / Cfg::BN;
   if (p.causal) {
-    const int last_key = min(p.Sk - 1, q0 + Cfg::BM - 1 + off);
+    const int last_key = min(Sk - 1, q0 + Cfg::BM - 1 + off);
     n_tiles = min(n_tiles, last_key / Cfg::BN + 1);
   }
 
 #pragma unroll
   for (int t = 0; t < MT; ++t) load_tile<HD>(sQ + t * Cfg::TILE_BYTES, qg, p.q_rs, q0 + t * 64, p.Sq);
-  load_tile<HD>(sK0, kg, p.k_rs, 0, p.Sk);
-  load_tile<HD>(sV0, vg, p.v_rs, 0, p.Sk);
+  load_tile<HD>(sK0, kg, p.k_rs, 0, Sk);
+  load_tile<HD>(sV0, vg, p.v_rs, 0, Sk);
   cp_async_commit();
 
   constexpr int DT = HD / 8;  // output n8-tiles per row
@@ -127,8 +129,8 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
   for (int t = 0; t < n_tiles; ++t) {
     const int buf = t & 1;
     if (t + 1 < n_tiles) {
-      load_tile<HD>(sK0 + (buf ^ 1) * Cfg::TILE_BYTES, kg, p.k_rs, (t + 1) * Cfg::BN, p.Sk);
-      load_tile<HD>(sV0 + (buf ^ 1) * Cfg::TILE_BYTES, vg, p.v_rs, (t + 1) * Cfg::BN, p.Sk);
+      load_tile<HD>(sK0 + (buf ^ 1) * Cfg::TILE_BYTES, kg, p.k_rs, (t + 1) * Cfg::BN, Sk);
+      load_tile<HD>(sV0 + (buf ^ 1) * Cfg::TILE_BYTES, vg, p.v_rs, (t + 1) * Cfg::BN, Sk);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const int q_min = q0 + (warp * MT + mt) * 16;  // smallest query row of this m-tile (warp-uniform)
-      const bool general = (p.table != nullptr) || (k0 + Cfg::BN > p.Sk) || (p.causal && (k0 + Cfg::BN - 1 > q_min + off));
+      const bool general = (p.table != nullptr) || (k0 + Cfg::BN > Sk) || (p.causal && (k0 + Cfg::BN - 1 > q_min + off));
       float mx[2] = {-INFINITY, -INFINITY};
       if (general) {
 #pragma unroll
@@ -187,9 +189,9 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
             const int hi = e >> 1;
             const int qi = r_lo[mt] + hi * 8;
             float v = s[mt][nt][e] * sl2;
-            if (p.table != nullptr && qi < p.Sq && kj < p.Sk)
-              v += (hi ? gate_hi[mt] : gate_lo[mt]) * p.table[((size_t)h * p.Sq + qi) * p.Sk + kj] * 1.4426950408889634f;
-            const bool masked = (kj >= p.Sk) || (p.causal && kj > qi + off);
+            if (p.table != nullptr && qi < p.Sq && kj < Sk)
+              v += (hi ? gate_hi[mt] : gate_lo[mt]) * p.table[((size_t)h * p.Sq + qi) * Sk + kj] * 1.4426950408889634f;
+            const bool masked = (kj >= Sk) || (p.causal && kj > qi + off);
             v = masked ? -INFINITY : v;
             s[mt][nt][e] = v;
             mx[hi] = fmaxf(mx[hi], v);
@@ -614,6 +616,7 @@ extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
   CRAB_REQUIRE(a->B > 0 && a->H > 0 && a->KVH > 0 && a->H % a->KVH == 0 && a->Sq > 0 && a->Sk > 0, "crab_flash_attn: bad shape");
   CRAB_REQUIRE((a->gate == nullptr) == (a->bias_table == nullptr), "crab_flash_attn: gate and bias_table go together");
   CRAB_REQUIRE(!a->causal || a->Sk >= a->Sq, "crab_flash_attn: causal needs Sk >= Sq");
+  CRAB_REQUIRE(!a->sk_dev || (!a->causal && !a->bias_table), "crab_flash_attn: sk_dev is for bias-free non-causal problems");
   const long long strides[] = {a->q_bs, a->q_rs, a->q_hs, a->k_bs, a->k_rs, a->k_hs, a->v_bs, a->v_rs, a->v_hs, a->o_rs, a->o_hs, a->o_bs};
   for (long long s : strides) CRAB_REQUIRE(s % 8 == 0, "crab_flash_attn: strides must be multiples of 8 elements");
   CRAB_REQUIRE(((uintptr_t)a->q % 16 == 0) && ((uintptr_t)a->k % 16 == 0) && ((uintptr_t)a->v % 16 == 0) && ((uintptr_t)a->o % 4 == 0),
@@ -625,10 +628,10 @@ extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
   p.v_bs = a->v_bs; p.v_rs = a->v_rs; p.v_hs = a->v_hs;
   p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
   p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.Sq = a->Sq; p.Sk = a->Sk;
-  p.scale = a->scale; p.causal = a->causal; p.gate = a->gate; p.table = a->bias_table;
+  p.scale = a->scale; p.causal = a->causal; p.gate = a->gate; p.table = a->bias_table; p.sk_dev = a->sk_dev;
   cudaStream_t st = (cudaStream_t)stream;
   {  // head_dim 128 without a bias table and with TMA-describable strides: the tcgen05 / TMEM kernel (flash_tcgen05.cu)
-    const int rc = flash_attn_tcgen05_try(a, st);
+    const int rc = a->sk_dev ? -1 : flash_attn_tcgen05_try(a, st);
     if (rc == 0) return CRAB_OK;
     if (rc < -1) return rc;
   }

@@ -330,8 +330,7 @@ __global__ void beats_posconv_finish_kernel(const __nv_bfloat16* __restrict__ x,
 // ----------------------------------------------------------------------------------------------------------------
 // arg-max over the first V columns of fp32 logits rows (first index wins ties, like torch.argmax on CPU/CUDA)
 // ----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ logits, int ld, int V,
-                                                     int64_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) argmax_kernel(const float* logits, int ld, int V, int64_t* out) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sv[8];
@@ -365,6 +364,76 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ l
   }
 }
 
+
+// Large vocabularies (Qwen2: 152 k logits per row): the row is split over the 8 CTAs of a cluster, the (max, index) partials
+// meet in rank 0's shared memory (DSMEM) and rank 0 picks the winner — smallest index among equal maxima, like the
+// single-block kernel.  133 us -> a few us per decode step at bs 32.
+__global__ void __launch_bounds__(256) argmax_cluster_kernel(const float* logits, int ld, int V, int64_t* out) {
+  // no __restrict__ / __ldg on the logits: they come from the previous kernel of the (possibly PDL) chain, and invariant loads
+  // may be hoisted above griddepcontrol.wait
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  __shared__ float pv[8];
+  __shared__ int pi[8];
+  uint32_t rank, nranks;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nranks));
+  const float* r = logits + (size_t)blockIdx.x * ld;
+  const int per = ((V + (int)nranks - 1) / (int)nranks + 3) & ~3;  // multiple of 4: float4 loads (ld % 4 == 0 on the host)
+  const int lo = (int)rank * per, hi = min(V, lo + per);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = lo + 4 * (int)threadIdx.x; i < hi; i += 4 * (int)blockDim.x) {
+    if (i + 3 < hi) {
+      const float4 q = *reinterpret_cast<const float4*>(r + i);
+      const float vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (vv[e] > best || (vv[e] == best && i + e < bi)) { best = vv[e]; bi = i + e; }
+    } else {
+      for (int e = 0; i + e < hi; ++e) {
+        const float v = r[i + e];
+        if (v > best || (v == best && i + e < bi)) { best = v; bi = i + e; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sv[w] = best; si[w] = bi; }
+  __syncthreads();
+  if (w == 0) {
+    best = (l < 8) ? sv[l] : -INFINITY;
+    bi = (l < 8) ? si[l] : 0x7fffffff;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (l == 0) {
+      uint32_t a0 = smem_u32(&pv[rank]), a1 = smem_u32(&pi[rank]), r0, r1;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r0) : "r"(a0));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r1) : "r"(a1));
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(r0), "f"(best) : "memory");
+      asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(r1), "r"(bi) : "memory");
+    }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (rank == 0 && threadIdx.x == 0) {
+    float b = -INFINITY;
+    int ix = 0x7fffffff;
+    for (uint32_t k = 0; k < nranks; ++k)
+      if (pv[k] > b || (pv[k] == b && pi[k] < ix)) { b = pv[k]; ix = pi[k]; }
+    out[blockIdx.x] = ix;
+  }
+}
 
 // ----------------------------------------------------------------------------------------------------------------
 // Small-M (decode) row kernel: optional RMSNorm, then the hyper-LoRA pre-pass for up to 3 linears sharing the row:
@@ -740,6 +809,25 @@ extern "C" int crab_beats_posconv_finish(const void* x, const void* conv_g, cons
 extern "C" int crab_argmax(const float* logits, int ld, int rows, int V, int64_t* out, void* stream) {
   CRAB_REQUIRE(logits && out && V > 0, "crab_argmax: bad args");
   if (rows <= 0) return CRAB_OK;
+  if (V >= 16384 && ld % 4 == 0 && ((uintptr_t)logits % 16 == 0)) {  // one cluster of 8 CTAs per row
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)rows, 8);
+    cfg.blockDim = dim3(256);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 8; at[0].val.clusterDim.z = 1;
+    int na = 1;
+    if (pdl_mask() & PDL_LIGHT) {
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = na;
+    CRAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, argmax_cluster_kernel, logits, ld, V, out));
+    return CRAB_OK;
+  }
   CRAB_CHECK_CUDA(launch_pdl(PDL_LIGHT, argmax_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, logits, ld, V, out));
   return CRAB_OK;
 }

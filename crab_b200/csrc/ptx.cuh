@@ -200,6 +200,12 @@ __device__ __forceinline__ uint4 ld_dep_u4(const void* p) {
 }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ float ld_dep_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------

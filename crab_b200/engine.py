@@ -175,6 +175,7 @@ class CrabEngine:
         self.pdl_chain, self.pdl_after_attn = int(plan[0]), int(plan[-1])
         # decode step: RoPE + KV append + o_proj LoRA pre-pass inside the attention kernel (8 launches per layer, not 10)
         self.fuse_decode_attn = os.environ.get("CRAB_DECODE_FUSE", "1") != "0"
+        self.gqa_decode_tc = os.environ.get("CRAB_GQA_DECODE_TC", "1") != "0"
         self._graph = None
         self._graph_bs = None
         self._use_graph = False
@@ -626,8 +627,19 @@ class CrabEngine:
                 if self.lora:
                     ops.gemm(xn[:, :D], L["ra_qkv"], act=ops.ACT_LORA_Z, out_scale=sc, out=xn[:, D:D + 72])
                 ops.gemm(xn, L["wqkv"], bias=L["bqkv"], out=qkv, k=D + (self.EXT_QKV if self.lora else 0))
-            fused = skinny and self.fuse_decode_attn
-            if fused:
+            G = H // KV
+            # grouped-query decode with enough (batch x kv-head) problems to fill the SMs: the G query heads of a kv group are
+            # the Sq = G "rows" of one flash-attention problem, so QK^T / PV run on tensor cores instead of G scalar dot
+            # products per key per lane (Qwen2-7B, G = 7: 120 us -> ~15 us per layer at bs 32)
+            gqa_tc = skinny and G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
+            fused = skinny and self.fuse_decode_attn and not gqa_tc
+            if gqa_tc:
+                ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, S, H, KV, hd, past=past, past_dev=past_dev)
+                ops.flash_attn(qkv, self.k_cache[li], self.v_cache[li], at, B=B, H=KV, KVH=KV, Sq=G, Sk=ctx, head_dim=hd,
+                               q_strides=(nq + 2 * nk, hd, G * hd), k_strides=(KV * ctx * hd, hd, ctx * hd),
+                               v_strides=(KV * ctx * hd, hd, ctx * hd), o_strides=(nq + self.EXT_O, hd, G * hd),
+                               scale=1 / math.sqrt(hd), sk_dev=len_dev)
+            elif fused:
                 # one launch: RoPE on q / new k, cache append, attention over past + 1 keys, and (nsplit == 1) the o_proj
                 # LoRA pre-pass whose z columns land in at[:, nq:]
                 lo = self.lora and nsplit == 1
@@ -638,7 +650,7 @@ class CrabEngine:
                                       lora_counters=self._buf("dec_lora_cnt", (B,), torch.int32, zero=True) if lo else None)
             else:
                 ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, S, H, KV, hd, past=past, past_dev=past_dev)
-            if fused:
+            if fused or gqa_tc:
                 pass
             elif S == 1 and len_dev is not None:
                 ops.attn_decode(qkv, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV, head_dim=hd,

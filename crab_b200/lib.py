@@ -70,7 +70,7 @@ class AttnArgs(C.Structure):
         ("o_bs", C.c_int64), ("o_rs", C.c_int64), ("o_hs", C.c_int64),
         ("B", C.c_int32), ("H", C.c_int32), ("KVH", C.c_int32), ("Sq", C.c_int32), ("Sk", C.c_int32),
         ("head_dim", C.c_int32), ("scale", C.c_float), ("causal", C.c_int32),
-        ("gate", C.c_void_p), ("bias_table", C.c_void_p),
+        ("gate", C.c_void_p), ("bias_table", C.c_void_p), ("sk_dev", C.c_void_p),
     ]
 
 

@@ -220,7 +220,8 @@ def rope_kv_append(qkv: torch.Tensor, cos_sin: torch.Tensor, k_cache: torch.Tens
 
 def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, H: int, KVH: int,
                Sq: int, Sk: int, head_dim: int, q_strides, k_strides, v_strides, o_strides, scale: float,
-               causal: bool = False, gate: Optional[torch.Tensor] = None, bias_table: Optional[torch.Tensor] = None):
+               causal: bool = False, gate: Optional[torch.Tensor] = None, bias_table: Optional[torch.Tensor] = None,
+               sk_dev: Optional[torch.Tensor] = None):
     """Strides are (batch, row, head) in elements; q/k/v/out are any bf16 tensors whose data_ptr is the origin."""
     _req_cuda(q, k, v, out, gate, bias_table)
     a = _l.AttnArgs(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), o=out.data_ptr(),
@@ -229,10 +230,11 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
                     v_bs=v_strides[0], v_rs=v_strides[1], v_hs=v_strides[2],
                     o_bs=o_strides[0], o_rs=o_strides[1], o_hs=o_strides[2],
                     B=B, H=H, KVH=KVH, Sq=Sq, Sk=Sk, head_dim=head_dim, scale=scale, causal=int(causal),
-                    gate=_ptr(gate), bias_table=_ptr(bias_table))
+                    gate=_ptr(gate), bias_table=_ptr(bias_table), sk_dev=_ptr(sk_dev))
     # algorithmic work: 4*Sq*Sk*hd per (b, h), the visible half under a causal mask; hd-128 problems with >= 128 queries and no
     # bias run on the tcgen05 / TMEM kernel (flash_tcgen05.cu), the rest on the mma.sync kernel
-    tag = "crab_flash_attn_tcgen05<128>" if (head_dim == 128 and gate is None and Sq >= 128) else f"crab_flash_attn<{head_dim}>"
+    tag = ("crab_flash_attn_tcgen05<128>" if (head_dim == 128 and gate is None and Sq >= 128 and sk_dev is None)
+           else f"crab_flash_attn<{head_dim}>")
     fl = 4.0 * B * H * Sq * Sk * head_dim * ((Sk - Sq / 2.0) / Sk if causal else 1.0)
     with _timed(tag, fl, 2.0 * (B * H * Sq * head_dim * 2 + 2 * B * KVH * Sk * head_dim)):
         _l.check(_l.load().crab_flash_attn(C.byref(a), _stream()), "crab_flash_attn")

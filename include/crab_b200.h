@@ -107,6 +107,8 @@ int crab_rope_kv_append(void* qkv, int ldq, const float* cos_sin, void* k_cache,
  *           (models/Qformer.py:207-266) and causal LlamaAttention / Qwen2Attention prefill
  *           (models/modeling_llama.py:405-450, models/qwen/modeling_qwen2.py:190-199 repeat_kv).
  *           All strides are in elements; head_dim in {64,128}; bias = gate[B,H,Sq] * bias_table[H,Sq,Sk] (fp32) or NULL.
+ *           With sk_dev the number of keys is read on the device: the GQA decode step calls this with the G query heads of
+ *           a kv group as the Sq = G "rows" of one problem (q_rs = head_dim), so grouped-query decode runs on tensor cores.
  * crab_attn_decode replaces: the same attention at q_len == 1 over the KV cache (decode step), split over the
  *           context into `nsplit` partitions (workspace from crab_attn_decode_workspace_bytes when nsplit > 1).
  * ---------------------------------------------------------------------------------------------------------------- */
@@ -121,6 +123,7 @@ typedef struct crab_attn_args {
   int32_t causal;                                        /* key j visible to query i iff j <= i + (Sk - Sq) */
   const float* gate;
   const float* bias_table;
+  const int* sk_dev;                                     /* NULL, or device int overriding Sk (decode inside a CUDA graph) */
 } crab_attn_args;
 int crab_flash_attn(const crab_attn_args* args, void* stream);
 int crab_attn_decode_workspace_bytes(int B, int H, int head_dim, int nsplit, int64_t* bytes);

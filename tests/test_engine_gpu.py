@@ -156,3 +156,28 @@ def test_full_width_decoder_layer_vs_oracle(cuda_dev):
     e = [rel_l2(logits[i], ref_logits[i]) for i in range(3)]
     print("full-width logits rel_l2 per step:", ["%.3e" % v for v in e])
     assert max(e) < 4e-2
+
+
+def test_full_width_qwen7b_layer_vs_oracle(cuda_dev):
+    """BASELINE configs[4] shapes: Qwen2-7B-dim layers (D=3584, F=18944, 28 query / 4 kv heads x 128, qkv bias, theta 1e6)
+    with hyper-LoRA, 1 layer, bs 2, S=160: prefill (CTA-pair / tcgen05 flash with GQA) and two decode steps (cluster row
+    kernels on 18944-column rows, fused GQA decode attention, split-K streaming GEMMs) against the CPU oracle."""
+    from crab_b200 import engine as E
+    from crab_b200.models.unified_arch import decoder_manifest
+    from oracle import synth
+
+    dcfg = E.DecoderConfig(hidden=3584, inter=18944, layers=1, heads=28, kv_heads=4, head_dim=128, vocab=2048,
+                           rope_theta=1e6, qkv_bias=True)
+    sd = synth.synth_state_dict(decoder_manifest(dcfg), 5)
+    dec_o = O.DecoderCfg(hidden=3584, inter=18944, layers=1, heads=28, kv_heads=4, head_dim=128, vocab=2048, rope_theta=1e6,
+                         qkv_bias=True)
+    g = torch.Generator(device="cpu").manual_seed(10)
+    emb = torch.randn(2, 160, 3584, generator=g)
+    eng = E.CrabEngine(sd, E.CrabConfig(decoder=dcfg, max_ctx=192), cuda_dev, load_encoders=False)
+    with torch.no_grad():
+        ref_ids, ref_logits = O.greedy_generate(sd, emb.to(torch.bfloat16).float(), dec_o, 3)
+    out, logits = eng.generate_from_embeds(emb.to(cuda_dev).to(torch.bfloat16), 3, return_logits=True,
+                                           teacher_tokens=ref_ids.to(cuda_dev))
+    e = [rel_l2(logits[i], ref_logits[i]) for i in range(3)]
+    print("qwen-7B-width logits rel_l2 per step:", ["%.3e" % v for v in e])
+    assert max(e) < 4e-2

@@ -204,6 +204,32 @@ def test_attn_decode_fused_equals_the_three_kernel_sequence(cuda_dev, B, H, KVH,
             assert o2[:, nq + 24:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("B,H,KVH,length", [(32, 28, 4, 1150), (16, 32, 8, 77), (20, 8, 4, 64), (16, 28, 4, 1)])
+def test_gqa_decode_on_tensor_cores(cuda_dev, B, H, KVH, length):
+    """Grouped-query decode as a flash-attention problem (the G heads of a kv group = the query rows; key count read from
+    device memory, as inside the decode graph) against the scalar decode kernel and the fp32 reference."""
+    from crab_b200 import ops
+
+    hd, ctx, G = 128, 1280, H // KVH
+    g = _g(B + H + length)
+    ld = (H + 2 * KVH) * hd
+    q = torch.randn(B, ld, generator=g).to(torch.bfloat16).to(cuda_dev)
+    kc = torch.randn(B, KVH, ctx, hd, generator=g).to(torch.bfloat16).to(cuda_dev)
+    vc = torch.randn(B, KVH, ctx, hd, generator=g).to(torch.bfloat16).to(cuda_dev)
+    ldv = torch.tensor([length], dtype=torch.int32, device=cuda_dev)
+    o1 = torch.zeros(B, H * hd + 32, dtype=torch.bfloat16, device=cuda_dev)
+    o2 = torch.zeros_like(o1)
+    ops.attn_decode(q, kc, vc, o1[:, : H * hd], B=B, H=H, KVH=KVH, head_dim=hd, scale=hd ** -0.5, len_dev=ldv)
+    ops.flash_attn(q, kc, vc, o2, B=B, H=KVH, KVH=KVH, Sq=G, Sk=ctx, head_dim=hd, q_strides=(ld, hd, G * hd),
+                   k_strides=(KVH * ctx * hd, hd, ctx * hd), v_strides=(KVH * ctx * hd, hd, ctx * hd),
+                   o_strides=(H * hd + 32, hd, G * hd), scale=hd ** -0.5, sk_dev=ldv)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q[:, : H * hd].view(B, 1, H, hd).transpose(1, 2), kc[:, :, :length], vc[:, :, :length], hd ** -0.5)
+    _close(o2[:, : H * hd].view(B, H, hd), ref[:, :, 0], 2e-2)
+    _close(o2[:, : H * hd], o1[:, : H * hd], 2e-2)
+    assert o2[:, H * hd:].abs().max().item() == 0
+
+
 def test_gather_cast_patchify_argmax(cuda_dev):
     from crab_b200 import ops
 
@@ -227,6 +253,11 @@ def test_gather_cast_patchify_argmax(cuda_dev):
     logits = torch.randn(7, 32024, generator=g).to(cuda_dev)
     logits[:, 32017:] = 100.0  # padding columns must be ignored
     assert torch.equal(ops.argmax(logits, 32017), logits[:, :32017].argmax(-1))
+    big = torch.randn(32, 152088, generator=_g(4)).to(cuda_dev)   # Qwen2 vocabulary: the 8-CTA cluster kernel
+    big[3, 777] = big[3, 150001] = 50.0                            # tie: the first index wins
+    big[5, 152080] = 60.0                                          # winner in the last, ragged slice
+    assert torch.equal(ops.argmax(big, 152081), big[:, :152081].argmax(-1))
+    assert int(ops.argmax(big, 152081)[3]) == 777
 
 
 def test_clip_embed_and_beats_helpers(cuda_dev):
