@@ -22,7 +22,7 @@ import torch
 from . import ops
 
 SD = Dict[str, torch.Tensor]
-DEFAULT_PDL_PLAN = "0,0"
+DEFAULT_PDL_PLAN = "19,17"  # streaming GEMM + row kernels + light kernels; attention / RoPE stay plain launches
 
 
 # --------------------------------------------------------------------------------------------------------------
