@@ -34,9 +34,10 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // LayerNorm / RMSNorm: one block per row, row cached in registers (cols <= 8 * 8 * blockDim.x)
 // ----------------------------------------------------------------------------------------------------------------
 template <bool RMS, int VPT /* 8-element vectors per thread */>
-__global__ void __launch_bounds__(256) norm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+__global__ void __launch_bounds__(256) norm_kernel(const __nv_bfloat16* x, int ldx,
                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                   __nv_bfloat16* __restrict__ y, int ldy, int rows, int cols, float eps) {
+                                                   __nv_bfloat16* y, int ldy, int rows, int cols, float eps) {
+  // x is produced by the previous kernel of a (possibly PDL) chain: ordered loads, no __restrict__ / __ldg (ptx.cuh: ld_dep_u4)
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[32];
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(256) norm_kernel(const __nv_bfloat16* __restri
   for (int i = 0; i < VPT; ++i) {
     const int vi = threadIdx.x + i * blockDim.x;
     if (vi < nvec) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + vi), v[i]);
+      unpack8(ld_dep_u4(reinterpret_cast<const uint4*>(xr) + vi), v[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += RMS ? v[i][j] * v[i][j] : v[i][j];
     }
@@ -185,17 +186,17 @@ __global__ void __launch_bounds__(256) rope_kv_kernel(__nv_bfloat16* __restrict_
 // Row gather / scatter (embedding lookup, splice of modality embeddings, left padding)
 // dst[dst_rows[i] or i] = src[src_rows[i] or i]   (cols bf16, multiples of 8)
 // ----------------------------------------------------------------------------------------------------------------
-__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, int lds, const int64_t* __restrict__ src_rows,
-                                   __nv_bfloat16* __restrict__ dst, int ldd, const int64_t* __restrict__ dst_rows,
-                                   int n, int cols) {
+__global__ void gather_rows_kernel(const __nv_bfloat16* src, int lds, const int64_t* src_rows,
+                                   __nv_bfloat16* dst, int ldd, const int64_t* dst_rows, int n, int cols) {
+  // the row indices (and, for the splice, the source rows) may come from the previous kernel of a PDL chain: plain loads
   pdl_trigger();
   pdl_wait();
   const int i = blockIdx.x;
-  const int64_t sr = src_rows ? src_rows[i] : i;
-  const int64_t dr = dst_rows ? dst_rows[i] : i;
+  const int64_t sr = src_rows ? *reinterpret_cast<const volatile int64_t*>(src_rows + i) : i;
+  const int64_t dr = dst_rows ? *reinterpret_cast<const volatile int64_t*>(dst_rows + i) : i;
   const uint4* s = reinterpret_cast<const uint4*>(src + sr * lds);
   uint4* d = reinterpret_cast<uint4*>(dst + dr * ldd);
-  for (int v = threadIdx.x; v < cols / 8; v += blockDim.x) d[v] = __ldg(s + v);
+  for (int v = threadIdx.x; v < cols / 8; v += blockDim.x) d[v] = ld_dep_u4(s + v);
 }
 
 // fp32 -> bf16 rows (encoder inputs / fp32 features entering the bf16 path)

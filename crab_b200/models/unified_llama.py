@@ -268,15 +268,21 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
         if n > 1:
             eng.begin_decode(B)
         steps = 0
+        alive = []  # per step: does any row still need tokens after it?  (kept on the device; read once at the end)
         for step in range(n):
             tok = torch.where(done, torch.full_like(nxt, int(self.model.pad_token_id or 0)), nxt)
             out[:, step] = tok
             done |= torch.isin(tok, eos)
+            alive.append((~done).any())
             steps = step + 1
             if step % 8 == 7 and bool(done.all()):  # one host sync every 8 tokens instead of every token
                 break
             if step + 1 < n:
                 _, nxt = eng.decode_step()
+        # HF stops right after the step at which the last row emitted EOS: drop the (all-pad) columns decoded past it
+        hist = torch.stack(alive).cpu().tolist()
+        if False in hist:
+            steps = hist.index(False) + 1
         return out[:, :steps]
 
     def generate_avs(self, *a, **k):

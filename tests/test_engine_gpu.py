@@ -181,3 +181,39 @@ def test_full_width_qwen7b_layer_vs_oracle(cuda_dev):
     e = [rel_l2(logits[i], ref_logits[i]) for i in range(3)]
     print("qwen-7B-width logits rel_l2 per step:", ["%.3e" % v for v in e])
     assert max(e) < 4e-2
+
+
+def test_batched_generate_with_eos_and_unequal_prompts(cuda_dev):
+    """The batched-evaluation call pattern (scripts/finetune/inference_hyper_lora.py: generate(**sample,
+    max_new_tokens=500) on a batch with unequal prompt lengths): rows stop at EOS, finished rows emit the pad id, decoding ends
+    right after the last row finishes (HF semantics), and tokens before EOS equal the unconstrained greedy run."""
+    from crab_b200.engine import CrabEngine
+    from crab_b200.models.unified_llama import UnifiedConfig, UnifiedForCausalLM
+
+    g, case, sd, ocfg, ids, X = load_golden("llama_small_bs2")
+    assert len({int(t.numel()) for t in ids}) > 1, "the golden case must have unequal prompt lengths"
+    eng = CrabEngine(sd, engine_cfg(case, ocfg), cuda_dev)
+    lc = case["llama_cfg"]
+    model = UnifiedForCausalLM.from_engine(UnifiedConfig(hidden_size=lc["hidden_size"], intermediate_size=lc["intermediate_size"],
+                                                         num_hidden_layers=lc["num_hidden_layers"],
+                                                         num_attention_heads=lc["num_attention_heads"],
+                                                         num_key_value_heads=lc["num_key_value_heads"],
+                                                         vocab_size=lc["vocab_size"] + 17), eng)
+    n = 24
+    free = model.generate(batch_input_ids=ids, batch_labels=None, batch_X_modals=X, batch_task_names=["avqa"] * len(ids),
+                          max_new_tokens=n).cpu()
+    assert tuple(free.shape) == (len(ids), n)
+    # choose EOS ids so that row 0 stops at step 2 and row 1 at step 5
+    eos = [int(free[0, 2]), int(free[1, 5])]
+    pad = int(model.model.pad_token_id or 0)
+    exp = free.clone()
+    stop = []
+    for r in range(exp.shape[0]):
+        hit = [i for i in range(n) if int(exp[r, i]) in eos]
+        k = hit[0] if hit else n - 1
+        exp[r, k + 1:] = pad
+        stop.append(k)
+    exp = exp[:, : max(stop) + 1]
+    out = model.generate(batch_input_ids=ids, batch_labels=None, batch_X_modals=X, batch_task_names=["avqa"] * len(ids),
+                         max_new_tokens=n, eos_token_id=eos).cpu()
+    assert torch.equal(out, exp), (out.tolist(), exp.tolist())
