@@ -11,6 +11,8 @@
 //                        (dataset/quick_start_dataset.py:303-315) -> bf16 patch rows, skipping the fp32 NCHW tensor.
 //  normalize_u8_kernel — the same arithmetic to a fp32 NCHW tensor (`pixel_values`), for callers that want the
 //                        reference's intermediate.
+//  resample_u8_kernel  — Pillow's 8-bit bicubic resampler (the processor's shortest-edge resize), one separable pass,
+//                        integer arithmetic, bit-exact; the centre crop is folded in.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -146,6 +148,36 @@ __global__ void normalize_u8_kernel(const uint8_t* __restrict__ img, float* __re
   o[2 * (size_t)HW] = ((float)s[2] * rescale - m2) * is2;
 }
 
+// One separable pass of Pillow's 8-bit resampler (src/libImaging/Resample.c: ImagingResampleHorizontal_8bpc /
+// ImagingResampleVertical_8bpc — the routine HF's CLIPImageProcessor of the reference's pinned transformers calls through
+// PIL.Image.resize(..., BICUBIC)): out = clip8((2^21 + sum_k in[xmin + k] * kk[k]) >> 22) with integer coefficients built on
+// the host.  uint8 [n, H, W, 3] interleaved; `axis` 1 = along x, 0 = along y; output index i uses coefficient row out0 + i, so the
+// centre crop that follows the resize costs nothing (only the kept window is computed).  Integer arithmetic: bit-exact.
+__global__ void resample_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n, int in_h, int in_w,
+                                   int out_h, int out_w, int axis, const int* __restrict__ bounds,
+                                   const int* __restrict__ kk, int ksize, int out0) {
+  const long long total = (long long)n * out_h * out_w * 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % 3);
+  const int x = (int)((i / 3) % out_w);
+  const int y = (int)((i / (3LL * out_w)) % out_h);
+  const int img = (int)(i / (3LL * out_w * out_h));
+  const int o = out0 + (axis ? x : y);
+  const int lo = bounds[2 * o], cnt = bounds[2 * o + 1];
+  const int* k = kk + (size_t)o * ksize;
+  int ss = 1 << 21;
+  if (axis) {
+    const uint8_t* p = in + (((size_t)img * in_h + y) * in_w + lo) * 3 + c;
+    for (int t = 0; t < cnt; ++t) ss += (int)p[(size_t)t * 3] * k[t];
+  } else {
+    const uint8_t* p = in + (((size_t)img * in_h + lo) * in_w + x) * 3 + c;
+    for (int t = 0; t < cnt; ++t) ss += (int)p[(size_t)t * in_w * 3] * k[t];
+  }
+  ss >>= 22;
+  out[i] = (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+}
+
 }  // namespace crab
 
 using namespace crab;
@@ -200,6 +232,20 @@ extern "C" int crab_normalize_u8(const void* images_hwc, float* out_nchw, int n_
   normalize_u8_kernel<<<(unsigned)((n_pix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint8_t*>(images_hwc), out_nchw, n_pix, H * W, mean3[0], mean3[1], mean3[2], 1.f / std3[0],
       1.f / std3[1], 1.f / std3[2], rescale);
+  CRAB_CHECK_CUDA(cudaGetLastError());
+  return CRAB_OK;
+}
+
+extern "C" int crab_resample_u8(const void* in_hwc, void* out_hwc, int n_img, int in_h, int in_w, int out_h, int out_w, int axis,
+                                const int* bounds, const int* kk, int ksize, int out0, void* stream) {
+  CRAB_REQUIRE(in_hwc && out_hwc && bounds && kk && ksize > 0 && out0 >= 0, "crab_resample_u8: bad args");
+  CRAB_REQUIRE(axis == 0 || axis == 1, "crab_resample_u8: axis must be 0 (rows) or 1 (columns)");
+  CRAB_REQUIRE(axis == 1 ? in_h == out_h : in_w == out_w, "crab_resample_u8: the other axis must keep its size");
+  const long long total = (long long)n_img * out_h * out_w * 3;
+  if (total <= 0) return CRAB_OK;
+  resample_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint8_t*>(in_hwc), reinterpret_cast<uint8_t*>(out_hwc), n_img, in_h, in_w, out_h, out_w, axis, bounds,
+      kk, ksize, out0);
   CRAB_CHECK_CUDA(cudaGetLastError());
   return CRAB_OK;
 }

@@ -353,6 +353,24 @@ def normalize_u8(images: torch.Tensor, mean, std, rescale: float = 1.0 / 255.0) 
     return out
 
 
+def resample_u8(images: torch.Tensor, out_size: int, axis: int, bounds: torch.Tensor, kk: torch.Tensor, out0: int) -> torch.Tensor:
+    """One pass of Pillow's 8-bit resampler on uint8 (n, H, W, 3): axis 1 -> (n, H, out_size, 3), axis 0 -> (n, out_size, W, 3);
+    output index j uses coefficient row out0 + j (centre crop folded in)."""
+    _req_cuda(images, bounds, kk)
+    if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[-1] != 3 or not images.is_contiguous():
+        raise _l.CrabError("resample_u8 wants a contiguous uint8 (n, H, W, 3) tensor")
+    assert bounds.dtype == torch.int32 and kk.dtype == torch.int32 and bounds.is_contiguous() and kk.is_contiguous()
+    n, h, w, _ = images.shape
+    oh, ow = (h, out_size) if axis == 1 else (out_size, w)
+    assert out0 + out_size <= bounds.shape[0]
+    out = torch.empty((n, oh, ow, 3), device=images.device, dtype=torch.uint8)
+    with _timed("crab_resample_u8"):
+        _l.check(_l.load().crab_resample_u8(_vp(images), _vp(out), _i(n), _i(h), _i(w), _i(oh), _i(ow), _i(axis), _vp(bounds),
+                                            _vp(kk), _i(kk.shape[1]), _i(out0), _stream()), "crab_resample_u8")
+    count_launches(1)
+    return out
+
+
 def fbank_num_frames(n_samples: int) -> int:
     n = C.c_int(0)
     _l.check(_l.load().crab_fbank_num_frames(_i(n_samples), C.byref(n)), "crab_fbank_num_frames")

@@ -235,6 +235,13 @@ int crab_patchify_u8(const void* images_hwc, void* out, int ld_out, int n_img, i
                      const float* mean3, const float* std3, float rescale, void* stream);
 int crab_normalize_u8(const void* images_hwc, float* out_nchw, int n_img, int H, int W, const float* mean3,
                       const float* std3, float rescale, void* stream);
+/* crab_resample_u8 replaces: the processor's shortest-edge resize, i.e. PIL.Image.resize(size, BICUBIC) of the pinned
+ *           transformers (Pillow's ImagingResample{Horizontal,Vertical}_8bpc), one separable pass per call on uint8
+ *           [n, H, W, 3]: axis 1 resamples columns (in_h == out_h), axis 0 rows (in_w == out_w).  bounds[2*i] / bounds[2*i+1]
+ *           = first tap / tap count and kk[i*ksize ..] = 22-bit fixed-point coefficients of output index i (built on the host
+ *           from Pillow's formula); output element j reads coefficient row out0 + j, which folds the centre crop in. */
+int crab_resample_u8(const void* in_hwc, void* out_hwc, int n_img, int in_h, int in_w, int out_h, int out_w, int axis,
+                     const int* bounds, const int* kk, int ksize, int out0, void* stream);
 
 /* Diagnostic (not on the product path): pure HBM->smem ring streaming, used by tools/ to size the decode pipelines. */
 int crab_debug_stream(const void* src, int64_t bytes, int chunk_bytes, int stages, int ctas, void* sink, void* stream);

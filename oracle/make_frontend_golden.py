@@ -48,10 +48,17 @@ def main():
     frames = synth_frames(5, 1)
     pil = [Image.fromarray(f.numpy()) for f in frames]
     pv = proc.preprocess(pil, return_tensors="pt")["pixel_values"].to(torch.float32)
+    # non-224 input: Pillow itself (what transformers 4.37's CLIPImageProcessor.resize calls), shortest edge 224 + centre crop
+    import numpy as np
+    big = synth_frames(9, 1, 8)[0].numpy().repeat(45, 0).repeat(61, 1)[:300, :400]   # 300 x 400 blocky image with hard edges
+    oh, ow = 224, int(224 * 400 / 300)
+    rz = np.asarray(Image.fromarray(big).resize((ow, oh), Image.BICUBIC))
+    top, left = (oh - 224) // 2, (ow - 224) // 2
+    resize_crop = torch.from_numpy(rz[top:top + 224, left:left + 224].copy())
     import torchaudio.compliance.kaldi as K
     mel_banks, _ = K.get_mel_banks(128, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)
     window = K._feature_window_function(K.POVEY, 400, 0.42, torch.device('cpu'), torch.float32)
-    out = dict(mel_banks=mel_banks.clone(), window=window.clone(), wave_seed=11, fbank=fb.clone(), fbank_ragged=fb2.clone(), ragged_len=int(wav2.shape[1]),
+    out = dict(resize_seed=9, resize_crop_300x400=resize_crop, mel_banks=mel_banks.clone(), window=window.clone(), wave_seed=11, fbank=fb.clone(), fbank_ragged=fb2.clone(), ragged_len=int(wav2.shape[1]),
                frame_seed=5, pixel_values=pv.clone(),
                versions=dict(torch=str(torch.__version__), torchaudio=str(__import__("torchaudio").__version__),
                              transformers=str(__import__("transformers").__version__)))

@@ -53,6 +53,30 @@ def test_host_tables_are_the_reference_tables(gold):
     assert torch.equal(dense, gold["mel_banks"])  # the sparse rows lose nothing
 
 
+def test_oracle_resize_is_pillow_bit_exact_and_tables_agree():
+    """The resize restatement against Pillow itself (the routine transformers 4.37's CLIPImageProcessor calls), bit for bit,
+    including the committed golden; the product's vectorised coefficient tables against the oracle's loops."""
+    import numpy as np
+    from PIL import Image
+
+    from crab_b200.dataset import image_processor as P
+
+    rng = np.random.default_rng(0)
+    for (H, W, oh, ow) in [(37, 53, 24, 34), (480, 640, 224, 298), (100, 80, 280, 224), (231, 517, 224, 501), (224, 300, 224, 300),
+                           (224, 224, 224, 224)]:
+        im = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(im).resize((ow, oh), Image.BICUBIC))
+        assert np.array_equal(F.pil_resize_bicubic(im, oh, ow), ref), (H, W, oh, ow)
+        for a, b in ((W, ow), (H, oh)):
+            bt, kk = P.pil_bicubic_tables(a, b)
+            for i, (lo, k) in enumerate(F.pil_coeffs(a, b)):
+                assert bt[i, 0] == lo and bt[i, 1] == len(k) and kk[i, : len(k)].tolist() == k and not kk[i, len(k):].any()
+    assert P.resize_output_size(300, 400, 224) == (224, 298) and P.resize_output_size(480, 360, 224) == (298, 224)
+    gold = torch.load(GOLD)
+    got = F.clip_resize_crop(F.synth_frames(gold["resize_seed"], 1, 8)[0].numpy().repeat(45, 0).repeat(61, 1)[:300, :400])
+    assert np.array_equal(got, gold["resize_crop_300x400"].numpy())
+
+
 def test_frontend_refuses_cpu_and_bad_shapes():
     from crab_b200.dataset import audio_processor as A
     from crab_b200.dataset.image_processor import ClipImageProcessorB200, frames_to_uint8_thwc

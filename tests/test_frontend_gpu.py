@@ -103,3 +103,28 @@ def test_engine_accepts_raw_uint8_frames(cuda_dev):
     o1 = eng.generate(ids, X_u8, 6)
     o2 = eng.generate(ids, X_f32, 6)
     assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("H,W", [(300, 400), (480, 360), (150, 224), (224, 300), (640, 480), (96, 131)])
+def test_resize_crop_is_pillow_bit_exact(cuda_dev, H, W):
+    """Shortest-edge bicubic resize + centre crop on the GPU == PIL.Image.resize(BICUBIC) + crop, byte for byte (up- and
+    down-scaling, either orientation, one-axis-only cases), and the processor's pixel_values follow from it."""
+    import numpy as np
+    from PIL import Image
+
+    from crab_b200.dataset.image_processor import ClipImageProcessorB200, resize_output_size
+
+    rng = np.random.default_rng(H * 1000 + W)
+    frames = rng.integers(0, 256, (3, H, W, 3), dtype=np.uint8)
+    frames[0, : H // 2] = 255           # saturated regions: the bicubic overshoot must clip exactly as Pillow clips
+    frames[0, H // 2:] = 0
+    proc = ClipImageProcessorB200()
+    got = proc.to_device_uint8(torch.from_numpy(frames)).cpu().numpy()
+    nh, nw = resize_output_size(H, W, 224)
+    top, left = (nh - 224) // 2, (nw - 224) // 2
+    for i in range(3):
+        ref = np.asarray(Image.fromarray(frames[i]).resize((nw, nh), Image.BICUBIC))[top:top + 224, left:left + 224]
+        assert np.array_equal(got[i], ref), (i, np.abs(got[i].astype(int) - ref.astype(int)).max())
+        assert np.array_equal(F.clip_resize_crop(frames[i]), ref)
+    pv = proc.preprocess(torch.from_numpy(frames))["pixel_values"].cpu()
+    assert (pv - F.clip_pixel_values(torch.from_numpy(got))).abs().max().item() < 2e-6

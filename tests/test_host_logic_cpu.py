@@ -116,3 +116,20 @@ def test_all_gather_of_generated_ids_world2_gloo():
         p.join(timeout=60)
     want = (torch.arange(5)[:, None] * 10 + torch.arange(4)[None, :]).tolist()
     assert res[0] == want and res[1] == want
+
+
+def test_bench_roofline_constants_match_the_survey():
+    """bench.py's algorithmic FLOP count per sample reproduces SURVEY.md 8(d): 15.86 TFLOP at S = 1086 for LLaMA-7B dims (the
+    figure `phases.prefill_frac_of_tensor_roofline` divides by), and both backbones resolve to their checkpoint dims."""
+    import types
+
+    import bench
+
+    a = types.SimpleNamespace(backbone="llama", layers=0)
+    b = bench.backbone(a)
+    assert (b["hidden"], b["inter"], b["layers"], b["heads"], b["kv_heads"], b["vocab"]) == (4096, 11008, 32, 32, 32, 32017)
+    assert abs(bench.algorithmic_prefill_tflop(b, 1086) - 15.86) < 0.01
+    q = bench.backbone(types.SimpleNamespace(backbone="qwen", layers=0))
+    assert (q["hidden"], q["inter"], q["layers"], q["heads"], q["kv_heads"], q["vocab"]) == (3584, 18944, 28, 28, 4, 152081)
+    assert q["qkv_bias"] and q["rope_theta"] == 1e6
+    assert bench.backbone(types.SimpleNamespace(backbone="qwen", layers=3))["layers"] == 3
