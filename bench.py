@@ -301,6 +301,8 @@ def main():
     ap.add_argument("--cpu-layers", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-pass", action="store_true",
+                    help="for ncu launch lists: stop after the timed resident steps (NVTX range 'crab_timed'); prints no JSON")
     args = ap.parse_args()
 
     # stdout carries exactly ONE line (the JSON): library chatter on fd 1 (e.g. NCCL's version banner) goes to stderr
@@ -408,10 +410,15 @@ def main():
     barrier()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
+    torch.cuda.nvtx.range_push("crab_timed")  # ncu --nvtx --nvtx-include "crab_timed/" profiles exactly the timed steps
     for i in range(args.steps):
         out = step_resident(evs[i])
+    torch.cuda.nvtx.range_pop()
     e_end.record()
     barrier()
+    if args.profile_pass:
+        sys.stderr.write(f"profile pass: {args.steps} timed step(s), {e_start.elapsed_time(e_end) / args.steps:.1f} ms/step under the profiler\n")
+        return
     kt = ops.stop_kernel_timing()
     launches = (ops.launch_count() - n0) // args.steps
     ms_total = e_start.elapsed_time(e_end)
