@@ -7,7 +7,7 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:"gemm_bf16_tcgen05|gemm_skinny|flash_attn|attn_decode|row_loraz|fbank|patchify_u8" -f -o gpurun_out/${TAG}_kernels \
+    -k regex:"gemm_bf16_tcgen05|gemm2_bf16_tcgen05|resample_u8|gemm_skinny|flash_attn|attn_decode|row_loraz|fbank|patchify_u8" -f -o gpurun_out/${TAG}_kernels \
     python tools/profile_kernels.py > gpurun_out/${TAG}_ncu.log 2>&1
 if [ "$2" == "--with-launch-list" ]; then
   # only the timed step is profiled (NVTX range pushed by bench.py); everything before it runs at native speed
