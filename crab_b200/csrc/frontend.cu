@@ -97,10 +97,9 @@ __global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const FbankParams p) 
     const int k = t + h * FB_THREADS;
     if (k <= FB_N / 2) {
       const float a = __fsqrt_rn(s_re[k] * s_re[k] + s_im[k] * s_im[k]);
-      s_x[k < FB_N ? k : 0] = a * a;
+      s_x[k] = a * a;
     }
   }
-  // bin 256 lives in s_x[256]; s_x has 512 slots so no overlap with anything still needed
   __syncthreads();
   if (t < p.n_mel) {
     const int b0 = p.mel_start[t], o0 = p.mel_off[t], n = p.mel_off[t + 1] - o0;

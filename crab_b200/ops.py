@@ -531,3 +531,81 @@ def row_norm_loraz(x: torch.Tensor, *, gamma: Optional[torch.Tensor] = None, eps
                                                _i(z.stride(0) if z is not None else 0), C.c_float(scale), _i(rows), _i(cols),
                                                _stream()), "crab_row_norm_loraz")
     count_launches(1)
+
+
+# ---- segmentation-head helpers (csrc/seg.cu) -------------------------------------------------------------------------
+EW_ADD, EW_RELU, EW_GELU, EW_GATE = 0, 1, 2, 3
+
+
+def small_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int, head_dim: int) -> torch.Tensor:
+    """softmax(q k^T / sqrt(hd)) v for bf16 [N, heads*hd] views (row strides free, unit inner stride), hd in {16, 32}."""
+    _req_cuda(q, k, v, out)
+    for t in (q, k, v, out):
+        assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.bfloat16 and t.shape[1] >= heads * head_dim
+    assert k.shape[0] == v.shape[0] and out.shape[0] == q.shape[0]
+    with _timed("crab_small_attn"):
+        _l.check(_l.load().crab_small_attn(_vp(q), _i(q.stride(0)), _vp(k), _i(k.stride(0)), _vp(v), _i(v.stride(0)), _vp(out),
+                                           _i(out.stride(0)), _i(q.shape[0]), _i(k.shape[0]), _i(heads), _i(head_dim),
+                                           C.c_float(head_dim ** -0.5), _stream()), "crab_small_attn")
+    count_launches(1)
+    return out
+
+
+def elementwise(a: torch.Tensor, op: int, b: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 [R, C]: EW_ADD (b is [R, C] or [1, C]), EW_RELU, EW_GELU, EW_GATE ((sigmoid(gate[r]) + 1) * a, gate fp32 [R])."""
+    _req_cuda(a, b, gate, out)
+    assert a.dim() == 2 and a.stride(1) == 1 and a.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty((a.shape[0], a.shape[1]), device=a.device, dtype=torch.bfloat16)
+    if b is not None:
+        assert b.dim() == 2 and b.stride(1) == 1 and b.dtype == torch.bfloat16 and b.shape[1] >= a.shape[1] and b.shape[0] in (1, a.shape[0])
+    if gate is not None:
+        assert gate.dtype == torch.float32 and gate.is_contiguous() and gate.numel() >= a.shape[0]
+    with _timed("crab_elementwise"):
+        _l.check(_l.load().crab_elementwise(_vp(a), _i(a.stride(0)), _vp(b), _i(b.stride(0) if b is not None else 0),
+                                            _i(b.shape[0] if b is not None else 0), _vp(gate), _vp(out), _i(out.stride(0)),
+                                            _i(a.shape[0]), _i(a.shape[1]), _i(op), _stream()), "crab_elementwise")
+    count_launches(1)
+    return out
+
+
+def row_mean_f32(x: torch.Tensor, cols: int) -> torch.Tensor:
+    _req_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32 and cols <= x.shape[1]
+    out = torch.empty((x.shape[0],), device=x.device, dtype=torch.float32)
+    with _timed("crab_row_mean_f32"):
+        _l.check(_l.load().crab_row_mean_f32(_vp(x), _i(x.stride(0)), _i(x.shape[0]), _i(cols), _vp(out), _stream()),
+                 "crab_row_mean_f32")
+    count_launches(1)
+    return out
+
+
+def im2col3x3(x: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """token-major bf16 [h*w, C] -> [h*w, 9*C] (columns (ky, kx, c), zero padding)."""
+    _req_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16 and x.shape[0] == h * w
+    c = x.shape[1]
+    out = torch.empty((h * w, 9 * c), device=x.device, dtype=torch.bfloat16)
+    with _timed("crab_im2col3x3"):
+        _l.check(_l.load().crab_im2col3x3(_vp(x), _i(x.stride(0)), _vp(out), _i(h), _i(w), _i(c), _stream()), "crab_im2col3x3")
+    count_launches(1)
+    return out
+
+
+def bilinear_f32(x: torch.Tensor, hin: int, win: int, hout: int, wout: int, channels: int, out: Optional[torch.Tensor] = None,
+                 alpha: float = 1.0, beta: float = 0.0, nchw_out: bool = False) -> torch.Tensor:
+    """token-major fp32 [hin*win, >=channels] -> [hout*wout, channels] (or [channels, hout, wout]); out = beta*out + alpha*interp."""
+    _req_cuda(x, out)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32 and x.shape[0] == hin * win and x.shape[1] >= channels
+    if out is None:
+        assert beta == 0.0
+        out = torch.empty((channels, hout, wout) if nchw_out else (hout * wout, channels), device=x.device, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    ldo = wout if nchw_out else out.shape[1]
+    with _timed("crab_bilinear_f32"):
+        _l.check(_l.load().crab_bilinear_f32(_vp(x), _i(x.stride(0)), _i(hin), _i(win), _vp(out), _i(ldo), _i(hout), _i(wout),
+                                             _i(channels), C.c_float(alpha), C.c_float(beta), _i(1 if nchw_out else 0), _stream()),
+                 "crab_bilinear_f32")
+    count_launches(1)
+    return out

@@ -243,6 +243,27 @@ int crab_normalize_u8(const void* images_hwc, float* out_nchw, int n_img, int H,
 int crab_resample_u8(const void* in_hwc, void* out_hwc, int n_img, int in_h, int in_w, int out_h, int out_w, int axis,
                      const int* bounds, const int* kk, int ksize, int out0, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Segmentation head helpers (SegModule / MaskDecoderMultiScale, models/multimodal_encoder.py:268-543,
+ * 891-1445).  Feature maps are token-major (one row per pixel); convolutions and MLPs go through crab_gemm_bf16.
+ * crab_small_attn replaces: Attention.forward (:1368-1393) and nn.MultiheadAttention of the query generator: heads of 16 or
+ *           32 channels at column h * head_dim of q / k / v / o (bf16), softmax(q k^T * scale) v in fp32.
+ * crab_elementwise: op 0 out = a + b (b_rows 1 = row broadcast), 1 ReLU, 2 GELU (erf), 3 (sigmoid(gate[r]) + 1) * a
+ *           (predict_masks :1110-1112); bf16 in / out.
+ * crab_row_mean_f32: mean over the first `cols` fp32 columns of every row (class mean of the previous masks).
+ * crab_im2col3x3: bf16 [h*w, C] -> [h*w, 9*C], columns (ky, kx, c), zero padding (image_feature_neck's 3x3 conv).
+ * crab_bilinear_f32: F.interpolate(mode="bilinear", align_corners=False) on token-major fp32 maps;
+ *           out = beta * out + alpha * interp; nchw_out = 1 writes [C, hout, wout] (the final masks).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int crab_small_attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int Nq, int Nk,
+                    int heads, int head_dim, float scale, void* stream);
+int crab_elementwise(const void* a, int lda, const void* b, int ldb, int b_rows, const float* gate, void* out, int ldo, int rows,
+                     int cols, int op, void* stream);
+int crab_row_mean_f32(const float* x, int ldx, int rows, int cols, float* out, void* stream);
+int crab_im2col3x3(const void* in, int ldi, void* out, int h, int w, int C, void* stream);
+int crab_bilinear_f32(const float* in, int ldi, int hin, int win, float* out, int ldo, int hout, int wout, int C, float alpha,
+                      float beta, int nchw_out, void* stream);
+
 /* Diagnostic (not on the product path): pure HBM->smem ring streaming, used by tools/ to size the decode pipelines. */
 int crab_debug_stream(const void* src, int64_t bytes, int chunk_bytes, int stages, int ctas, void* sink, void* stream);
 
