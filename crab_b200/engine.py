@@ -163,12 +163,19 @@ class CrabEngine:
         self.decode_packed = decode_packed
         sd = {(k[len("base_model.model."):] if k.startswith("base_model.model.") else k): v for k, v in sd.items()}
         self._pack_decoder(sd)
+        self.seg = None
+        if "model.seg_module.no_mask_embed.weight" in sd:   # segmentation branch present: the mask head (crab_b200/seg.py)
+            from .seg import SegHead
+
+            self.seg = SegHead(sd, self.dev, prefix="model.seg_module", grid=cfg.clip.image // cfg.clip.patch)
         self.has_encoders = load_encoders and ("model.vl_projector.visual_ln.weight" in sd)
         if self.has_encoders:
             self._pack_clip(sd)
             self._pack_beats(sd)
             self._pack_bridges(sd)
         self._bufs: Dict[Tuple, torch.Tensor] = {}
+        self._tap_layers: Tuple[int, ...] = ()   # CLIP layers whose patch tokens prepare_inputs(want_image_taps=True) keeps
+        self._last_taps: Dict[int, torch.Tensor] = {}
         # Programmatic dependent launch over the decode chain: (mask for the chain, mask for the kernel that follows the
         # decode attention).  Env CRAB_PDL_PLAN="chain,after_attn" overrides; see profiles/r02_pdl_plans.txt for the A/B.
         plan = os.environ.get("CRAB_PDL_PLAN", DEFAULT_PDL_PLAN).split(",")
@@ -408,7 +415,8 @@ class CrabEngine:
         o = self._buf("clip_o", (M, D))
         m = self._buf("clip_m", (M, c.inter))
         hd = D // c.heads
-        for L in self.clip_layers:
+        self._last_taps = {}
+        for li, L in enumerate(self.clip_layers):
             ops.layernorm(x, *L["ln1"], c.eps, out=h)
             ops.gemm(h, L["qkv"].w, bias=L["qkv"].b, out=qkv)
             ops.flash_attn(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B=n, H=c.heads, KVH=c.heads, Sq=tokens, Sk=tokens,
@@ -418,6 +426,10 @@ class CrabEngine:
             ops.layernorm(x, *L["ln2"], c.eps, out=h)
             ops.gemm(h, L["fc1"].w, bias=L["fc1"].b, act=ops.ACT_QUICK_GELU, out=m)
             ops.gemm(m, L["fc2"].w, bias=L["fc2"].b, residual=x, out=x)
+            if (li + 1) in self._tap_layers:
+                # hidden_states[li + 1] without the CLS row: the multi-scale image features the segmentation head reads
+                # (VisualEncoder.feature_select, models/multimodal_encoder.py:52-65; unified_arch.py:245-247)
+                self._last_taps[li + 1] = x.view(n, tokens, D)[:, 1:].reshape(n * (tokens - 1), D).clone()
         return x
 
     def _qformer(self, W: _QformerWeights, query: torch.Tensor, enc: torch.Tensor, n: int, enc_tokens: int,
@@ -511,7 +523,8 @@ class CrabEngine:
         return ops.gemm(h, self.a_proj[1].w, bias=self.a_proj[1].b)
 
     # ---- prepare_multimodal_inputs -----------------------------------------------------------------------------
-    def prepare_inputs(self, batch_input_ids: Sequence[torch.Tensor], batch_X_modals: Sequence[dict]):
+    def prepare_inputs(self, batch_input_ids: Sequence[torch.Tensor], batch_X_modals: Sequence[dict],
+                       want_image_taps: Sequence[int] = ()):
         """Splice modality embeddings at the placeholder ids, left-pad with pad-token embeddings
         (models/unified_arch.py:262-373).  The index bookkeeping runs on the host over the (host) token ids; the data
         movement is two gathers on the device.  Encoders run batched across samples (the reference runs them one
@@ -537,7 +550,7 @@ class CrabEngine:
                         plan.append(("aud", len(aud_items), X.shape[0] * nq))
                         aud_items.append(X)
                     else:
-                        plan.append(("vis", len(vis_items), X.shape[0] * nq))
+                        plan.append(("vis", len(vis_items), X.shape[0] * nq, key))
                         vis_items.append(X)
                     pre = i + 1
             plan.append(("text", t[pre:]))
@@ -545,8 +558,18 @@ class CrabEngine:
         lens = [sum((len(p[1]) if p[0] == "text" else p[2]) for p in plan) for plan in plans]
         S = max(lens)
         # encoders, batched by input shape
-        vis_out = self._encode_grouped(vis_items, self.encode_video)
+        self._tap_layers, self._item_taps = tuple(want_image_taps), {}
+        try:
+            vis_out = self._encode_grouped(vis_items, self.encode_video)
+        finally:
+            self._tap_layers = ()
         aud_out = self._encode_grouped(aud_items, self.encode_audio)
+        # per sample: the taps of its first '<image>' item (generate_avs reads one image per sample, unified_arch.py:243-247)
+        self.image_taps = []
+        if want_image_taps:
+            for plan in plans:
+                first = next((p[1] for p in plan if p[0] == "vis" and p[3] == "<image>"), None)
+                self.image_taps.append(None if first is None else self._item_taps[first])
         embeds = torch.empty((B * S, D), device=self.dev, dtype=torch.bfloat16)
         txt_src, txt_dst = [], []
         mask = torch.zeros((B, S), dtype=torch.int32)
@@ -590,6 +613,13 @@ class CrabEngine:
                 nrows = items[i].shape[0] * nq
                 out[i] = y[r:r + nrows]
                 r += nrows
+            if self._tap_layers and fn == self.encode_video:
+                per = self._last_taps[self._tap_layers[0]].shape[0] // xs.shape[0]   # patch tokens per frame
+                f0 = 0
+                for i in idxs:
+                    nf = items[i].shape[0]
+                    self._item_taps[i] = [self._last_taps[k][f0 * per:(f0 + nf) * per] for k in self._tap_layers]
+                    f0 += nf
         return out  # type: ignore
 
     # ---- decoder -----------------------------------------------------------------------------------------------
@@ -714,6 +744,12 @@ class CrabEngine:
         last = self._buf("last_x", (B, D))
         rows = (torch.arange(B, device=self.dev) * S + (S - 1))
         ops.gather_rows(x, last, B, D, src_rows=rows)
+        t = getattr(self, "_tail_rows", 0)
+        if t:  # final-normed hidden states of the last t prompt positions (HF hidden_states[0][-1][:, -t:])
+            trows = (torch.arange(B, device=self.dev).view(B, 1) * S + torch.arange(S - t, S, device=self.dev).view(1, t)).reshape(-1)
+            tail = torch.empty((B * t, D), device=self.dev, dtype=torch.bfloat16)
+            ops.gather_rows(x, tail, B * t, D, src_rows=trows.contiguous())
+            self.hidden_prefill_tail = ops.rmsnorm(tail, self.final_norm, self.cfg.decoder.eps).view(B, t, D)
         self.logits = self._buf("logits", (B, self.vocab_pad), torch.float32)
         self.next_ids = self._buf("next_ids", (B,), torch.int64)
         self._head(last, self.logits, self.next_ids)
@@ -780,16 +816,23 @@ class CrabEngine:
 
     @torch.no_grad()
     def generate_from_embeds(self, inputs_embeds: torch.Tensor, max_new_tokens: int, use_graph: bool = True,
-                             return_logits: bool = False, teacher_tokens: Optional[torch.Tensor] = None):
-        """Greedy loop (EOS handling is the caller's: fixed-length).  Returns ids [B, n] (int64, device)."""
-        B = inputs_embeds.shape[0]
+                             return_logits: bool = False, teacher_tokens: Optional[torch.Tensor] = None,
+                             capture_hidden: int = 0):
+        """Greedy loop (EOS handling is the caller's: fixed-length).  Returns ids [B, n] (int64, device).
+        capture_hidden = t > 0 additionally records what HF's `output_hidden_states` exposes of the LAST layer (after the final
+        norm): `self.hidden_prefill_tail` [B, min(t, S), D] (the last positions of the prompt pass) and `self.hidden_steps`
+        [n - 1, B, D] (one row per decode step) — the inputs of generate_avs' mask-token pairing (unified_llama.py:335-345)."""
+        B, S = inputs_embeds.shape[0], inputs_embeds.shape[1]
         assert inputs_embeds.shape[1] + max_new_tokens <= self.cfg.max_ctx, "raise CrabConfig.max_ctx"
+        self._tail_rows = min(int(capture_hidden), S) if capture_hidden else 0
         logits, nxt = self.prefill(inputs_embeds)
+        self._tail_rows = 0
         out = torch.empty((B, max_new_tokens), device=self.dev, dtype=torch.int64)
         out[:, 0].copy_(nxt)
         all_logits = [logits.clone()] if return_logits else None
+        steps_h = []
         if max_new_tokens > 1:
-            self.begin_decode(B, use_graph)
+            self.begin_decode(B, use_graph and self.dev.type == "cuda")
         for step in range(1, max_new_tokens):
             if teacher_tokens is not None:
                 self.next_ids.copy_(teacher_tokens[:, step - 1])
@@ -797,6 +840,11 @@ class CrabEngine:
             out[:, step].copy_(nxt)
             if return_logits:
                 all_logits.append(logits.clone())
+            if capture_hidden:
+                steps_h.append(self._buf("head_hn", (B, self.cfg.decoder.hidden)).clone())
+        if capture_hidden:
+            D = self.cfg.decoder.hidden
+            self.hidden_steps = torch.stack(steps_h, 0) if steps_h else torch.empty((0, B, D), device=self.dev, dtype=torch.bfloat16)
         return (out, torch.stack(all_logits, 0)) if return_logits else out
 
     @torch.no_grad()

@@ -183,6 +183,77 @@ def full_manifest(cfg: CrabConfig, d_model: Optional[int] = None, lora: bool = T
     return m
 
 
+def seg_manifest(d_model: int, prompt_dim: int = 256, vit_dim: int = 1024, scales: int = 2, depth: int = 2, queries: int = 300,
+                 query_layers: int = 2, mlp_dim: int = 2048) -> Dict[str, Tuple[int, ...]]:
+    """Parameter / buffer names and shapes of the reference `SegModule` (models/multimodal_encoder.py:268-353; mask decoder
+    :891-963, two-way transformer :1163-1299, query generator :1396-1439), i.e. the `seg_module.*` keys of a checkpoint."""
+    E, m = prompt_dim, {}
+
+    def lin(name, o, i, bias=True):
+        m[name + ".weight"] = (o, i)
+        if bias:
+            m[name + ".bias"] = (o,)
+
+    def norm(name, c=E):
+        m[name + ".weight"], m[name + ".bias"] = (c,), (c,)
+
+    lin("text_hidden_fcs.0.0", d_model, d_model)
+    lin("text_hidden_fcs.0.2", E, d_model)
+    m["no_mask_embed.weight"] = (1, E)
+    m["image_feature_neck.0.weight"] = (E, vit_dim, 1, 1)
+    norm("image_feature_neck.1")
+    m["image_feature_neck.2.weight"] = (E, E, 3, 3)
+    norm("image_feature_neck.3")
+    m["pe_layer.positional_encoding_gaussian_matrix"] = (2, E // 2)
+    md = "mask_decoder."
+    for l in range(scales):
+        tp = f"{md}transformer.{l}."
+
+        def attn(name, internal):
+            for pj in ("q_proj", "k_proj", "v_proj"):
+                lin(f"{name}.{pj}", internal, E)
+            lin(f"{name}.out_proj", E, internal)
+
+        for i in range(depth):
+            lp = f"{tp}layers.{i}."
+            attn(lp + "self_attn", E)
+            norm(lp + "norm1")
+            attn(lp + "cross_attn_token_to_image", E // 2)
+            norm(lp + "norm2")
+            lin(lp + "mlp.lin1", mlp_dim, E)
+            lin(lp + "mlp.lin2", E, mlp_dim)
+            norm(lp + "norm3")
+            norm(lp + "norm4")
+            attn(lp + "cross_attn_image_to_token", E // 2)
+        attn(tp + "final_attn_token_to_image", E // 2)
+        norm(tp + "norm_final_attn")
+    m[md + "avs_query_tokens.weight"] = (queries, E)
+    for i in range(query_layers):
+        qp = f"{md}query_generator.layers.{i}."
+        for a in ("self_attn", "cross_attn"):
+            m[qp + a + ".in_proj_weight"], m[qp + a + ".in_proj_bias"] = (3 * E, E), (3 * E,)
+            lin(qp + a + ".out_proj", E, E)
+        lin(qp + "ffn.0", mlp_dim, E)
+        lin(qp + "ffn.2", E, mlp_dim)
+        for n_ in ("norm1", "norm2", "norm3"):
+            norm(qp + n_)
+    dims = [queries, E, E, E // 8]
+    for i in range(3):
+        m[f"{md}hyper_mlp_out.layers.{i}.weight"], m[f"{md}hyper_mlp_out.layers.{i}.bias"] = (dims[i + 1], dims[i], 1, 1), (dims[i + 1],)
+    dims = [E, E, E, E // 8]
+    for i in range(3):
+        lin(f"{md}hyper_mlp.layers.{i}", dims[i + 1], dims[i])
+    m[md + "output_upscaling.0.weight"], m[md + "output_upscaling.0.bias"] = (E, E // 8, 2, 2), (E // 8,)
+    norm(md + "output_upscaling.1", E // 8)
+    m[md + "upsample_2x.0.weight"], m[md + "upsample_2x.0.bias"] = (E, E, 2, 2), (E,)
+    norm(md + "upsample_2x.1")
+    m[md + "pe1.positional_encoding_gaussian_matrix"] = (2, E // 2)
+    m[md + "level_embed.weight"] = (scales, E)
+    m[md + "ms3_s4_classfier.weight"] = (1, E // 8, 1, 1)
+    m[md + "avss_classifier.weight"] = (71, E // 8, 1, 1)
+    return m
+
+
 def special_token_ids(base_vocab: int, mask_token_nums: int = 6) -> Dict[str, int]:
     names = _IMAGE_TOKENS + _VIDEO_TOKENS + _AUDIO_TOKENS + _MASK_TOKENS + [f"<mask_{i}>" for i in range(mask_token_nums)]
     return {t: base_vocab + i for i, t in enumerate(names)}
@@ -284,8 +355,18 @@ class UnifiedMetaModel:
         """Same keyword surface as the reference (models/unified_arch.py:31-61).  `qformer_config` is an extra,
         optional knob: the reference reads bert-base-uncased's config from a hard-coded path
         (models/multimodal_encoder.py:90,192); the defaults here are those values."""
-        if segment_branch or use_vqgan:
-            raise NotImplementedError("crab_b200 accelerates the text-generation path; SegModule / VQGAN are out of scope")
+        if use_vqgan:
+            raise NotImplementedError("the VQGAN mask tokeniser is out of scope for the B200 path")
+        if segment_branch:
+            # parameter container with the reference SegModule's names; the arithmetic is crab_b200.seg.SegHead
+            assert (image_scale_nums, token_nums_per_scale, prompt_embed_dim) == (2, 3, 256), \
+                "the B200 segmentation head is built for the reference's shipped geometry (2 scales x 3 tokens, 256-d prompts)"
+            self.low_res_mask_size = low_res_mask_size
+            self.seg_module = ParamTree(seg_manifest(d_model, prompt_embed_dim, vit_image_embedding_dim, image_scale_nums,
+                                                     mask_decoder_transformer_depth, avs_query_num, query_generator_num_layers))
+            for n_, p_ in self.seg_module.named_parameters():   # the two PositionEmbeddingRandom buffers are random in the reference
+                if n_.endswith("positional_encoding_gaussian_matrix"):
+                    nn.init.normal_(p_)
         q = qformer_config or QformerConfig()
         self.qformer_cfg = q
         self.select_layer_list = list(select_layer_list)
@@ -353,10 +434,9 @@ class UnifiedMetaForCausalLM:
 
     def prepare_multimodal_inputs(self, batch_input_ids, batch_labels, batch_X_modals, batch_task_names=None,
                                   return_multi_scale_features=False, return_gt_mask=False):
-        if return_multi_scale_features or return_gt_mask:
-            raise NotImplementedError("segmentation inputs are out of scope for the B200 path")
         eng = self.engine()
-        embeds, mask, pos = eng.prepare_inputs(batch_input_ids, batch_X_modals)
+        taps = tuple(eng.cfg.select_layers[:2]) if return_multi_scale_features else ()
+        embeds, mask, pos = eng.prepare_inputs(batch_input_ids, batch_X_modals, want_image_taps=taps)
         labels = None
         if batch_labels is not None:
             S = embeds.shape[1]
@@ -378,8 +458,21 @@ class UnifiedMetaForCausalLM:
                         pos_out += (X.shape[0] if X.dim() > 2 else 1) * nq
                 rows.append(full)
             labels = torch.stack(rows).to(eng.dev)
-        return {"input_ids": None, "inputs_embeds": embeds, "attention_mask": mask.to(eng.dev), "labels": labels,
-                "position_ids": pos.to(eng.dev)}
+        out = {"input_ids": None, "inputs_embeds": embeds, "attention_mask": mask.to(eng.dev), "labels": labels,
+               "position_ids": pos.to(eng.dev)}
+        if return_multi_scale_features:
+            # [(bs, 256, 1024)] * scales: ViT taps of every sample's '<image>' (zeros for samples without one, unified_arch.py:233-238)
+            tok, dim = (eng.cfg.clip.image // eng.cfg.clip.patch) ** 2, eng.cfg.clip.hidden
+            feats = []
+            for sidx in range(len(taps)):
+                rows = [t[sidx][:tok] if t is not None else torch.zeros((tok, dim), device=eng.dev, dtype=torch.bfloat16)
+                        for t in eng.image_taps]
+                feats.append(torch.stack(rows, 0))
+            out["multi_scale_image_features"] = feats
+        if return_gt_mask:
+            gts = [X.get("<mask>") for X in batch_X_modals]
+            out["gt_mask"] = torch.stack([g.to(eng.dev) for g in gts], 0) if all(g is not None for g in gts) else None
+        return out
 
 
 def build_crab_config(decoder: DecoderConfig, model, max_ctx: int) -> CrabConfig:

@@ -27,6 +27,30 @@ from ..engine import CrabEngine, DecoderConfig
 from .unified_arch import UnifiedMetaForCausalLM, UnifiedMetaModel, build_crab_config
 
 
+def select_pred_embeddings(output_ids, mask_token_ids, prefill_tail: torch.Tensor, step_hidden: torch.Tensor):
+    """The reference's pairing of generated tokens and hidden states (models/unified_llama.py:331-351): entry t of
+    `output_hidden_states` (t = 0: the prompt pass, (S, D); t >= 1: one row) is kept when generated token t + 1 is a `<mask_i>`
+    token; the kept rows are concatenated, more than six -> the last six, fewer than six -> no segmentation (returns None).
+    `prefill_tail` holds the last <= 6 rows of the prompt pass (all that can survive the last-six rule), `step_hidden[t - 1]` the
+    row of step t.  Returns a (6, D) tensor or None."""
+    n = len(output_ids)
+    rows, count = [], 0
+    for t in range(n - 1):                       # zip(mask_list over output_ids[1:], hidden_states) stops at n - 1 entries
+        if output_ids[t + 1] in mask_token_ids:
+            if t == 0:
+                rows.append(prefill_tail)        # stands for all S rows of the prompt pass: only its tail can reach the last six
+                count += 10 ** 6                 # "at least six more rows than needed"
+            else:
+                rows.append(step_hidden[t - 1].unsqueeze(0))
+                count += 1
+    if count < 6:
+        return None
+    allrows = torch.cat(rows, 0)
+    if allrows.shape[0] < 6:
+        raise RuntimeError("prompt shorter than six positions: cannot apply the reference's last-six rule")
+    return allrows[-6:]
+
+
 class UnifiedConfig(LlamaConfig):
     model_type = "unified_llm"
 
@@ -285,8 +309,32 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
             steps = hist.index(False) + 1
         return out[:, :steps]
 
-    def generate_avs(self, *a, **k):
-        raise NotImplementedError("generate_avs / SegModule are out of scope for the B200 path (SURVEY.md §8f)")
+    @torch.no_grad()
+    def generate_avs(self, batch_input_ids=None, batch_labels=None, batch_X_modals=None, batch_task_names=None, *,
+                     max_new_tokens: Optional[int] = None, forced_output_ids: Optional[torch.Tensor] = None, **kwargs):
+        """Mirror of the reference's `generate_avs` (models/unified_llama.py:270-361), one sample per call as there
+        (`mask_list = ...tolist()[0]  # bs == 1`): greedy generation with the last layer's hidden states kept, the hidden states
+        paired with the generated `<mask_i>` tokens -> `pred_embeddings`, then `postprocess_seg` (the segmentation head) with the
+        ViT taps of the sample's image.  Returns {'output_ids': (1, n)} plus 'pred_masks': [(num_classes, 224, 224)] when six mask
+        embeddings were produced.  `forced_output_ids` (1, n) teacher-forces the generated sequence (tests)."""
+        eng = self.engine()
+        if eng.seg is None:
+            raise RuntimeError("generate_avs needs the segmentation branch: init_multimodal_modules(segment_branch=True) and its weights")
+        assert len(batch_input_ids) == 1, "generate_avs handles one sample per call, as the reference does"
+        inputs = self.prepare_multimodal_inputs(batch_input_ids, batch_labels, batch_X_modals, batch_task_names,
+                                                return_multi_scale_features=True, return_gt_mask=False)
+        n = max_new_tokens or self.generation_config.max_new_tokens
+        ids = eng.generate_from_embeds(inputs["inputs_embeds"], n, capture_hidden=6,
+                                       teacher_tokens=None if forced_output_ids is None else forced_output_ids.to(eng.dev))
+        output_ids = ids if forced_output_ids is None else forced_output_ids.to(eng.dev)
+        result = {"output_ids": output_ids}
+        mask_ids = [self.SPECIAL_TOKEN_2_IDS[f"<mask_{i}>"] for i in range(6)]
+        pred = select_pred_embeddings(output_ids[0].tolist(), mask_ids, eng.hidden_prefill_tail[0], eng.hidden_steps[:, 0])
+        if pred is None:
+            return result
+        masks = eng.seg.forward(pred.unsqueeze(0).contiguous(), inputs["multi_scale_image_features"], list(batch_task_names))
+        result["pred_masks"] = masks
+        return result
 
     def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
         """Kept for peft_hyper.PeftModelForCausalLM, which wraps this attribute (peft_model.py:518-520)."""

@@ -208,3 +208,46 @@ def seg_module_forward(sd: SD, pred_embeddings: torch.Tensor, multi_scale_feats:
         mask = F.interpolate(low.float(), (image_size, image_size), mode="bilinear", align_corners=False).to(low)
         out.append(mask[0])
     return out
+
+
+# ---- generate_avs: the LLM half (models/unified_llama.py:270-361) on top of oracle/crab_oracle.py ----------------------------
+def generate_avs(sd: SD, input_ids: torch.Tensor, X_modals: dict, cfg, max_new_tokens: int, task: str,
+                 forced_output_ids: torch.Tensor = None, grid: int = 16):
+    """One sample, as the reference (`bs == 1`): prepare inputs with the ViT taps of the '<image>' (select_layers[0], [1];
+    models/unified_arch.py:243-247), greedy generation keeping the last layer's final-normed hidden states of every forward
+    pass (HF `output_hidden_states`), pair entry t with generated token t + 1 being a `<mask_i>` token (:331-340), keep the last
+    six rows (:346-348), run the segmentation head.  `forced_output_ids` (n,) teacher-forces the generated sequence.
+    Returns dict(output_ids, pred_embeddings, pred_masks)."""
+    from oracle import crab_oracle as O
+
+    prep = O.prepare_multimodal_inputs(sd, [input_ids], [X_modals], cfg)
+    taps = O.visual_encoder(sd, X_modals["<image>"].unsqueeze(0), cfg.clip, cfg.select_layers)
+    feats = [taps[0][:, : grid * grid], taps[1][:, : grid * grid]]
+    emb = prep["inputs_embeds"].to(sd["model.embed_tokens.weight"].dtype)
+    h, cache = O.decoder_forward(sd, emb, cfg.decoder)
+    hidden = [h]                                            # hidden_states[0][-1]: (1, S, D)
+    ids = []
+    logits = O.lm_head(sd, h[:, -1])
+    for step in range(max_new_tokens):
+        nxt = logits.argmax(-1) if forced_output_ids is None else forced_output_ids[step:step + 1]
+        ids.append(nxt)
+        if step + 1 == max_new_tokens:
+            break
+        h, cache = O.decoder_forward(sd, sd["model.embed_tokens.weight"][nxt].unsqueeze(1), cfg.decoder, cache)
+        hidden.append(h)                                    # (1, 1, D)
+        logits = O.lm_head(sd, h[:, -1])
+    output_ids = torch.stack(ids, 1)                        # (1, n)
+    mask_ids = [cfg.special_ids[f"<mask_{i}>"] for i in range(6)]
+    flags = [int(t) in mask_ids for t in output_ids[0, 1:].tolist()]
+    pred = [hs for f, hs in zip(flags, hidden) if f]
+    res = {"output_ids": output_ids, "pred_embeddings": None, "pred_masks": None}
+    if not pred:
+        return res
+    pred = torch.cat(pred, dim=1)
+    if pred.shape[1] > 6:
+        pred = pred[:, -6:]
+    elif pred.shape[1] < 6:
+        return res
+    res["pred_embeddings"] = pred
+    res["pred_masks"] = seg_module_forward(sd, pred, feats, [task], p="model.seg_module", grid=grid)
+    return res

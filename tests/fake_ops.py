@@ -137,3 +137,241 @@ def bilinear_f32(x, hin, win, hout, wout, channels, out=None, alpha=1.0, beta=0.
         return alpha * res
     out.copy_(beta * out + alpha * res)
     return out
+
+
+# ======================================================================================================================
+# The rest of the library, for running the whole engine (crab_b200/engine.py) on the CPU in plumbing tests
+# ======================================================================================================================
+ACT_SWIGLU, ACT_LORA_Z = 3, 4
+BF16, F32 = 0, 1
+MIN_K = 64          # the seg-head path keeps every GEMM at >= one k-block; engine tests lower this to 8
+_launches = 0
+
+
+def init(dev=0):
+    pass
+
+
+def set_pdl(mask):
+    pass
+
+
+def set_gemm_2cta(mode):
+    pass
+
+
+def launch_count():
+    return _launches
+
+
+def count_launches(n):
+    global _launches
+    _launches += n
+
+
+def _bfr(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _lora_z(y, scale):
+    M, N = y.shape
+    g = N // 11
+    t = y.view(M, g, 11)
+    r = torch.softmax(t[..., :3], -1)
+    return (scale * r.unsqueeze(-1) * t[..., 3:].unsqueeze(-2)).reshape(M, g * 24)
+
+
+def _swiglu_packed(y, scale=1.0):
+    M, N = y.shape
+    t = y.view(M, N // 128, 2, 64)
+    return (torch.nn.functional.silu(t[:, :, 0]) * t[:, :, 1] * scale).reshape(M, N // 2)
+
+
+_gemm_plain = gemm
+
+
+def gemm(a, w, *, bias=None, residual=None, res_scale=1.0, out_scale=1.0, act=ACT_NONE, out=None, out_dtype=torch.bfloat16,
+         block_n=0, max_ctas=0, k=None, n=None):  # noqa: F811  (extends the plain version with the engine's epilogues)
+    if act not in (ACT_SWIGLU, ACT_LORA_Z):
+        global MIN_K
+        if MIN_K != 64:   # engine mode: small K allowed
+            K = k if k is not None else a.shape[1]
+            N = n if n is not None else w.shape[0]
+            y = a[:, :K].float() @ w[:N, :K].float().t()
+            if bias is not None:
+                y = y + bias[:N]
+            if act == ACT_GELU:
+                y = torch.nn.functional.gelu(y)
+            elif act == ACT_QUICK_GELU:
+                y = y * torch.sigmoid(1.702 * y)
+            y = y * out_scale
+            if residual is not None:
+                y = y + res_scale * residual[:, :N].float()
+            if out is None:
+                out = torch.empty((a.shape[0], N), dtype=out_dtype)
+            assert N % 8 == 0 and a.stride(0) % 8 == 0 and w.stride(0) % 8 == 0 and _al16(a) and _al16(w) and _al16(out)
+            out[:, :N] = y.to(out.dtype)
+            return out
+        return _gemm_plain(a, w, bias=bias, residual=residual, res_scale=res_scale, out_scale=out_scale, act=act, out=out,
+                           out_dtype=out_dtype, block_n=block_n, max_ctas=max_ctas, k=k, n=n)
+    K = k if k is not None else a.shape[1]
+    N = n if n is not None else w.shape[0]
+    assert bias is None and residual is None and a.stride(0) % 8 == 0 and w.stride(0) % 8 == 0 and _al16(a) and _al16(w)
+    y = a[:, :K].float() @ w[:N, :K].float().t()
+    res = _lora_z(y, out_scale) if act == ACT_LORA_Z else _swiglu_packed(y, out_scale)
+    if out is None:
+        out = torch.empty((a.shape[0], res.shape[1]), dtype=torch.bfloat16)
+    out[:, : res.shape[1]] = res.to(torch.bfloat16)
+    return out
+
+
+def rmsnorm(x, gamma, eps, out=None):
+    xf = x.float()
+    y = _bfr(gamma * _bfr(xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps))).to(torch.bfloat16)
+    if out is None:
+        return y
+    out.copy_(y)
+    return out
+
+
+def rope_table(max_pos, head_dim, theta, device):
+    half = head_dim // 2
+    inv = (1.0 / (theta ** (torch.arange(0, half, dtype=torch.float64) * 2 / head_dim))).float()
+    ang = torch.arange(max_pos, dtype=torch.float32).unsqueeze(1) * inv.unsqueeze(0)
+    return torch.cat([torch.cos(ang.double()).float(), torch.sin(ang.double()).float()], 1)
+
+
+def _rope(x, cs, hd):
+    """x (..., hd) float, cs (hd,) = [cos | sin] for one position."""
+    half = hd // 2
+    c, s = cs[:half], cs[half:]
+    lo, hi = x[..., :half], x[..., half:]
+    return torch.cat([lo * c - hi * s, hi * c + lo * s], -1)
+
+
+def rope_kv_append(qkv, cos_sin, k_cache, v_cache, B, S, H, KVH, head_dim, past=0, past_dev=None):
+    p0 = int(past_dev[0]) if past_dev is not None else past
+    hd = head_dim
+    for b in range(B):
+        for s_ in range(S):
+            row = qkv[b * S + s_]
+            cs = cos_sin[p0 + s_]
+            q = row[: H * hd].float().view(H, hd)
+            k = row[H * hd:(H + KVH) * hd].float().view(KVH, hd)
+            v = row[(H + KVH) * hd:(H + 2 * KVH) * hd].view(KVH, hd)
+            row[: H * hd] = _rope(q, cs, hd).reshape(-1).to(torch.bfloat16)
+            k_cache[b, :, p0 + s_] = _rope(k, cs, hd).to(torch.bfloat16)
+            v_cache[b, :, p0 + s_] = v
+
+
+def flash_attn(q, k, v, out, *, B, H, KVH, Sq, Sk, head_dim, q_strides, k_strides, v_strides, o_strides, scale, causal=False,
+               gate=None, bias_table=None, sk_dev=None):
+    if sk_dev is not None:
+        Sk = int(sk_dev[0])
+    hd = head_dim
+
+    def view(t, n_heads, S, st):
+        return torch.as_strided(t, (B, n_heads, S, hd), (st[0], st[2], st[1], 1), t.storage_offset())
+
+    qf, kf, vf = view(q, H, Sq, q_strides).float(), view(k, KVH, Sk, k_strides).float(), view(v, KVH, Sk, v_strides).float()
+    if KVH != H:
+        kf, vf = kf.repeat_interleave(H // KVH, 1), vf.repeat_interleave(H // KVH, 1)
+    s = qf @ kf.transpose(-1, -2) * scale
+    if bias_table is not None:
+        s = s + gate.unsqueeze(-1) * bias_table.unsqueeze(0)
+    if causal:
+        s = s + torch.full((Sq, Sk), float("-inf")).triu(diagonal=Sk - Sq + 1)
+    o = torch.softmax(s, -1) @ vf
+    view(out, H, Sq, o_strides).copy_(o.to(torch.bfloat16))
+    return out
+
+
+def _lora_rows(src, ra, groups, scale):
+    t = src.float() @ ra[: groups * 11].float().t()
+    return _lora_z(t, scale)
+
+
+def row_norm_loraz(x, *, gamma=None, eps=0.0, y=None, ra=None, groups=0, z=None, scale=1.0):
+    src = x
+    if gamma is not None:
+        y.copy_(rmsnorm(x, gamma, eps))
+        src = y
+    if groups:
+        z[:, : groups * 24] = _lora_rows(src, ra, groups, scale).to(torch.bfloat16)
+
+
+def attn_decode_fused(qkv, rope, k_cache, v_cache, out, *, B, H, KVH, head_dim, scale, past_dev, nsplit=1, workspace=None,
+                      ra=None, z=None, lora_scale=0.0, lora_ws=None, lora_counters=None):
+    hd, past = head_dim, int(past_dev[0])
+    G = H // KVH
+    for b in range(B):
+        row = qkv[b]
+        cs = rope[past]
+        q = _bfr(_rope(row[: H * hd].float().view(H, hd), cs, hd))
+        k_cache[b, :, past] = _rope(row[H * hd:(H + KVH) * hd].float().view(KVH, hd), cs, hd).to(torch.bfloat16)
+        v_cache[b, :, past] = row[(H + KVH) * hd:(H + 2 * KVH) * hd].view(KVH, hd)
+        kk = k_cache[b, :, : past + 1].float().repeat_interleave(G, 0)
+        vv = v_cache[b, :, : past + 1].float().repeat_interleave(G, 0)
+        a = torch.softmax((q.unsqueeze(1) @ kk.transpose(-1, -2)) * scale, -1) @ vv      # (H, 1, hd)
+        out[b, : H * hd] = a.reshape(-1).to(torch.bfloat16)
+    if ra is not None:
+        assert nsplit == 1
+        z[:, :24] = _lora_rows(out[:, : H * hd], ra, 1, lora_scale).to(torch.bfloat16)
+    return out
+
+
+class PackedWeight:
+    def __init__(self, data, N, K, swiglu=False):
+        self.data, self.N, self.K, self.swiglu = data, N, K, swiglu
+
+
+def pack_skinny_weight(w, k=None, swiglu=False):
+    return PackedWeight(w, w.shape[0], k if k is not None else w.shape[1], swiglu)
+
+
+def gemm_skinny(x, w, *, bias=None, residual=None, act=ACT_NONE, out=None, out_dtype=torch.bfloat16, k=None, n=None, splits=0):
+    packed = isinstance(w, PackedWeight)
+    W = w.data if packed else w
+    K = w.K if packed else (k if k is not None else x.shape[1])
+    N = w.N if packed else (n if n is not None else W.shape[0])
+    assert x.shape[0] <= 32 and x.stride(0) % 8 == 0 and x.shape[1] >= K
+    y = x[:, :K].float() @ W[:N, :K].float().t()
+    if act == ACT_SWIGLU:
+        assert packed and w.swiglu and bias is None and residual is None
+        y = _swiglu_packed(y)
+    else:
+        if bias is not None:
+            y = y + bias[:N]
+        if residual is not None:
+            y = y + residual[:, : y.shape[1]].float()
+    if out is None:
+        out = torch.empty((x.shape[0], y.shape[1]), dtype=out_dtype)
+    out[:, : y.shape[1]] = y.to(out.dtype)
+    return out
+
+
+def argmax(logits, V, out=None):
+    r = logits[:, :V].argmax(-1)
+    if out is None:
+        return r
+    out.copy_(r)
+    return out
+
+
+def add_scalar_i32(p, v):
+    p += v
+
+
+def patchify(images, patch, ld_out):
+    n, c, h, w = images.shape
+    cols = torch.nn.functional.unfold(images, patch, stride=patch).transpose(1, 2).reshape(n * (h // patch) * (w // patch), c * patch * patch)
+    out = torch.zeros((cols.shape[0], ld_out), dtype=torch.bfloat16)
+    out[:, : cols.shape[1]] = cols.to(torch.bfloat16)
+    return out
+
+
+def clip_embed_ln(patch_emb, cls, pos, gamma, beta, n_img, tokens, D, eps):
+    x = torch.empty((n_img, tokens, D))
+    x[:, 0] = cls + pos[0]
+    x[:, 1:] = patch_emb.float().view(n_img, tokens - 1, D) + pos[1:]
+    return torch.nn.functional.layer_norm(x, (D,), gamma, beta, eps).reshape(n_img * tokens, D).to(torch.bfloat16)

@@ -93,3 +93,49 @@ def test_seg_head_vs_oracle(cuda_dev):
     # the binary masks the evaluation thresholds (mask > 0) agree with the reference's on all but the uncertain band
     agree = ((out[0].cpu() > 0) == (g["mask_s4"] > 0)).float().mean().item()
     assert agree > 0.99, agree
+
+
+def test_generate_avs_end_to_end_vs_oracle(cuda_dev):
+    """`UnifiedForCausalLM.generate_avs` on the GPU (ViT taps, hidden-state capture from prefill and the decode graph, the
+    reference's mask-token pairing, segmentation head) vs the oracle restatement of models/unified_llama.py:270-361, with the
+    generated sequence teacher-forced to contain the six mask tokens.  Same flow as tests/test_generate_avs_plumbing_cpu.py."""
+    from helpers import engine_cfg, load_golden
+
+    from crab_b200.engine import CrabEngine
+    from crab_b200.models import unified_arch
+    from crab_b200.models.unified_llama import UnifiedConfig, UnifiedForCausalLM
+
+    g, case, sd, ocfg, ids, X = load_golden("llama_small")
+    D = ocfg.decoder.hidden
+    sd = dict(sd)
+    sd.update(synth.synth_state_dict({"model.seg_module." + k: v for k, v in unified_arch.seg_manifest(D).items()}, 77))
+    grid = case["image_size"] // case["patch_size"]
+    eng = CrabEngine(sd, engine_cfg(case, ocfg), cuda_dev)
+    gi = torch.Generator().manual_seed(3)
+    image = torch.randn(1, 3, case["image_size"], case["image_size"], generator=gi)
+    prompt = torch.randint(3, ocfg.base_vocab, (12,), generator=gi)
+    prompt[4] = ocfg.special_ids["<image>"]
+    Xs = {"<image>": image}
+    d = ocfg.decoder
+    model = UnifiedForCausalLM.from_engine(UnifiedConfig(hidden_size=d.hidden, intermediate_size=d.inter, num_hidden_layers=d.layers,
+                                                         num_attention_heads=d.heads, num_key_value_heads=d.kv_heads,
+                                                         vocab_size=d.vocab), eng)
+    m = [ocfg.special_ids[f"<mask_{i}>"] for i in range(6)]
+    forced = torch.tensor([7, ocfg.special_ids["<mask_start>"]] + m + [ocfg.special_ids["<mask_end>"]])
+    with torch.no_grad():
+        ref = S.generate_avs(sd, prompt, Xs, ocfg, forced.numel(), "s4", forced_output_ids=forced, grid=grid)
+    res = model.generate_avs(batch_input_ids=[prompt], batch_labels=None, batch_X_modals=[Xs], batch_task_names=["s4"],
+                             max_new_tokens=forced.numel(), forced_output_ids=forced.view(1, -1))
+    torch.cuda.synchronize()
+    assert torch.equal(res["output_ids"].cpu(), forced.view(1, -1))
+    out = res["pred_masks"][0].cpu()
+    rel = ((out - ref["pred_masks"][0]).norm() / ref["pred_masks"][0].norm()).item()
+    print(f"generate_avs pred_masks rel_l2 vs oracle = {rel:.3e}")
+    assert tuple(out.shape) == (1, 224, 224) and rel < 8e-2, rel
+    # ViT taps are the reference's multi-scale features
+    with torch.no_grad():
+        from oracle import crab_oracle as O
+        taps = O.visual_encoder(sd, image.unsqueeze(0), ocfg.clip, ocfg.select_layers)
+    for k in range(2):
+        got = eng.image_taps[0][k].float().cpu()
+        assert ((got - taps[k][0]).norm() / taps[k][0].norm()).item() < 2e-2
