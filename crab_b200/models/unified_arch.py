@@ -9,8 +9,8 @@ whose names and shapes reproduce the reference state-dict layout (so `load_state
   UnifiedMetaModel.encode_video / encode_audio  <- models/unified_arch.py:113-155
   UnifiedMetaForCausalLM.prepare_multimodal_inputs   <- models/unified_arch.py:217-406 (generation branch)
   UnifiedMetaForCausalLM.initialize_MM_tokenizer     <- models/unified_arch.py:409-459
-The segmentation branch (SegModule / generate_avs) is out of scope for this path: requesting it
-raises NotImplementedError instead of silently degrading.
+The segmentation branch (`segment_branch=True`) creates the reference SegModule's parameter names; its
+arithmetic lives in crab_b200/seg.py.  The VQGAN mask tokeniser (`use_vqgan`) is not built and raises NotImplementedError.
 """
 from __future__ import annotations
 

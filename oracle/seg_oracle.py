@@ -1,7 +1,6 @@
 """TEST INFRASTRUCTURE — CPU restatement of the reference's segmentation head, the post-processing half of
 `UnifiedForCausalLM.generate_avs` (models/unified_llama.py:270-361 -> `postprocess_seg`, models/unified_arch.py:162-176).
-Only tests/ may import this; the product path (crab_b200/) never does.  The CUDA path for this row is round-2 work: this file
-and tests/golden/seg_small.pt are its oracle, written and pinned first as the build order asks.
+Only tests/ may import this; the product path (crab_b200/seg.py, engine.py) never does.
 
 Functional torch on a state dict with the reference's key names (`seg_module.*` of `UnifiedMetaModel`):
 
