@@ -7,7 +7,9 @@ import math
 
 import torch
 
-ACT_NONE, ACT_QUICK_GELU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU, ACT_SWIGLU, ACT_LORA_Z = 0, 1, 2, 3, 4
+BF16, F32 = 0, 1
+MIN_K = 64          # the seg-head path keeps every GEMM at >= one k-block; engine plumbing tests lower this to 8
 EW_ADD, EW_RELU, EW_GELU, EW_GATE = 0, 1, 2, 3
 calls = []
 
@@ -18,31 +20,38 @@ def _al16(t):
 
 def gemm(a, w, *, bias=None, residual=None, res_scale=1.0, out_scale=1.0, act=ACT_NONE, out=None, out_dtype=torch.bfloat16,
          block_n=0, max_ctas=0, k=None, n=None):
+    """crab_gemm_bf16: out = epilogue(a[M, K] @ w[N, K]^T) with the C entry point's argument checks."""
     assert a.dim() == 2 and w.dim() == 2 and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.stride(1) == 1 and w.stride(1) == 1
     M, K, N = a.shape[0], (k if k is not None else a.shape[1]), (n if n is not None else w.shape[0])
     assert w.shape[1] >= K and a.shape[1] >= K and M > 0 and N > 0 and K > 0
     assert a.stride(0) % 8 == 0 and w.stride(0) % 8 == 0 and a.stride(0) >= K and w.stride(0) >= K, "lda/ldb"
-    assert N % 8 == 0, f"N % 8 (N={N})"
-    assert K >= 64 and K % 8 == 0, f"keep K a multiple of 8 and at least one k-block on this path (K={K})"
-    if out is None:
-        out = torch.empty((M, N), dtype=out_dtype)
-    assert out.stride(1) == 1 and out.shape[0] == M and out.shape[1] >= N
-    assert out.stride(0) % (8 if out.dtype == torch.bfloat16 else 4) == 0, "ldc"
-    assert _al16(a) and _al16(w) and _al16(out), "16-byte alignment of A / B / C"
+    assert K >= MIN_K and K % 8 == 0, f"K={K}: this path keeps K a multiple of 8 and >= {MIN_K}"
+    assert _al16(a) and _al16(w), "16-byte alignment of A / B"
     y = a[:, :K].float() @ w[:N, :K].float().t()
-    if bias is not None:
-        assert bias.dtype == torch.float32 and bias.numel() >= N and _al16(bias)
-        y = y + bias[:N]
-    if act == ACT_GELU:
-        y = torch.nn.functional.gelu(y)
-    elif act == ACT_QUICK_GELU:
-        y = y * torch.sigmoid(1.702 * y)
-    y = y * out_scale
-    if residual is not None:
-        assert residual.dtype == torch.bfloat16 and residual.stride(1) == 1 and residual.stride(0) % 8 == 0 and _al16(residual)
-        y = y + res_scale * residual[:, :N].float()
-    out[:, :N] = y.to(out.dtype)
+    if act in (ACT_SWIGLU, ACT_LORA_Z):
+        assert bias is None and residual is None
+        y = _lora_z(y, out_scale) if act == ACT_LORA_Z else _swiglu_packed(y, out_scale)
+        n_out = y.shape[1]
+    else:
+        assert N % 8 == 0, f"N % 8 (N={N})"
+        if bias is not None:
+            assert bias.dtype == torch.float32 and bias.numel() >= N and _al16(bias)
+            y = y + bias[:N]
+        if act == ACT_GELU:
+            y = torch.nn.functional.gelu(y)
+        elif act == ACT_QUICK_GELU:
+            y = y * torch.sigmoid(1.702 * y)
+        y = y * out_scale
+        if residual is not None:
+            assert residual.dtype == torch.bfloat16 and residual.stride(1) == 1 and residual.stride(0) % 8 == 0 and _al16(residual)
+            y = y + res_scale * residual[:, :N].float()
+        n_out = N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=out_dtype)
+    assert out.stride(1) == 1 and out.shape[0] == M and out.shape[1] >= n_out and _al16(out)
+    assert out.stride(0) % (8 if out.dtype == torch.bfloat16 else 4) == 0, "ldc"
+    out[:, :n_out] = y.to(out.dtype)
     calls.append(("gemm", M, N, K))
     return out
 
@@ -142,9 +151,6 @@ def bilinear_f32(x, hin, win, hout, wout, channels, out=None, alpha=1.0, beta=0.
 # ======================================================================================================================
 # The rest of the library, for running the whole engine (crab_b200/engine.py) on the CPU in plumbing tests
 # ======================================================================================================================
-ACT_SWIGLU, ACT_LORA_Z = 3, 4
-BF16, F32 = 0, 1
-MIN_K = 64          # the seg-head path keeps every GEMM at >= one k-block; engine tests lower this to 8
 _launches = 0
 
 
@@ -185,44 +191,6 @@ def _swiglu_packed(y, scale=1.0):
     M, N = y.shape
     t = y.view(M, N // 128, 2, 64)
     return (torch.nn.functional.silu(t[:, :, 0]) * t[:, :, 1] * scale).reshape(M, N // 2)
-
-
-_gemm_plain = gemm
-
-
-def gemm(a, w, *, bias=None, residual=None, res_scale=1.0, out_scale=1.0, act=ACT_NONE, out=None, out_dtype=torch.bfloat16,
-         block_n=0, max_ctas=0, k=None, n=None):  # noqa: F811  (extends the plain version with the engine's epilogues)
-    if act not in (ACT_SWIGLU, ACT_LORA_Z):
-        global MIN_K
-        if MIN_K != 64:   # engine mode: small K allowed
-            K = k if k is not None else a.shape[1]
-            N = n if n is not None else w.shape[0]
-            y = a[:, :K].float() @ w[:N, :K].float().t()
-            if bias is not None:
-                y = y + bias[:N]
-            if act == ACT_GELU:
-                y = torch.nn.functional.gelu(y)
-            elif act == ACT_QUICK_GELU:
-                y = y * torch.sigmoid(1.702 * y)
-            y = y * out_scale
-            if residual is not None:
-                y = y + res_scale * residual[:, :N].float()
-            if out is None:
-                out = torch.empty((a.shape[0], N), dtype=out_dtype)
-            assert N % 8 == 0 and a.stride(0) % 8 == 0 and w.stride(0) % 8 == 0 and _al16(a) and _al16(w) and _al16(out)
-            out[:, :N] = y.to(out.dtype)
-            return out
-        return _gemm_plain(a, w, bias=bias, residual=residual, res_scale=res_scale, out_scale=out_scale, act=act, out=out,
-                           out_dtype=out_dtype, block_n=block_n, max_ctas=max_ctas, k=k, n=n)
-    K = k if k is not None else a.shape[1]
-    N = n if n is not None else w.shape[0]
-    assert bias is None and residual is None and a.stride(0) % 8 == 0 and w.stride(0) % 8 == 0 and _al16(a) and _al16(w)
-    y = a[:, :K].float() @ w[:N, :K].float().t()
-    res = _lora_z(y, out_scale) if act == ACT_LORA_Z else _swiglu_packed(y, out_scale)
-    if out is None:
-        out = torch.empty((a.shape[0], res.shape[1]), dtype=torch.bfloat16)
-    out[:, : res.shape[1]] = res.to(torch.bfloat16)
-    return out
 
 
 def rmsnorm(x, gamma, eps, out=None):
