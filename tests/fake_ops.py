@@ -343,3 +343,23 @@ def clip_embed_ln(patch_emb, cls, pos, gamma, beta, n_img, tokens, D, eps):
     x[:, 0] = cls + pos[0]
     x[:, 1:] = patch_emb.float().view(n_img, tokens - 1, D) + pos[1:]
     return torch.nn.functional.layer_norm(x, (D,), gamma, beta, eps).reshape(n_img * tokens, D).to(torch.bfloat16)
+
+
+# ---- BEATs helpers (csrc/elementwise.cu: beats_gate_kernel, beats_group_pack_kernel, beats_posconv_finish_kernel) ----------
+def beats_gate(q, grep_w, grep_b, grep_a, B, T, H):
+    """gate[b, h, t] = ga * (gb * grep_a[h] - 1) + 2, (ga, gb) = sigmoid of the two 4-output sums of grep_linear(q_head)."""
+    x = q[:, : H * 64].float().view(B, T, H, 64)
+    y = x @ grep_w.t() + grep_b                                    # (B, T, H, 8)
+    ga, gb = torch.sigmoid(y[..., :4].sum(-1)), torch.sigmoid(y[..., 4:].sum(-1))
+    return (ga * (gb * grep_a.view(1, 1, H) - 1.0) + 2.0).permute(0, 2, 1).contiguous()
+
+
+def beats_group_pack(x, B, T, Cc, G):
+    cg = Cc // G
+    return x.view(B, T, G, cg).permute(2, 0, 1, 3).reshape(G, B, T * cg).contiguous()
+
+
+def beats_posconv_finish(x, conv_g, bias, B, T, Cc, G):
+    cg = Cc // G
+    conv = conv_g.float().view(G, B, T, cg).permute(1, 2, 0, 3).reshape(B * T, Cc) + bias
+    return (x.float() + torch.nn.functional.gelu(conv)).to(torch.bfloat16)

@@ -16,15 +16,15 @@ def test_engine_on_the_stand_in_library_reproduces_the_reference(monkeypatch, na
     monkeypatch.setattr(fake_ops, "MIN_K", 8)
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
     g, case, sd, ocfg, ids, X = load_golden(name)
-    if any("<audio>" in x for x in X):
-        # the BEATs helper kernels are not part of the stand-in: keep the reference's audio features out of this test by
-        # feeding the reference's own inputs_embeds to the decoder, and check the visual + text splice separately
-        eng = engine.CrabEngine(sd, engine_cfg(case, ocfg), torch.device("cpu"))
-        emb = g["inputs_embeds"].to(torch.bfloat16)
+    eng = engine.CrabEngine(sd, engine_cfg(case, ocfg), torch.device("cpu"))
+    emb = g["inputs_embeds"].to(torch.bfloat16)   # the reference's own inputs_embeds: decoder parity isolated from the encoders
     n_new = g["generated_ids"].shape[1]
     out, logits = eng.generate_from_embeds(emb.clone(), n_new, return_logits=True, teacher_tokens=g["generated_ids"])
     assert rel_l2(logits[0], g["prefill_last_logits"]) < 3e-2 and rel_l2(logits[1], g["step1_logits"]) < 3e-2
     assert torch.equal(out[:, 0], g["generated_ids"][:, 0])
-    # video branch + projector through the stand-in (CLIP, Q-Former, MLP)
-    v = X[0]["<video>"]
-    assert rel_l2(eng.encode_video(v), g["vl_out"]) < 3e-2
+    # encoders, bridges and the splice (CLIP, BEATs incl. the Toeplitz pos-conv and gated bias, Q-Formers, left padding)
+    assert rel_l2(eng.encode_video(X[0]["<video>"]), g["vl_out"]) < 3e-2
+    assert rel_l2(eng.encode_audio(X[0]["<audio>"]), g["al_out"]) < 3e-2
+    e2, mask, pos = eng.prepare_inputs(ids, X)
+    assert tuple(e2.shape) == tuple(g["inputs_embeds"].shape) and rel_l2(e2, g["inputs_embeds"]) < 3e-2
+    assert torch.equal(mask, g["attention_mask"]) and torch.equal(pos, g["position_ids"])
