@@ -18,7 +18,7 @@ into the passes (only the kept 224 x 224 window is computed).
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional, Sequence, Tuple, Union
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

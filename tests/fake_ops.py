@@ -3,8 +3,6 @@ packing, index tables) of modules such as crab_b200/seg.py without a GPU.  Each 
 kernel it stands for with the kernel's own index formulas, rounds to bf16 where the kernel stores bf16, and enforces the same
 argument checks as the C entry point (alignment, N % 8, row strides ...), so a call sequence that passes here is accepted by
 the real library.  It is never imported by the product."""
-import math
-
 import torch
 
 ACT_NONE, ACT_QUICK_GELU, ACT_GELU, ACT_SWIGLU, ACT_LORA_Z = 0, 1, 2, 3, 4

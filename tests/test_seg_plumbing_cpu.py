@@ -4,7 +4,6 @@ which enforces the C ABI's argument checks) and compared with the oracle on the 
 themselves are checked on the GPU (tests/test_seg_gpu.py)."""
 from pathlib import Path
 
-import pytest
 import torch
 
 import fake_ops
