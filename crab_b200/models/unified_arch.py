@@ -438,7 +438,7 @@ class UnifiedMetaForCausalLM:
         taps = tuple(eng.cfg.select_layers[:2]) if return_multi_scale_features else ()
         embeds, mask, pos = eng.prepare_inputs(batch_input_ids, batch_X_modals, want_image_taps=taps)
         labels = None
-        if batch_labels is not None:
+        if batch_labels is not None and all(lab is not None for lab in batch_labels):
             S = embeds.shape[1]
             rows = []
             for ids, lab, m in zip(batch_input_ids, batch_labels, mask):

@@ -321,7 +321,7 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
         if eng.seg is None:
             raise RuntimeError("generate_avs needs the segmentation branch: init_multimodal_modules(segment_branch=True) and its weights")
         assert len(batch_input_ids) == 1, "generate_avs handles one sample per call, as the reference does"
-        inputs = self.prepare_multimodal_inputs(batch_input_ids, batch_labels, batch_X_modals, batch_task_names,
+        inputs = self.prepare_multimodal_inputs(batch_input_ids, None, batch_X_modals, batch_task_names,   # labels are unused here
                                                 return_multi_scale_features=True, return_gt_mask=False)
         n = max_new_tokens or self.generation_config.max_new_tokens
         ids = eng.generate_from_embeds(inputs["inputs_embeds"], n, capture_hidden=6,
