@@ -35,7 +35,7 @@ int crab_version(void);
  * initial value, default 0): 1 = weight-streaming GEMM, 2 = row norm/LoRA pre-pass, 4 = RoPE + KV append,
  * 8 = decode attention, 16 = the other light kernels (norm, gather, arg-max, counters); modifier 32 = the decode
  * attention releases its dependents after its streaming loop instead of at its top.  Read at launch time. */
-int crab_set_pdl(int mask);
+int crab_set_pdl(int mask);   /* process-wide launch policy, like crab_set_gemm_2cta: set it from the thread that launches */
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Dense linear:  C[M,N] = epilogue( A[M,K] . B[N,K]^T )       (tcgen05 + TMEM + TMA, persistent, warp-specialised)
@@ -107,6 +107,10 @@ int crab_rope_kv_append(void* qkv, int ldq, const float* cos_sin, void* k_cache,
  *           (models/Qformer.py:207-266) and causal LlamaAttention / Qwen2Attention prefill
  *           (models/modeling_llama.py:405-450, models/qwen/modeling_qwen2.py:190-199 repeat_kv).
  *           All strides are in elements; head_dim in {64,128}; bias = gate[B,H,Sq] * bias_table[H,Sq,Sk] (fp32) or NULL.
+ *           head_dim-128 problems with >= 128 queries, no bias and TMA-describable strides run on the tcgen05 / TMEM kernel,
+ *           which fetches whole 64-key tiles: K / V memory up to the next multiple of 64 rows past Sk must hold FINITE values
+ *           (masked keys get probability 0, and 0 x NaN would poison the row) — zero-initialised KV caches do; rows past the
+ *           end of the tensor are zero-filled by TMA.
  *           With sk_dev the number of keys is read on the device: the GQA decode step calls this with the G query heads of
  *           a kv group as the Sq = G "rows" of one problem (q_rs = head_dim), so grouped-query decode runs on tensor cores.
  * crab_attn_decode replaces: the same attention at q_len == 1 over the KV cache (decode step), split over the
