@@ -106,3 +106,32 @@ def test_mirror_generate_avs_call_matches_the_oracle(monkeypatch):
     res2 = model.generate_avs(batch_input_ids=[prompt], batch_labels=None, batch_X_modals=[X], batch_task_names=["avss"],
                               max_new_tokens=4)
     assert "pred_masks" not in res2 and tuple(res2["output_ids"].shape) == (1, 4)
+
+
+def test_select_pred_embeddings_equals_the_literal_reference_loop():
+    """Random generated sequences: the tail-based selection equals the reference's literal code (models/unified_llama.py:
+    331-351: zip(mask_list, hidden_states), cat along the sequence axis, last six) evaluated on full hidden states."""
+    from crab_b200.models.unified_llama import select_pred_embeddings
+
+    g = torch.Generator().manual_seed(0)
+    D, S, mask_ids = 4, 9, [90, 91, 92, 93, 94, 95]
+    for trial in range(300):
+        n = int(torch.randint(2, 14, (1,), generator=g))
+        ids = [int(v) for v in torch.randint(85, 99, (n,), generator=g)]
+        hidden = [torch.randn(1, S, D, generator=g)] + [torch.randn(1, 1, D, generator=g) for _ in range(n - 1)]
+        # --- literal restatement of the reference lines
+        mask_list = [int(t in mask_ids) for t in ids[1:]]
+        pred = [hs for item, hs in zip(mask_list, hidden) if item == 1]
+        ref = None
+        if pred:
+            cat = torch.cat(pred, dim=1)
+            if cat.shape[1] > 6:
+                ref = cat[:, -6:]
+            elif cat.shape[1] == 6:
+                ref = cat
+        # --- ours: only the prompt pass's last six rows and one row per step are kept by the engine
+        got = select_pred_embeddings(ids, mask_ids, hidden[0][0, -6:], torch.cat(hidden[1:], 0)[:, 0] if n > 1 else torch.empty(0, D))
+        if ref is None:
+            assert got is None, (trial, ids)
+        else:
+            assert got is not None and torch.equal(got, ref[0]), (trial, ids)
