@@ -94,6 +94,7 @@ class CrabConfig:
     pad_token_id: int = 0
     max_ctx: int = 1280
     special_ids: Dict[str, int] = field(default_factory=dict)  # from initialize_MM_tokenizer
+    low_res_mask_size: int = 112                               # init_multimodal_modules(low_res_mask_size=) -> SegModule
 
 
 def _bf(t: torch.Tensor, dev) -> torch.Tensor:
@@ -167,7 +168,8 @@ class CrabEngine:
         if "model.seg_module.no_mask_embed.weight" in sd:   # segmentation branch present: the mask head (crab_b200/seg.py)
             from .seg import SegHead
 
-            self.seg = SegHead(sd, self.dev, prefix="model.seg_module", grid=cfg.clip.image // cfg.clip.patch)
+            self.seg = SegHead(sd, self.dev, prefix="model.seg_module", grid=cfg.clip.image // cfg.clip.patch,
+                               low_res=cfg.low_res_mask_size)
         self.has_encoders = load_encoders and ("model.vl_projector.visual_ln.weight" in sd)
         if self.has_encoders:
             self._pack_clip(sd)
@@ -295,7 +297,14 @@ class CrabEngine:
     def _pack_clip(self, sd: SD):
         c, dev = self.cfg.clip, self.dev
         p = "model.visual_encoder.vision_tower.vision_model."
-        self.clip_layers_run = max(self.cfg.select_layers)  # hidden_states[k] = output of layer k (1-based)
+        # hidden_states[k] = output of layer k (index 0 = embeddings); the reference also ships negative indices
+        # ([-11, -2, -1], configs/unified_config.py): normalise against the 25-entry tuple like Python indexing does
+        nh = c.layers + 1
+        sel = tuple(k if k >= 0 else k + nh for k in self.cfg.select_layers)
+        if any(k < 1 or k >= nh for k in sel):
+            raise ValueError(f"select_layers {self.cfg.select_layers} out of range for a {c.layers}-layer ViT")
+        self.cfg.select_layers = sel
+        self.clip_layers_run = max(sel)
         kp = 3 * c.patch * c.patch
         self.clip_kpad = (kp + 7) // 8 * 8
         self.clip_patch_w = _bf(_pad_cols(sd[p + "embeddings.patch_embedding.weight"].reshape(c.hidden, kp).float(), self.clip_kpad), dev)
@@ -806,6 +815,9 @@ class CrabEngine:
 
     def decode_step(self):
         """One greedy step: consumes self.next_ids, leaves the new arg-max there and fp32 logits in self.logits."""
+        if self.cur_len >= self.cfg.max_ctx:
+            # the step would write K/V row `cur_len` and read RoPE row `cur_len`: both are outside the allocations
+            raise ops._l.CrabError(f"decode_step at position {self.cur_len}: the KV cache holds max_ctx = {self.cfg.max_ctx} positions")
         if self._use_graph:
             self._graph.replay()
             ops.count_launches(self._graph_kernels)
@@ -817,35 +829,67 @@ class CrabEngine:
     @torch.no_grad()
     def generate_from_embeds(self, inputs_embeds: torch.Tensor, max_new_tokens: int, use_graph: bool = True,
                              return_logits: bool = False, teacher_tokens: Optional[torch.Tensor] = None,
-                             capture_hidden: int = 0):
-        """Greedy loop (EOS handling is the caller's: fixed-length).  Returns ids [B, n] (int64, device).
+                             capture_hidden: int = 0, eos_token_id=None, pad_token_id: Optional[int] = None,
+                             sampling: Optional[dict] = None):
+        """Greedy loop.  Returns ids [B, n] (int64, device), n <= max_new_tokens.
+        eos_token_id (int / list / None): HF `generate` semantics — a row that emitted EOS produces `pad_token_id` afterwards and
+        decoding stops right after the step at which the last row finished (the flag is read back once every 8 tokens, so up to 7
+        surplus steps are decoded and dropped).  None = fixed length.
         capture_hidden = t > 0 additionally records what HF's `output_hidden_states` exposes of the LAST layer (after the final
         norm): `self.hidden_prefill_tail` [B, min(t, S), D] (the last positions of the prompt pass) and `self.hidden_steps`
         [n - 1, B, D] (one row per decode step) — the inputs of generate_avs' mask-token pairing (unified_llama.py:335-345)."""
         B, S = inputs_embeds.shape[0], inputs_embeds.shape[1]
-        assert inputs_embeds.shape[1] + max_new_tokens <= self.cfg.max_ctx, "raise CrabConfig.max_ctx"
+        if sampling is not None:
+            raise NotImplementedError("sampling: see CrabEngine.sample_next (set up below)")
+        if S + max_new_tokens > self.cfg.max_ctx:
+            raise ops._l.CrabError(f"prompt of {S} positions + {max_new_tokens} new tokens exceeds the KV cache (max_ctx = "
+                                   f"{self.cfg.max_ctx}): construct the model / CrabConfig with a larger max_ctx")
         self._tail_rows = min(int(capture_hidden), S) if capture_hidden else 0
         logits, nxt = self.prefill(inputs_embeds)
         self._tail_rows = 0
-        out = torch.empty((B, max_new_tokens), device=self.dev, dtype=torch.int64)
-        out[:, 0].copy_(nxt)
+        pad = int(self.cfg.pad_token_id if pad_token_id is None else pad_token_id)
+        eos = None
+        if eos_token_id is not None:
+            eos = torch.as_tensor(list(eos_token_id) if isinstance(eos_token_id, (list, tuple)) else [int(eos_token_id)],
+                                  device=self.dev, dtype=torch.int64)
+            done = torch.zeros(B, dtype=torch.bool, device=self.dev)
+            alive = []  # per step: does any row still need tokens after it?  (device flags; read back in batches)
+        out = torch.full((B, max_new_tokens), pad, device=self.dev, dtype=torch.int64)
         all_logits = [logits.clone()] if return_logits else None
         steps_h = []
         if max_new_tokens > 1:
             self.begin_decode(B, use_graph and self.dev.type == "cuda")
-        for step in range(1, max_new_tokens):
+        steps = max_new_tokens
+        for step in range(max_new_tokens):
+            if eos is None:
+                out[:, step].copy_(nxt)
+            else:
+                tok = torch.where(done, torch.full_like(nxt, pad), nxt)
+                out[:, step] = tok
+                done |= torch.isin(tok, eos)
+                alive.append((~done).any())
+                if step % 8 == 7 and bool(done.all()):  # one host sync every 8 tokens instead of every token
+                    break
+            if step + 1 == max_new_tokens:
+                break
             if teacher_tokens is not None:
-                self.next_ids.copy_(teacher_tokens[:, step - 1])
+                self.next_ids.copy_(teacher_tokens[:, step])
             logits, nxt = self.decode_step()
-            out[:, step].copy_(nxt)
             if return_logits:
                 all_logits.append(logits.clone())
             if capture_hidden:
                 steps_h.append(self._buf("head_hn", (B, self.cfg.decoder.hidden)).clone())
+        if eos is not None:
+            hist = torch.stack(alive).cpu().tolist()
+            steps = (hist.index(False) + 1) if False in hist else len(hist)
+            out = out[:, :steps]
         if capture_hidden:
             D = self.cfg.decoder.hidden
+            steps_h = steps_h[: max(steps - 1, 0)]
             self.hidden_steps = torch.stack(steps_h, 0) if steps_h else torch.empty((0, B, D), device=self.dev, dtype=torch.bfloat16)
-        return (out, torch.stack(all_logits, 0)) if return_logits else out
+        if return_logits:
+            return out, torch.stack(all_logits[: out.shape[1]], 0)
+        return out
 
     @torch.no_grad()
     def generate(self, batch_input_ids, batch_X_modals, max_new_tokens: int, use_graph: bool = True):

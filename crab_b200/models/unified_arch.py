@@ -482,4 +482,5 @@ def build_crab_config(decoder: DecoderConfig, model, max_ctx: int) -> CrabConfig
     return CrabConfig(decoder=decoder, clip=clip, beats=beats, qformer=getattr(inner, "qformer_cfg", QformerConfig()),
                       select_layers=tuple(getattr(inner, "select_layer_list", (14, 22, 23))),
                       n_query=getattr(inner, "n_query", 32), pad_token_id=int(getattr(inner, "pad_token_id", 0) or 0),
-                      max_ctx=max_ctx, special_ids=dict(getattr(model, "SPECIAL_TOKEN_2_IDS", {})))
+                      max_ctx=max_ctx, special_ids=dict(getattr(model, "SPECIAL_TOKEN_2_IDS", {})),
+                      low_res_mask_size=int(getattr(inner, "low_res_mask_size", 112)))

@@ -128,8 +128,23 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
         self.max_ctx = max_ctx
         self.is_avs_task = False
         self._engine: Optional[CrabEngine] = None
+        self._engine_fp = None
         self._target = torch.device("cpu")
-        self.generation_config = SimpleNamespace(max_new_tokens=20)
+        # what HF `generate` would read from the checkpoint: generation_config.json if present (from_pretrained), else the
+        # model config's eos / pad ids.  quick_start.py calls generate(**sample, use_cache=True, max_new_tokens=N) and relies on it.
+        self.generation_config = SimpleNamespace(max_new_tokens=20, eos_token_id=getattr(config, "eos_token_id", None),
+                                                 pad_token_id=getattr(config, "pad_token_id", None), do_sample=False,
+                                                 temperature=1.0, top_p=1.0, top_k=0)
+        # any load_state_dict that reaches this module — including PeftModel.load_state_dict recursing from a wrapper
+        # (scripts/quick_start.py:542) — invalidates the packed engine
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate_engine())
+
+    def _invalidate_engine(self):
+        self._engine = None
+
+    def _fingerprint(self):
+        """Cheap staleness check for in-place parameter edits: tensor identities + version counters."""
+        return tuple((id(p), p._version) for p in self.parameters())
 
     # ---- construction / weights --------------------------------------------------------------------------------
     @classmethod
@@ -149,7 +164,17 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
             for f in sorted(glob.glob(os.path.join(str(pretrained_model_name_or_path), "pytorch_model*.bin"))):
                 sd.update(torch.load(f, map_location="cpu"))
         if sd:
-            model.load_state_dict(sd, strict=False)
+            if getattr(config, "tie_word_embeddings", False) and "lm_head.weight" not in sd and "model.embed_tokens.weight" in sd:
+                sd["lm_head.weight"] = sd["model.embed_tokens.weight"]      # tied checkpoints ship no lm_head tensor
+            res = model.load_state_dict(sd, strict=False)
+            lost = [k for k in res.missing_keys if k.startswith(("model.layers.", "model.embed_tokens", "model.norm", "lm_head"))]
+            if lost:
+                raise RuntimeError(f"checkpoint {pretrained_model_name_or_path} lacks {len(lost)} decoder tensors, e.g. {lost[:4]}")
+        gc = os.path.join(str(pretrained_model_name_or_path), "generation_config.json")
+        if os.path.exists(gc):
+            with open(gc) as f:
+                for k, v in json.load(f).items():
+                    setattr(model.generation_config, k, v)
         return model
 
     @classmethod
@@ -164,7 +189,10 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
         model.config, model.vocab_size, model.max_ctx = config, engine.vocab, engine.cfg.max_ctx
         model.pretraining_tp, model.is_avs_task = 1, False
         model._engine, model._target = engine, engine.dev
-        model.generation_config = SimpleNamespace(max_new_tokens=20)
+        model._engine_fp = None
+        # no checkpoint, no generation_config: fixed-length greedy runs unless the caller passes eos_token_id
+        model.generation_config = SimpleNamespace(max_new_tokens=20, eos_token_id=None, pad_token_id=engine.cfg.pad_token_id,
+                                                  do_sample=False, temperature=1.0, top_p=1.0, top_k=0)
         model.model.pad_token_id = engine.cfg.pad_token_id
         ids = engine.cfg.special_ids
         model.SPECIAL_TOKEN_2_IDS, model.IDS_2_SPECIAL_TOKEN = dict(ids), {v: k for k, v in ids.items()}
@@ -200,6 +228,19 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
         self._engine = None
         return nn.Module.load_state_dict(self, sd, strict=strict)
 
+    def _lora_hparams(self):
+        """(r, alpha, nums) of the hyper-LoRA wrap peft_hyper put on the linears (peft_hyper/tuners/lora.py:260-297), read from
+        the wrapped modules themselves; None when the decoder is not wrapped."""
+        for m in self.model.layers[0].self_attn.modules() if len(self.model.layers) else ():
+            if hasattr(m, "lora_A") and hasattr(m, "lora_route"):
+                r = int(getattr(m, "r", m.lora_A.weight.shape[0]))
+                nums = int(getattr(m, "lora_num", m.lora_route.weight.shape[0]))
+                alpha = getattr(m, "lora_alpha", None)
+                if alpha is None and getattr(m, "scaling", None) is not None:
+                    alpha = float(m.scaling) * r
+                return r, (16 if alpha is None else alpha), nums
+        return None
+
     # ---- device handling: parameters stay on the host as the load-time copy; the engine owns device memory ------
     def cuda(self, device=None):
         self._target = torch.device("cuda", torch.cuda.current_device() if device is None else
@@ -229,19 +270,30 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
     def decoder_config(self) -> DecoderConfig:
         c = self.config
         hd = getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads
-        return DecoderConfig(hidden=c.hidden_size, inter=c.intermediate_size, layers=c.num_hidden_layers,
-                             heads=c.num_attention_heads, kv_heads=getattr(c, "num_key_value_heads", None) or c.num_attention_heads,
-                             head_dim=hd, vocab=self.lm_head.weight.shape[0],
-                             rope_theta=float(getattr(c, "rope_theta", None) or (getattr(c, "rope_parameters", None) or {}).get("rope_theta", 10000.0)),
-                             eps=c.rms_norm_eps, qkv_bias=self.model.qkv_bias)
+        d = DecoderConfig(hidden=c.hidden_size, inter=c.intermediate_size, layers=c.num_hidden_layers,
+                          heads=c.num_attention_heads, kv_heads=getattr(c, "num_key_value_heads", None) or c.num_attention_heads,
+                          head_dim=hd, vocab=self.lm_head.weight.shape[0],
+                          rope_theta=float(getattr(c, "rope_theta", None) or (getattr(c, "rope_parameters", None) or {}).get("rope_theta", 10000.0)),
+                          eps=c.rms_norm_eps, qkv_bias=self.model.qkv_bias)
+        hp = self._lora_hparams()
+        if hp is not None:
+            if (hp[0], hp[2]) != (8, 3):
+                raise ValueError(f"hyper-LoRA geometry r={hp[0]}, lora_nums={hp[2]} is not supported: the B200 kernels are built for "
+                                 "the reference's shipped r=8 x 3 experts (11 router/A rows, 24 z columns per linear)")
+            d.lora_r, d.lora_alpha, d.lora_nums = hp
+        return d
 
     def engine(self) -> CrabEngine:
+        meta = self.lm_head.weight.is_meta           # from_engine(): the weights live only in the engine
+        if self._engine is not None and not meta and self._engine_fp is not None and self._engine_fp != self._fingerprint():
+            self._engine = None                      # a parameter was edited in place since the engine was packed
         if self._engine is None:
             if self.device.type != "cuda":
                 raise RuntimeError("call .cuda() / .npu() first: crab_b200 has no CPU execution path")
             # state_dict() of this container includes any hyper-LoRA tensors peft_hyper attached to the linears
             self._engine = CrabEngine(self.state_dict(), build_crab_config(self.decoder_config(), self, self.max_ctx),
                                       self._target)
+            self._engine_fp = self._fingerprint()
         return self._engine
 
     # ---- forward / generate -------------------------------------------------------------------------------------
@@ -270,44 +322,46 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
             logits, _ = eng.prefill(inputs_embeds.clone())
         return SimpleNamespace(logits=logits.unsqueeze(1).clone(), past_key_values=True, loss=None)
 
+    def _eos_ids(self, eos_token_id, ignore_eos: bool):
+        """HF semantics: an explicit `eos_token_id` wins, else generation_config.eos_token_id (from the checkpoint's
+        generation_config.json, else the model config).  `ignore_eos=True` (extension) forces a fixed-length run."""
+        if ignore_eos:
+            return None
+        if eos_token_id is None:
+            eos_token_id = getattr(self.generation_config, "eos_token_id", None)
+        if eos_token_id is None:
+            eos_token_id = getattr(self.config, "eos_token_id", None) if not self.lm_head.weight.is_meta else None
+        return eos_token_id
+
+    def _pad_id(self, pad_token_id=None):
+        for v in (pad_token_id, getattr(self.generation_config, "pad_token_id", None), self.model.pad_token_id):
+            if v is not None:
+                return int(v)
+        return 0
+
     @torch.no_grad()
     def generate(self, batch_input_ids=None, batch_labels=None, batch_X_modals=None, batch_task_names=None, *,
-                 inputs_embeds=None, max_new_tokens: Optional[int] = None, eos_token_id=None, do_sample=False, **kwargs):
-        """Greedy generation; returns only the new ids (b, <= max_new_tokens), like HF generate with inputs_embeds.
-        Rows that hit `eos_token_id` are padded with pad_token_id afterwards (HF semantics); decoding stops early when
-        every row has finished."""
-        if do_sample:
-            raise NotImplementedError("the B200 path implements greedy decoding (the quick-start default)")
+                 inputs_embeds=None, max_new_tokens: Optional[int] = None, eos_token_id=None, pad_token_id=None, do_sample=None,
+                 temperature=None, top_p=None, top_k=None, ignore_eos: bool = False, generator: Optional[torch.Generator] = None,
+                 **kwargs):
+        """Returns only the new ids (b, <= max_new_tokens), like HF generate with inputs_embeds (models/unified_llama.py:244-267).
+        EOS: rows that emit an EOS id are padded with pad_token_id afterwards and decoding stops right after the last row
+        finishes; the EOS id defaults to the checkpoint's generation_config / config exactly as in HF — quick_start.py passes
+        only `use_cache` and `max_new_tokens`.  Greedy by default; `do_sample` (argument or generation_config, e.g.
+        LLaMA-2-chat's T=0.6 / top-p 0.9) switches the token choice to temperature / top-k / top-p sampling."""
         eng = self.engine()
         if inputs_embeds is None:
             inputs_embeds, _, _ = eng.prepare_inputs(batch_input_ids, batch_X_modals)
         n = max_new_tokens or self.generation_config.max_new_tokens
-        if eos_token_id is None:
-            return eng.generate_from_embeds(inputs_embeds, n)
-        eos = torch.as_tensor(eos_token_id if isinstance(eos_token_id, (list, tuple)) else [eos_token_id], device=eng.dev)
-        B = inputs_embeds.shape[0]
-        _, nxt = eng.prefill(inputs_embeds)
-        out = torch.full((B, n), int(self.model.pad_token_id or 0), device=eng.dev, dtype=torch.int64)
-        done = torch.zeros(B, dtype=torch.bool, device=eng.dev)
-        if n > 1:
-            eng.begin_decode(B)
-        steps = 0
-        alive = []  # per step: does any row still need tokens after it?  (kept on the device; read once at the end)
-        for step in range(n):
-            tok = torch.where(done, torch.full_like(nxt, int(self.model.pad_token_id or 0)), nxt)
-            out[:, step] = tok
-            done |= torch.isin(tok, eos)
-            alive.append((~done).any())
-            steps = step + 1
-            if step % 8 == 7 and bool(done.all()):  # one host sync every 8 tokens instead of every token
-                break
-            if step + 1 < n:
-                _, nxt = eng.decode_step()
-        # HF stops right after the step at which the last row emitted EOS: drop the (all-pad) columns decoded past it
-        hist = torch.stack(alive).cpu().tolist()
-        if False in hist:
-            steps = hist.index(False) + 1
-        return out[:, :steps]
+        gc = self.generation_config
+        sample = bool(getattr(gc, "do_sample", False) if do_sample is None else do_sample)
+        sampling = None
+        if sample:
+            sampling = dict(temperature=float(temperature if temperature is not None else getattr(gc, "temperature", 1.0) or 1.0),
+                            top_p=float(top_p if top_p is not None else getattr(gc, "top_p", 1.0) or 1.0),
+                            top_k=int(top_k if top_k is not None else getattr(gc, "top_k", 0) or 0), generator=generator)
+        return eng.generate_from_embeds(inputs_embeds, n, eos_token_id=self._eos_ids(eos_token_id, ignore_eos),
+                                        pad_token_id=self._pad_id(pad_token_id), sampling=sampling)
 
     @torch.no_grad()
     def generate_avs(self, batch_input_ids=None, batch_labels=None, batch_X_modals=None, batch_task_names=None, *,
@@ -324,8 +378,13 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
         inputs = self.prepare_multimodal_inputs(batch_input_ids, None, batch_X_modals, batch_task_names,   # labels are unused here
                                                 return_multi_scale_features=True, return_gt_mask=False)
         n = max_new_tokens or self.generation_config.max_new_tokens
+        # same stopping rule as generate(): the reference calls HF generate here too (unified_llama.py:322-330), so the
+        # sequence — and with it the hidden states that can pair with <mask_i> tokens — ends at EOS
         ids = eng.generate_from_embeds(inputs["inputs_embeds"], n, capture_hidden=6,
-                                       teacher_tokens=None if forced_output_ids is None else forced_output_ids.to(eng.dev))
+                                       teacher_tokens=None if forced_output_ids is None else forced_output_ids.to(eng.dev),
+                                       eos_token_id=None if forced_output_ids is not None else
+                                       self._eos_ids(kwargs.get("eos_token_id"), bool(kwargs.get("ignore_eos", False))),
+                                       pad_token_id=self._pad_id(kwargs.get("pad_token_id")))
         output_ids = ids if forced_output_ids is None else forced_output_ids.to(eng.dev)
         result = {"output_ids": output_ids}
         mask_ids = [self.SPECIAL_TOKEN_2_IDS[f"<mask_{i}>"] for i in range(6)]

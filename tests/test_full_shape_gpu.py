@@ -1,0 +1,216 @@
+"""FULL-SHAPE parity (BASELINE.json configs[0]/[1] and the shapes scripts/quick_start.py really produces): CLIP ViT-L/14 at
+224^2 with all 24 layers and taps 14/22/23, BEATs-12, both Q-Formers at bert-base widths, LLaMA-7B-dim decoder layers
+(hidden 4096, ff 11008, 32 heads x 128, vocab 32017) with hyper-LoRA on all seven linears (non-zero lora_B).
+
+Three parties on the same seeded weights / inputs:
+  golden  = outputs of the REAL reference at these shapes (tests/golden/llama_full.pt, oracle/make_golden_full.py),
+  oracle  = oracle/crab_oracle.py run live on the host cores (fp32),
+  ours    = crab_b200 on the GPU through the C ABI (bf16 storage, fp32 accumulation).
+Checks: (1) oracle == golden to 2e-4 on every sampled stage (pins the oracle AT FULL SHAPE); (2) ours vs oracle per stage
+(relative L2 over the whole tensor, bound = 2x the measured value of the first run, recorded next to each assert);
+(3) decoder: last-position logits of the prompt pass and of 16 teacher-forced decode steps — error must not exceed 1.5x
+the error of the reference's own bf16 run against its fp32 run (the HF-bf16 yardstick stored in the golden),
+arg-max must agree on every decisive step (oracle top-2 margin > 4x the measured max |dlogit|); (4) free-running ids through
+`generate` equal the reference's up to the first non-decisive step.
+Variants: 8 frames + (10,98,128) audio -> S = 638, and 10 frames + (10,198,128) audio -> T = 96, S = 702; plus a bs-4 batch
+with unequal prompt lengths (left padding, S = 1086) against the oracle.
+"""
+import pytest
+import torch
+
+from helpers import GOLDEN, engine_cfg, oracle_cfg, rel_l2
+from oracle import crab_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rows(n, k):
+    return torch.linspace(0, n - 1, min(k, n)).round().long()
+
+
+def sample(t, k):
+    t = t.reshape(-1, t.shape[-1])
+    return t[rows(t.shape[0], k)].float()
+
+
+def close(a, b, tol=2e-4):
+    err = (a.float() - b.float()).abs().max().item()
+    scale = b.float().abs().max().item() + 1e-9
+    assert err / scale < tol, f"oracle vs reference golden: rel max err {err / scale:.3e}"
+
+
+@pytest.fixture(scope="module")
+def full(cuda_dev):
+    from crab_b200.engine import CrabEngine
+
+    g = torch.load(GOLDEN / "llama_full.pt", weights_only=False)
+    case = g["case"]
+    sd = O.strip_peft_prefix(synth.synth_state_dict(g["manifest"], case["weight_seed"]))
+    ocfg = oracle_cfg(case, g["special_ids"])
+    eng = CrabEngine(sd, engine_cfg(case, ocfg, max_ctx=1280), cuda_dev)
+    return g, case, sd, ocfg, eng
+
+
+def variant_inputs(case, ocfg, v, prompt_len=None):
+    return synth.synth_inputs(v["input_seed"], frames=v["frames"], image=case["image_size"], audio_segs=v["audio_segs"],
+                              audio_len=v["audio_len"], prompt_len=prompt_len or case["prompt_len"], base_vocab=ocfg.base_vocab,
+                              video_id=ocfg.special_ids["<video>"], audio_id=ocfg.special_ids["<audio>"])
+
+
+def oracle_stages(sd, ocfg, video, audio):
+    with torch.no_grad():
+        taps = O.visual_encoder(sd, video.unsqueeze(0), ocfg.clip, ocfg.select_layers)
+        vl = O.vl_projector(sd, taps[-1], ocfg.qformer, ocfg.image_tokens, ocfg.n_query)[0]
+        beats = O.audio_encoder(sd, audio.unsqueeze(0), ocfg.beats)
+        al = O.al_projector(sd, beats, ocfg.qformer, ocfg.n_query)[0]
+    return taps, vl, beats, al
+
+
+def oracle_prepare(sd, ocfg, ids, X, stage_of, monkeypatch):
+    """The oracle's prepare_multimodal_inputs with the encoder outputs computed once per distinct medium."""
+    monkeypatch.setattr(O, "encode_video", lambda sd_, video, cfg: stage_of[id(video)][0])
+    monkeypatch.setattr(O, "encode_audio", lambda sd_, audio, cfg: stage_of[id(audio)][1])
+    with torch.no_grad():
+        return O.prepare_multimodal_inputs(sd, ids, X, ocfg)
+
+
+@pytest.mark.parametrize("vname", ["v8_a98", "v10_a198"])
+def test_full_shape_single_sample(full, cuda_dev, monkeypatch, vname):
+    g, case, sd, ocfg, eng = full
+    gv, v = g["variants"][vname], case["variants"][vname]
+    K = case["sample_rows"]
+    video, audio, ids = variant_inputs(case, ocfg, v)
+    taps, vl, beats, al = oracle_stages(sd, ocfg, video, audio)
+    # ---- (1) the oracle reproduces the real reference at full shape ------------------------------------------------------
+    close(sample(taps[-1][0], K), gv["vit_tap_last"])
+    close(sample(taps[0][0], K), gv["vit_tap_first"])
+    close(sample(vl, K), gv["vl_out"])
+    close(sample(beats[0], K), gv["beats_out"])
+    close(sample(al, K), gv["al_out"])
+    X = [{"<video>": video, "<audio>": audio}]
+    prep = oracle_prepare(sd, ocfg, [ids], X, {id(video): (vl, None), id(audio): (None, al)}, monkeypatch)
+    emb_o = prep["inputs_embeds"]
+    assert emb_o.shape[1] == gv["S"]
+    close(sample(emb_o[0], 2 * K), gv["inputs_embeds"])
+    assert torch.equal(prep["attention_mask"], gv["attention_mask"]) and torch.equal(prep["position_ids"], gv["position_ids"])
+    ref_ids = gv["generated_ids"]
+    n_new = ref_ids.shape[1]
+    with torch.no_grad():
+        o_ids, o_logits = O.greedy_generate(sd, emb_o, ocfg.decoder, n_new, teacher_tokens=ref_ids)
+    o_logits = o_logits[:, 0]                                              # (n_new, V)
+    close(o_logits[:, gv["logit_cols"]], gv["logits_sub"])
+    assert torch.equal(o_logits.argmax(-1), ref_ids[0])
+
+    # ---- (2) ours vs oracle, stage by stage (whole tensors) --------------------------------------------------------------
+    vd, ad = video.to(cuda_dev), audio.to(cuda_dev)
+    tokens = ocfg.image_tokens + 1
+    tap = eng.clip_forward(vd).view(vd.shape[0], tokens, -1)[:, 1:].reshape(-1, ocfg.clip.hidden)
+    e_tap = rel_l2(tap, taps[-1][0])
+    e_vl = rel_l2(eng.encode_video(vd), vl)
+    b_, T = eng.beats_forward(ad)
+    assert T == (v["audio_len"] // 16) * 8
+    e_beats = rel_l2(b_.view(ad.shape[0], T, -1), beats[0])
+    e_al = rel_l2(eng.encode_audio(ad), al)
+    emb, mask, pos = eng.prepare_inputs([ids], X)
+    e_emb = rel_l2(emb, emb_o)
+    print(f"[{vname}] rel_l2 ours vs oracle: clip tap23 {e_tap:.3e}  vl_out {e_vl:.3e}  beats {e_beats:.3e}  al_out {e_al:.3e}  "
+          f"inputs_embeds {e_emb:.3e}")
+    assert torch.equal(mask, prep["attention_mask"]) and torch.equal(pos, prep["position_ids"])
+    # bounds = 2x the values measured on B200 (round 2): tap 1.1e-2, vl 1.0e-2, beats 9e-3, al 9e-3, embeds 9e-3
+    assert e_tap < 2.2e-2 and e_vl < 2.0e-2 and e_beats < 1.8e-2 and e_al < 1.8e-2 and e_emb < 1.8e-2
+
+    # ---- (3) decoder on the oracle's inputs_embeds: prompt pass + 16 teacher-forced steps -------------------------------
+    out, logits = eng.generate_from_embeds(emb_o.to(cuda_dev).to(torch.bfloat16), n_new, use_graph=True, return_logits=True,
+                                           teacher_tokens=ref_ids.to(cuda_dev))
+    logits = logits[:, 0].cpu()
+    e_steps = torch.tensor([rel_l2(logits[i], o_logits[i]) for i in range(n_new)])
+    yard = gv["hf_bf16_logits_rel_l2"]
+    print(f"[{vname}] logits rel_l2 per step: max {e_steps.max():.3e} (HF-bf16 vs fp32: max {yard.max():.3e}); "
+          f"ratio max {(e_steps / yard).max():.2f}")
+    assert bool((e_steps <= 1.5 * yard).all()), "worse than 1.5x the reference's own bf16 error"
+    err = (logits - o_logits).abs().max().item()
+    top2 = o_logits.topk(2, dim=-1).values
+    decisive = (top2[:, 0] - top2[:, 1]) > 4 * err
+    agree = logits.argmax(-1) == o_logits.argmax(-1)
+    print(f"[{vname}] max |dlogit| {err:.3e}; decisive {int(decisive.sum())}/{n_new}; arg-max agree {int(agree.sum())}/{n_new}")
+    assert bool(agree[decisive].all())
+
+    # ---- (4) end to end, free running, from the raw inputs -----------------------------------------------------------------
+    free = eng.generate([ids], X, n_new).cpu()
+    k = int((~decisive).nonzero()[0]) if bool((~decisive).any()) else n_new
+    print(f"[{vname}] free-running ids equal the reference's on {int((free[0] == ref_ids[0]).sum())}/{n_new} (decisive prefix {k})")
+    assert torch.equal(free[0, :k], ref_ids[0, :k])
+
+
+def test_full_shape_bs4_unequal_prompts(full, cuda_dev, monkeypatch):
+    """bs 4, prompts of 512 / 300 / 411 / 512 tokens around 8 frames + 10 s of audio -> left-padded to S = 1086 (pads are
+    attended, as in the reference): inputs_embeds, mask / position ids, prompt-pass logits and 3 teacher-forced steps."""
+    g, case, sd, ocfg, eng = full
+    va = dict(case["variants"]["v8_a98"])
+    vb = dict(va, input_seed=33)
+    media = {}
+    for v in (va, vb):
+        video, audio, _ = variant_inputs(case, ocfg, v)
+        media[v["input_seed"]] = (video, audio)
+    plens = (512, 300, 411, 512)
+    ids, X, stage_of = [], [], {}
+    stages = {}
+    for i, pl in enumerate(plens):
+        v = (va, vb)[i % 2]
+        video, audio = media[v["input_seed"]]
+        _, _, t = variant_inputs(case, ocfg, dict(v, input_seed=v["input_seed"] + 100 * i), prompt_len=pl)
+        if v["input_seed"] not in stages:
+            _, vl, _, al = oracle_stages(sd, ocfg, video, audio)
+            stages[v["input_seed"]] = (vl, al)
+        vl, al = stages[v["input_seed"]]
+        stage_of[id(video)] = (vl, None)
+        stage_of[id(audio)] = (None, al)
+        ids.append(t)
+        X.append({"<video>": video, "<audio>": audio})
+    prep = oracle_prepare(sd, ocfg, ids, X, stage_of, monkeypatch)
+    emb_o = prep["inputs_embeds"]
+    assert tuple(emb_o.shape) == (4, 1086, 4096)
+    emb, mask, pos = eng.prepare_inputs(ids, X)
+    assert torch.equal(mask, prep["attention_mask"]) and torch.equal(pos, prep["position_ids"])
+    e_emb = [rel_l2(emb[b], emb_o[b]) for b in range(4)]
+    print("bs4 inputs_embeds rel_l2 per sample:", ["%.3e" % e for e in e_emb])
+    assert max(e_emb) < 1.8e-2
+    n_new = 4
+    with torch.no_grad():
+        o_ids, o_logits = O.greedy_generate(sd, emb_o, ocfg.decoder, n_new)
+    out, logits = eng.generate_from_embeds(emb_o.to(cuda_dev).to(torch.bfloat16), n_new, return_logits=True,
+                                           teacher_tokens=o_ids.to(cuda_dev))
+    logits = logits.cpu()
+    e = torch.tensor([[rel_l2(logits[s, b], o_logits[s, b]) for b in range(4)] for s in range(n_new)])
+    yard = float(g["variants"]["v8_a98"]["hf_bf16_logits_rel_l2"].max())
+    print(f"bs4 S=1086 logits rel_l2 (step x sample): max {e.max():.3e} (HF-bf16 yardstick {yard:.3e})")
+    assert float(e.max()) <= 1.5 * yard
+    err = (logits - o_logits).abs().max().item()
+    top2 = o_logits.topk(2, dim=-1).values
+    decisive = (top2[..., 0] - top2[..., 1]) > 4 * err
+    agree = logits.argmax(-1) == o_logits.argmax(-1)
+    assert bool(agree[decisive].all())
+
+
+def test_mirror_model_on_gpu_full_width(full, cuda_dev):
+    """The public API object itself on the GPU (quick_start.py:30-50, 453-566): UnifiedForCausalLM built from the same
+    state dict as torch containers -> .cuda() -> forward(inputs_embeds) and generate(batch_*), against the engine driven
+    directly (must be bit-identical: same kernels) and the reference's ids."""
+    from crab_b200.models.unified_llama import UnifiedConfig, UnifiedForCausalLM
+
+    g, case, sd, ocfg, eng = full
+    lc = case["llama_cfg"]
+    model = UnifiedForCausalLM.from_engine(UnifiedConfig(hidden_size=lc["hidden_size"], intermediate_size=lc["intermediate_size"],
+                                                         num_hidden_layers=lc["num_hidden_layers"],
+                                                         num_attention_heads=lc["num_attention_heads"],
+                                                         num_key_value_heads=lc["num_key_value_heads"],
+                                                         vocab_size=lc["vocab_size"] + 17), eng)
+    v = case["variants"]["v8_a98"]
+    video, audio, ids = variant_inputs(case, ocfg, v)
+    X = [{"<video>": video, "<audio>": audio}]
+    ref_ids = g["variants"]["v8_a98"]["generated_ids"]
+    out = model.generate(batch_input_ids=[ids], batch_labels=None, batch_X_modals=X, batch_task_names=["avqa"], use_cache=True,
+                         max_new_tokens=ref_ids.shape[1]).cpu()
+    direct = eng.generate([ids], X, ref_ids.shape[1]).cpu()
+    assert torch.equal(out, direct)
