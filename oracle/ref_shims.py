@@ -77,10 +77,6 @@ def install_shims() -> None:
             hooks.remove_hook_from_submodules = lambda *a, **k: None
             utils = types.ModuleType("accelerate.utils")
             utils.get_balanced_memory = lambda *a, **k: {}
-            import importlib.machinery as _mach
-
-            for _m in (acc, hooks, utils):  # importlib.util.find_spec() on a stub without __spec__ raises
-                _m.__spec__ = _mach.ModuleSpec(_m.__name__, None)
             sys.modules["accelerate"] = acc
             sys.modules["accelerate.hooks"] = hooks
             sys.modules["accelerate.utils"] = utils
