@@ -22,7 +22,7 @@ import torch
 from . import ops
 
 SD = Dict[str, torch.Tensor]
-DEFAULT_PDL_PLAN = "19,17"  # streaming GEMM + row kernels + light kernels; attention / RoPE stay plain launches
+DEFAULT_PDL_PLAN = "0,0"  # the persistent GEMM chain owns every SM: its neighbours are plain (fully ordered) launches
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -182,6 +182,8 @@ class CrabEngine:
         # decode attention).  Env CRAB_PDL_PLAN="chain,after_attn" overrides; see profiles/r02_pdl_plans.txt for the A/B.
         plan = os.environ.get("CRAB_PDL_PLAN", DEFAULT_PDL_PLAN).split(",")
         self.pdl_chain, self.pdl_after_attn = int(plan[0]), int(plan[-1])
+        # K-split (= thread-block-cluster size) of the persistent decode GEMM chain
+        self.chain_cluster = int(os.environ.get("CRAB_CHAIN_CLUSTER", "4"))
         # decode step: RoPE + KV append + o_proj LoRA pre-pass inside the attention kernel (8 launches per layer, not 10)
         self.fuse_decode_attn = os.environ.get("CRAB_DECODE_FUSE", "1") != "0"
         self.gqa_decode_tc = os.environ.get("CRAB_GQA_DECODE_TC", "1") != "0"
@@ -217,7 +219,11 @@ class CrabEngine:
         lm = torch.zeros((self.vocab_pad, D), dtype=torch.bfloat16, device=dev)
         lm[:V] = _bf(sd["lm_head.weight"], dev)
         self.lm_head = lm
-        self.lm_head_p = ops.pack_skinny_weight(lm) if self.decode_packed else None
+        # decode / last-position head: final-norm gamma folded into the streaming copy (the chain applies rstd in its epilogue)
+        lmf = lm.clone()
+        lmf[:] = (lm.float() * self.final_norm[None, :]).to(torch.bfloat16)
+        self.lm_head_c = ops.pack_skinny_weight(lmf) if self.decode_packed else None
+        del lmf
         self.scaling = c.lora_alpha / c.lora_r
         nl, r = c.lora_nums, c.lora_r
         zw = nl * r  # 24 z columns per linear
@@ -284,12 +290,25 @@ class CrabEngine:
             L["ln2"] = _f32(sd[lp + "post_attention_layernorm.weight"], dev)
             if self.decode_packed:
                 # second copy of the decode-step weights in the streaming layout (contiguous pre-swizzled 16 KB tile
-                # blocks): the prefill GEMM wants row-major K-extended rows, the M<=32 stream wants sequential HBM
+                # blocks): the prefill GEMM wants row-major K-extended rows, the M<=32 chain wants sequential HBM.
+                # The chain applies RMSNorm as rstd[b] in its epilogue, so gamma is folded into the columns here; the
+                # hyper-LoRA router/A rows go into the chain's statistics stream (gamma folded likewise).
                 lo = self.lora
-                L["wqkv_p"] = ops.pack_skinny_weight(wq, k=D + (self.EXT_QKV if lo else 0))
-                L["wo_p"] = ops.pack_skinny_weight(wo, k=nq + (self.EXT_O if lo else 0))
-                L["wgu_p"] = ops.pack_skinny_weight(L["wgu"], k=D + (self.EXT_GU if lo else 0), swiglu=True)
-                L["wd_p"] = ops.pack_skinny_weight(wd, k=F + (self.EXT_D if lo else 0))
+
+                def fold(w, K, gamma):
+                    t = w.clone()
+                    t[:, :K] = (w[:, :K].float() * gamma[None, :]).to(torch.bfloat16)
+                    return t
+
+                L["wqkv_c"] = ops.pack_skinny_weight(fold(wq, D, L["ln1"]), k=D + (self.EXT_QKV if lo else 0))
+                L["wo_c"] = ops.pack_skinny_weight(wo, k=nq + (self.EXT_O if lo else 0))
+                L["wgu_c"] = ops.pack_skinny_weight(fold(L["wgu"], D, L["ln2"]), k=D + (self.EXT_GU if lo else 0), swiglu=True)
+                L["wd_c"] = ops.pack_skinny_weight(wd, k=F + (self.EXT_D if lo else 0))
+                if lo:
+                    L["st_qkv"] = ops.pack_chain_stats(L["ra_qkv"], L["ln1"])
+                    L["st_o"] = ops.pack_chain_stats(L["ra_o"])
+                    L["st_gu"] = ops.pack_chain_stats(L["ra_gu"], L["ln2"])
+                    L["st_d"] = ops.pack_chain_stats(L["ra_d"])
             self.layers.append(L)
         self.rope = ops.rope_table(self.cfg.max_ctx, hd, c.rope_theta, dev)
 
@@ -643,8 +662,8 @@ class CrabEngine:
 
     def _decoder_layers(self, x: torch.Tensor, B: int, S: int, past: int, past_dev=None, len_dev=None, nsplit=1,
                         ws=None, tag="pf"):
-        """x bf16 [B*S, D], updated in place through all layers.  S > 1: prefill (flash attention over the cache);
-        S == 1 with past_dev/len_dev: one decode step."""
+        """x bf16 [B*S, D], updated in place through all layers: the dense-GEMM route.  S > 1: prefill (flash attention over
+        the cache); S == 1 with past_dev/len_dev: a decode step for batches beyond the 32-row streaming chain."""
         c = self.cfg.decoder
         D, F, H, KV, hd = c.hidden, c.inter, c.heads, c.kv_heads, c.head_dim
         M = B * S
@@ -654,44 +673,14 @@ class CrabEngine:
         at = self._buf(tag + "_attn", (M, nq + self.EXT_O), zero=True)
         hh = self._buf(tag + "_h", (M, F + self.EXT_D), zero=True)
         ctx = self.cfg.max_ctx
-        skinny = (S == 1 and len_dev is not None and M <= 32 and self.decode_packed)  # decode step: weight streaming
         sc = self.scaling
         for li, L in enumerate(self.layers):
-            if skinny:
-                ops.row_norm_loraz(x, gamma=L["ln1"], eps=c.eps, y=xn[:, :D], ra=L.get("ra_qkv"), groups=3 if self.lora else 0,
-                                   z=xn[:, D:] if self.lora else None, scale=sc)
-                ops.gemm_skinny(xn, L.get("wqkv_p", L["wqkv"]), bias=L["bqkv"], out=qkv, k=D + (self.EXT_QKV if self.lora else 0))
-            else:
-                ops.rmsnorm(x, L["ln1"], c.eps, out=xn[:, :D])
-                if self.lora:
-                    ops.gemm(xn[:, :D], L["ra_qkv"], act=ops.ACT_LORA_Z, out_scale=sc, out=xn[:, D:D + 72])
-                ops.gemm(xn, L["wqkv"], bias=L["bqkv"], out=qkv, k=D + (self.EXT_QKV if self.lora else 0))
-            G = H // KV
-            # grouped-query decode with enough (batch x kv-head) problems to fill the SMs: the G query heads of a kv group are
-            # the Sq = G "rows" of one flash-attention problem, so QK^T / PV run on tensor cores instead of G scalar dot
-            # products per key per lane (Qwen2-7B, G = 7: 120 us -> ~15 us per layer at bs 32)
-            gqa_tc = skinny and G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
-            fused = skinny and self.fuse_decode_attn and not gqa_tc
-            if gqa_tc:
-                ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, S, H, KV, hd, past=past, past_dev=past_dev)
-                ops.flash_attn(qkv, self.k_cache[li], self.v_cache[li], at, B=B, H=KV, KVH=KV, Sq=G, Sk=ctx, head_dim=hd,
-                               q_strides=(nq + 2 * nk, hd, G * hd), k_strides=(KV * ctx * hd, hd, ctx * hd),
-                               v_strides=(KV * ctx * hd, hd, ctx * hd), o_strides=(nq + self.EXT_O, hd, G * hd),
-                               scale=1 / math.sqrt(hd), sk_dev=len_dev)
-            elif fused:
-                # one launch: RoPE on q / new k, cache append, attention over past + 1 keys, and (nsplit == 1) the o_proj
-                # LoRA pre-pass whose z columns land in at[:, nq:]
-                lo = self.lora and nsplit == 1
-                ops.attn_decode_fused(qkv, self.rope, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV,
-                                      head_dim=hd, scale=1 / math.sqrt(hd), past_dev=past_dev, nsplit=nsplit, workspace=ws,
-                                      ra=L["ra_o"] if lo else None, z=at[:, nq:] if lo else None, lora_scale=sc,
-                                      lora_ws=self._buf("dec_lora_ws", (B * KV * 11,), torch.float32) if lo else None,
-                                      lora_counters=self._buf("dec_lora_cnt", (B,), torch.int32, zero=True) if lo else None)
-            else:
-                ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, S, H, KV, hd, past=past, past_dev=past_dev)
-            if fused or gqa_tc:
-                pass
-            elif S == 1 and len_dev is not None:
+            ops.rmsnorm(x, L["ln1"], c.eps, out=xn[:, :D])
+            if self.lora:
+                ops.gemm(xn[:, :D], L["ra_qkv"], act=ops.ACT_LORA_Z, out_scale=sc, out=xn[:, D:D + 72])
+            ops.gemm(xn, L["wqkv"], bias=L["bqkv"], out=qkv, k=D + (self.EXT_QKV if self.lora else 0))
+            ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, S, H, KV, hd, past=past, past_dev=past_dev)
+            if S == 1 and len_dev is not None:
                 ops.attn_decode(qkv, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV, head_dim=hd,
                                 scale=1 / math.sqrt(hd), len_dev=len_dev, nsplit=nsplit, workspace=ws)
             else:
@@ -699,46 +688,36 @@ class CrabEngine:
                                q_strides=(S * (nq + 2 * nk), nq + 2 * nk, hd), k_strides=(KV * ctx * hd, hd, ctx * hd),
                                v_strides=(KV * ctx * hd, hd, ctx * hd), o_strides=(S * (nq + self.EXT_O), nq + self.EXT_O, hd),
                                scale=1 / math.sqrt(hd), causal=True)
-            if skinny:
-                # the kernel right after the decode attention is launched under its own PDL mask: early-resident
-                # streaming-GEMM CTAs must not squat on the SMs while the 1024-CTA attention kernel still runs
-                if self.pdl_after_attn != self.pdl_chain:
-                    ops.set_pdl(self.pdl_after_attn)
-                if self.lora and not (fused and nsplit == 1):
-                    ops.row_norm_loraz(at[:, :nq], ra=L["ra_o"], groups=1, z=at[:, nq:], scale=sc)
-                    if self.pdl_after_attn != self.pdl_chain:
-                        ops.set_pdl(self.pdl_chain)
-                ops.gemm_skinny(at, L.get("wo_p", L["wo"]), residual=x, out=x, k=nq + (self.EXT_O if self.lora else 0))
-                if self.pdl_after_attn != self.pdl_chain:
-                    ops.set_pdl(self.pdl_chain)
-                ops.row_norm_loraz(x, gamma=L["ln2"], eps=c.eps, y=xn[:, :D], ra=L.get("ra_gu"), groups=2 if self.lora else 0,
-                                   z=xn[:, D:] if self.lora else None, scale=sc)
-                ops.gemm_skinny(xn, L["wgu_p"], act=ops.ACT_SWIGLU, out=hh[:, :F])
-                if self.lora:
-                    ops.row_norm_loraz(hh[:, :F], ra=L["ra_d"], groups=1, z=hh[:, F:], scale=sc)
-                ops.gemm_skinny(hh, L.get("wd_p", L["wd"]), residual=x, out=x, k=F + (self.EXT_D if self.lora else 0))
-            else:
-                if self.lora:
-                    ops.gemm(at[:, :nq], L["ra_o"], act=ops.ACT_LORA_Z, out_scale=sc, out=at[:, nq:nq + 24])
-                ops.gemm(at, L["wo"], residual=x, out=x, k=nq + (self.EXT_O if self.lora else 0))
-                ops.rmsnorm(x, L["ln2"], c.eps, out=xn[:, :D])
-                if self.lora:
-                    ops.gemm(xn[:, :D], L["ra_gu"], act=ops.ACT_LORA_Z, out_scale=sc, out=xn[:, D:D + 48])
-                ops.gemm(xn, L["wgu"], act=ops.ACT_SWIGLU, out=hh[:, :F], k=D + (self.EXT_GU if self.lora else 0))
-                if self.lora:
-                    ops.gemm(hh[:, :F], L["ra_d"], act=ops.ACT_LORA_Z, out_scale=sc, out=hh[:, F:F + 24])
-                ops.gemm(hh, L["wd"], residual=x, out=x, k=F + (self.EXT_D if self.lora else 0))
+            if self.lora:
+                ops.gemm(at[:, :nq], L["ra_o"], act=ops.ACT_LORA_Z, out_scale=sc, out=at[:, nq:nq + 24])
+            ops.gemm(at, L["wo"], residual=x, out=x, k=nq + (self.EXT_O if self.lora else 0))
+            ops.rmsnorm(x, L["ln2"], c.eps, out=xn[:, :D])
+            if self.lora:
+                ops.gemm(xn[:, :D], L["ra_gu"], act=ops.ACT_LORA_Z, out_scale=sc, out=xn[:, D:D + 48])
+            ops.gemm(xn, L["wgu"], act=ops.ACT_SWIGLU, out=hh[:, :F], k=D + (self.EXT_GU if self.lora else 0))
+            if self.lora:
+                ops.gemm(hh[:, :F], L["ra_d"], act=ops.ACT_LORA_Z, out_scale=sc, out=hh[:, F:F + 24])
+            ops.gemm(hh, L["wd"], residual=x, out=x, k=F + (self.EXT_D if self.lora else 0))
         return x
+
+    def _head_phase(self, x_rows: torch.Tensor, logits: torch.Tensor):
+        """final RMSNorm (rstd in the epilogue, gamma folded into lm_head_c) + lm_head as one chain phase."""
+        c = self.cfg.decoder
+        return ops.ChainPhase(x_rows, self.lm_head_c, logits, k=c.hidden, norm=True, eps=c.eps,
+                              rstd=self._buf("dec_rstd_head", (32,), torch.float32), n=self.vocab)
 
     def _head(self, x_last: torch.Tensor, logits: torch.Tensor, next_ids: torch.Tensor):
         """final RMSNorm -> lm_head (fp32 logits) -> greedy arg-max."""
         c = self.cfg.decoder
-        hn = ops.rmsnorm(x_last, self.final_norm, c.eps, out=self._buf("head_hn", tuple(x_last.shape)))
-        if x_last.shape[0] <= 32:
-            ops.gemm_skinny(hn, self.lm_head_p if self.lm_head_p is not None else self.lm_head, out=logits)
+        if x_last.shape[0] <= 32 and self.lm_head_c is not None:
+            ops.decode_chain([self._head_phase(x_last, logits)], x_last.shape[0], self._chain_counters(), self.chain_cluster)
         else:
+            hn = ops.rmsnorm(x_last, self.final_norm, c.eps, out=self._buf("head_hn", tuple(x_last.shape)))
             ops.gemm(hn, self.lm_head, out=logits)
         ops.argmax(logits, self.vocab, out=next_ids)
+
+    def _chain_counters(self) -> torch.Tensor:
+        return self._buf("dec_chain_cnt", (16,), torch.int32, zero=True)   # the kernel leaves them zero
 
     def prefill(self, inputs_embeds: torch.Tensor):
         """inputs_embeds bf16 [B,S,D] (consumed in place) -> (last-position logits fp32 [B, vocab], next ids [B])."""
@@ -765,14 +744,105 @@ class CrabEngine:
         return self.logits[:, : self.vocab], self.next_ids
 
     # ---- decode ------------------------------------------------------------------------------------------------
-    def _decode_body(self, B: int, nsplit: int, ws):
-        D = self.cfg.decoder.hidden
+    def _chain_plan(self, B: int, nsplit: int):
+        """The decode step as a list of launches: ('chain', [phases]) / ('attn', layer).  Per layer: ONE attention launch
+        (RoPE + KV append + attention [+ o_proj LoRA pre-pass]) and ONE persistent GEMM-chain launch
+        o_proj -> gate/up+SwiGLU -> down_proj -> next layer's qkv (or final norm + lm_head): 2 launches per layer instead of 8."""
+        key = (B, nsplit)
+        if getattr(self, "_plan_key", None) == key:
+            return self._plan
+        c = self.cfg.decoder
+        D, F, H, KV, hd = c.hidden, c.inter, c.heads, c.kv_heads, c.head_dim
+        nq, nk = H * hd, KV * hd
+        lo, sc = self.lora, self.scaling
         x = self._buf("dec_x", (B, D))
+        qkv = self._buf("dec_qkv", (B, nq + 2 * nk))
+        at = self._buf("dec_attn", (B, nq + self.EXT_O), zero=True)
+        hh = self._buf("dec_h", (B, F))
+        z = {n: self._buf("dec_z_" + n, (32, 128), zero=True) for n in ("qkv", "o", "gu", "d")}
+        rs = {n: self._buf("dec_rstd_" + n, (32,), torch.float32) for n in ("qkv", "gu")}
+        G = H // KV
+        gqa_tc = G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
+        fused = self.fuse_decode_attn and not gqa_tc
+        o_fused_lora = lo and fused and nsplit == 1     # the attention kernel writes o_proj's z columns into at[:, nq:]
+        self._dec_mode = (fused, gqa_tc, o_fused_lora)
+
+        def qkv_phase(L):
+            return ops.ChainPhase(x, L["wqkv_c"], qkv, k=D, z=z["qkv"] if lo else None, kext=self.EXT_QKV if lo else 0,
+                                  stats=L.get("st_qkv"), stats_linears=3 if lo else 0, norm=True, eps=c.eps, lora_scale=sc,
+                                  rstd=rs["qkv"], bias=L["bqkv"])
+
+        plan = [("chain", [qkv_phase(self.layers[0])])]
+        for li, L in enumerate(self.layers):
+            plan.append(("attn", li))
+            if o_fused_lora:
+                o_ph = ops.ChainPhase(at, L["wo_c"], x, k=nq, z=at[:, nq:], kext=self.EXT_O, residual=x)
+            else:
+                o_ph = ops.ChainPhase(at, L["wo_c"], x, k=nq, z=z["o"] if lo else None, kext=self.EXT_O if lo else 0,
+                                      stats=L.get("st_o"), stats_linears=1 if lo else 0, lora_scale=sc, residual=x)
+            gu_ph = ops.ChainPhase(x, L["wgu_c"], hh, k=D, z=z["gu"] if lo else None, kext=self.EXT_GU if lo else 0,
+                                   stats=L.get("st_gu"), stats_linears=2 if lo else 0, norm=True, eps=c.eps, lora_scale=sc,
+                                   rstd=rs["gu"], act=ops.ACT_SWIGLU)
+            d_ph = ops.ChainPhase(hh, L["wd_c"], x, k=F, z=z["d"] if lo else None, kext=self.EXT_D if lo else 0,
+                                  stats=L.get("st_d"), stats_linears=1 if lo else 0, lora_scale=sc, residual=x)
+            last = li + 1 == len(self.layers)
+            tail = self._head_phase(x, self.logits) if last else qkv_phase(self.layers[li + 1])
+            plan.append(("chain", [o_ph, gu_ph, d_ph, tail]))
+        self._plan_key, self._plan = key, plan
+        return plan
+
+    def _decode_body(self, B: int, nsplit: int, ws):
+        c = self.cfg.decoder
+        D, H, KV, hd = c.hidden, c.heads, c.kv_heads, c.head_dim
+        nq, nk = H * hd, KV * hd
+        ctx = self.cfg.max_ctx
+        if not (B <= 32 and self.decode_packed):
+            # more than 32 rows: the dense-GEMM route
+            x = self._buf("dec_x", (B, D))
+            ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)
+            self._decoder_layers(x, B, 1, past=0, past_dev=self.past_dev, len_dev=self.len_dev, nsplit=nsplit, ws=ws, tag="dec")
+            self._head(x, self.logits, self.next_ids)
+            ops.add_scalar_i32(self.past_dev, 1)
+            ops.add_scalar_i32(self.len_dev, 1)
+            return
+        plan = self._chain_plan(B, nsplit)
+        fused, gqa_tc, o_fused_lora = self._dec_mode
+        x = self._buf("dec_x", (B, D))
+        qkv = self._buf("dec_qkv", (B, nq + 2 * nk))
+        at = self._buf("dec_attn", (B, nq + self.EXT_O), zero=True)
+        cnt = self._chain_counters()
+        sc = self.scaling
         ops.set_pdl(self.pdl_chain)
         try:
             ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)  # embed_tokens of the previous arg-max
-            self._decoder_layers(x, B, 1, past=0, past_dev=self.past_dev, len_dev=self.len_dev, nsplit=nsplit, ws=ws, tag="dec")
-            self._head(x, self.logits, self.next_ids)
+            for kind, arg in plan:
+                if kind == "chain":
+                    ops.decode_chain(arg, B, cnt, self.chain_cluster)
+                    continue
+                li = arg
+                L = self.layers[li]
+                if gqa_tc:
+                    # grouped-query decode with enough (batch x kv-head) problems to fill the SMs: the G query heads of a kv
+                    # group are the Sq = G "rows" of one flash-attention problem, so QK^T / PV run on tensor cores
+                    G = H // KV
+                    ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, 1, H, KV, hd, past=0, past_dev=self.past_dev)
+                    ops.flash_attn(qkv, self.k_cache[li], self.v_cache[li], at, B=B, H=KV, KVH=KV, Sq=G, Sk=ctx, head_dim=hd,
+                                   q_strides=(nq + 2 * nk, hd, G * hd), k_strides=(KV * ctx * hd, hd, ctx * hd),
+                                   v_strides=(KV * ctx * hd, hd, ctx * hd), o_strides=(nq + self.EXT_O, hd, G * hd),
+                                   scale=1 / math.sqrt(hd), sk_dev=self.len_dev)
+                elif fused:
+                    # one launch: RoPE on q / new k, cache append, attention over past + 1 keys, and (nsplit == 1) the o_proj
+                    # LoRA pre-pass whose z columns land in at[:, nq:]
+                    ops.attn_decode_fused(qkv, self.rope, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV,
+                                          head_dim=hd, scale=1 / math.sqrt(hd), past_dev=self.past_dev, nsplit=nsplit, workspace=ws,
+                                          ra=L["ra_o"] if o_fused_lora else None, z=at[:, nq:] if o_fused_lora else None, lora_scale=sc,
+                                          lora_ws=self._buf("dec_lora_ws", (B * KV * 11,), torch.float32) if o_fused_lora else None,
+                                          lora_counters=self._buf("dec_lora_cnt", (B,), torch.int32, zero=True) if o_fused_lora else None)
+                else:
+                    ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, 1, H, KV, hd, past=0, past_dev=self.past_dev)
+                    ops.attn_decode(qkv, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV, head_dim=hd,
+                                    scale=1 / math.sqrt(hd), len_dev=self.len_dev, nsplit=nsplit, workspace=ws)
+            ops.argmax(self.logits, self.vocab, out=self.next_ids)
             ops.add_scalar_i32(self.past_dev, 1)
             ops.add_scalar_i32(self.len_dev, 1)
         finally:
@@ -878,7 +948,9 @@ class CrabEngine:
             if return_logits:
                 all_logits.append(logits.clone())
             if capture_hidden:
-                steps_h.append(self._buf("head_hn", (B, self.cfg.decoder.hidden)).clone())
+                # HF's last hidden state of the step: the final norm of the residual stream the decode step left in dec_x
+                # (the chain applies that norm inside the lm_head epilogue and never materialises it)
+                steps_h.append(ops.rmsnorm(self._buf("dec_x", (B, self.cfg.decoder.hidden)), self.final_norm, self.cfg.decoder.eps))
         if eos is not None:
             hist = torch.stack(alive).cpu().tolist()
             steps = (hist.index(False) + 1) if False in hist else len(hist)

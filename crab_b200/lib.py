@@ -83,6 +83,28 @@ class SkinnyArgs(C.Structure):
     ]
 
 
+class ChainPhase(C.Structure):
+    _fields_ = [
+        ("X", C.c_void_p), ("ldx", C.c_int32), ("K", C.c_int32),
+        ("Z", C.c_void_p), ("ldz", C.c_int32), ("Kext", C.c_int32),
+        ("W_packed", C.c_void_p),
+        ("stats_packed", C.c_void_p), ("stats_linears", C.c_int32), ("norm", C.c_int32),
+        ("eps", C.c_float), ("lora_scale", C.c_float),
+        ("rstd", C.c_void_p),
+        ("C", C.c_void_p), ("ldc", C.c_int32), ("N", C.c_int32), ("out_dtype", C.c_int32), ("act", C.c_int32),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("ldr", C.c_int32),
+    ]
+
+
+class ChainArgs(C.Structure):
+    _fields_ = [
+        ("phase", ChainPhase * 4),
+        ("n_phases", C.c_int32), ("M", C.c_int32), ("cluster", C.c_int32), ("max_clusters", C.c_int32),
+        ("counters", C.c_void_p),
+    ]
+
+
 class DecodeFusedArgs(C.Structure):
     _fields_ = [
         ("qkv", C.c_void_p), ("ldq", C.c_int32), ("cos_sin", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),

@@ -533,6 +533,76 @@ def row_norm_loraz(x: torch.Tensor, *, gamma: Optional[torch.Tensor] = None, eps
     count_launches(1)
 
 
+# ---- decode-step GEMM chain (csrc/decode_chain.cu) ---------------------------------------------------------------------
+def pack_chain_stats(ra: torch.Tensor, gamma: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Router/A rows [11 * linears, K] (rows of linear g: 3 lora_route rows, then 8 lora_A rows) -> the stats stream of
+    crab_decode_chain: [K / 64] blocks of 40 x 64 bf16 (rows past 11 * linears zero), each block pre-swizzled exactly like a
+    weight tile (16-byte chunk c of row r stored at c ^ (r & 7)).  `gamma` (RMSNorm scale) is folded into the columns.
+    Pure data movement at load time."""
+    _req_cuda(ra, gamma)
+    rows, K = ra.shape
+    assert rows <= 33 and K % 64 == 0
+    dense = torch.zeros((40, K), device=ra.device, dtype=torch.float32)
+    dense[:rows] = ra.float() if gamma is None else ra.float() * gamma.float()[None, :]
+    t = dense.to(torch.bfloat16).view(40, K // 64, 8, 8).permute(1, 0, 2, 3)                 # [kb, row, chunk, 8]
+    r = torch.arange(40, device=ra.device)
+    src_chunk = torch.arange(8, device=ra.device)[None, :] ^ (r[:, None] & 7)              # stored chunk cs holds source cs ^ (r & 7)
+    out = torch.gather(t, 2, src_chunk[None, :, :, None].expand(K // 64, 40, 8, 8)).contiguous()
+    assert out.data_ptr() % 128 == 0
+    return out.view(-1)
+
+
+class ChainPhase:
+    """One linear of a crab_decode_chain launch (see include/crab_b200.h).  Tensors are kept alive by the caller."""
+
+    def __init__(self, x: torch.Tensor, w: "PackedWeight", out: torch.Tensor, *, k: int, z: Optional[torch.Tensor] = None, kext: int = 0,
+                 stats: Optional[torch.Tensor] = None, stats_linears: int = 0, norm: bool = False, eps: float = 0.0,
+                 lora_scale: float = 1.0, rstd: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                 residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, n: Optional[int] = None):
+        _req_cuda(x, w.data, out, z, stats, rstd, bias, residual)
+        assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and x.shape[1] >= k
+        assert w.K == k + kext, (w.K, k, kext)
+        self.x, self.w, self.out, self.k, self.z, self.kext = x, w, out, k, z, kext
+        self.stats, self.stats_linears, self.norm, self.eps, self.lora_scale = stats, stats_linears, norm, eps, lora_scale
+        self.rstd, self.bias, self.residual, self.act, self.n = rstd, bias, residual, act, (n if n is not None else w.N)
+
+    def fill(self, p: "_l.ChainPhase"):
+        p.X, p.ldx, p.K = _ptr(self.x), self.x.stride(0), self.k
+        p.Z, p.ldz, p.Kext = _ptr(self.z), (self.z.stride(0) if self.z is not None else 0), self.kext
+        p.W_packed = _ptr(self.w.data)
+        p.stats_packed, p.stats_linears, p.norm = _ptr(self.stats), self.stats_linears, 1 if self.norm else 0
+        p.eps, p.lora_scale = self.eps, self.lora_scale
+        p.rstd = _ptr(self.rstd)
+        p.C, p.ldc, p.N = _ptr(self.out), self.out.stride(0), self.n
+        p.out_dtype = BF16 if self.out.dtype == torch.bfloat16 else F32
+        p.act = self.act
+        p.bias = _ptr(self.bias)
+        p.residual, p.ldr = _ptr(self.residual), (self.residual.stride(0) if self.residual is not None else 0)
+
+    def weight_bytes(self) -> float:
+        return 2.0 * self.w.N * self.w.K + (self.stats.numel() * 2.0 if self.stats is not None else 0.0)
+
+
+def decode_chain(phases, M: int, counters: torch.Tensor, cluster: int = 0, max_clusters: int = 0, tag: str = "crab_decode_chain"):
+    """One persistent launch over up to four dependent decode-step linears (M <= 32 rows)."""
+    assert 1 <= len(phases) <= 4 and counters.dtype == torch.int32 and counters.numel() >= 9
+    _req_cuda(counters)
+    a = _l.ChainArgs()
+    for i, ph in enumerate(phases):
+        ph.fill(a.phase[i])
+    a.n_phases, a.M, a.cluster, a.max_clusters, a.counters = len(phases), M, cluster, max_clusters, _ptr(counters)
+    nbytes = sum(ph.weight_bytes() for ph in phases)
+    with _timed(tag, sum(2.0 * M * ph.w.N * ph.w.K for ph in phases), nbytes):
+        _l.check(_l.load().crab_decode_chain(C.byref(a), _stream()), "crab_decode_chain")
+    count_launches(1)
+
+
+def decode_chain_max_clusters(cluster: int) -> int:
+    n = C.c_int(0)
+    _l.check(_l.load().crab_decode_chain_max_clusters(_i(cluster), C.byref(n)), "crab_decode_chain_max_clusters")
+    return n.value
+
+
 # ---- segmentation-head helpers (csrc/seg.cu) -------------------------------------------------------------------------
 EW_ADD, EW_RELU, EW_GELU, EW_GATE = 0, 1, 2, 3
 

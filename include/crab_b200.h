@@ -218,6 +218,49 @@ int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, float eps, v
                         int ldra, int groups, void* z, int ldz, float scale, int rows, int cols, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Decode-step GEMM chain (csrc/decode_chain.cu): up to four DEPENDENT M <= 32 linears of one decoder layer in one
+ * persistent launch — o_proj(+residual) -> [RMSNorm] gate/up + SwiGLU -> down_proj(+residual) -> [RMSNorm] qkv of the next
+ * layer (or the final norm + lm_head) — with the weight stream running across the phase boundaries.
+ * replaces: per decode step and layer, LlamaDecoderLayer.forward minus the attention core (models/modeling_llama.py:765-837:
+ *           two LlamaRMSNorm :103-117, o_proj :448-460, LlamaMLP :239-271, next layer's q/k/v projections :368-392; Qwen2:
+ *           models/qwen/modeling_qwen2.py:175-187, 234-237 with q/k/v bias), each linear being the hyper-LoRA Linear.forward of
+ *           peft_hyper/tuners/lora.py:338-369 (router softmax in fp32, r = 8 x 3 experts), and for the last layer
+ *           LlamaModel.norm + lm_head (models/modeling_llama.py:1119, 1254-1261).
+ * Per phase: C[M, N] = epilogue( s[b] * ( X[M, K] . W'[N, K]^T + Z[M, Kext] . Bcat[N, Kext]^T ) ) with
+ *   - W_packed: crab_pack_skinny_weight layout of the row-major [N, K + Kext] matrix [W' | Bcat] (SwiGLU: swiglu_interleave);
+ *     for a normalised phase W' = W * diag(gamma) (RMSNorm scale folded at load time) and s[b] = rstd[b], else s = 1;
+ *   - norm / stats_linears: the phase starts with a statistics item that computes rstd[b] = rsqrt(mean(X[b]^2) + eps) and, for
+ *     each of the `stats_linears` linears sharing X, t = X . [R; A]^T (11 dots), z' = lora_scale * softmax(s * t[0:3])_i *
+ *     t[3 + j] -> Z[b, 24 * linear + 8 * i + j] (bf16; with norm the rows of stats_packed carry gamma as well).  stats_packed:
+ *     [K / 64] blocks of 40 x 64 bf16, rows 11 * linear + j, pre-swizzled like the weights (crab_decode_chain_stats_bytes);
+ *     stats_linears == 0 with Kext > 0 means Z was filled by an earlier kernel (the fused decode attention writes o_proj's z);
+ *   - act CRAB_ACT_SWIGLU (N_out = N / 2), bias fp32 [N], residual bf16 [M, ldr] (may alias C), bf16 or fp32 output.
+ * Phase i + 1 may read what phase i wrote (X / residual); phases of one launch must not write a buffer an earlier phase still
+ * reads.  counters: 9 ints, zero on entry (the kernel leaves them zero).  cluster: K-split = thread-block-cluster size
+ * (1, 2, 4, 8; 0 = 4).  The launch is cooperative in effect: grid = (max co-resident clusters) x cluster, so it must not be
+ * launched concurrently with other work on the same device.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct crab_chain_phase {
+  const void* X; int32_t ldx; int32_t K;          /* bf16 [M, ldx], K % 64 == 0 */
+  const void* Z; int32_t ldz; int32_t Kext;       /* bf16 [M, ldz] z' columns (written by the stats item when stats_linears > 0) */
+  const void* W_packed;
+  const void* stats_packed; int32_t stats_linears; int32_t norm;
+  float eps; float lora_scale;
+  float* rstd;                                    /* 32 floats of scratch (norm phases) */
+  void* C; int32_t ldc; int32_t N; int32_t out_dtype; int32_t act;
+  const float* bias;
+  const void* residual; int32_t ldr;
+} crab_chain_phase;
+typedef struct crab_chain_args {
+  crab_chain_phase phase[4];
+  int32_t n_phases, M, cluster, max_clusters;      /* max_clusters 0 = all that fit */
+  int* counters;
+} crab_chain_args;
+int crab_decode_chain(const crab_chain_args* args, void* stream);
+int crab_decode_chain_stats_bytes(int K, int64_t* bytes);
+int crab_decode_chain_max_clusters(int cluster, int* n);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Front-end preprocessing (the step immediately before the path)
  * crab_kaldi_fbank replaces: dataset/audio_processor.py:29-41 `preprocess` = torchaudio.compliance.kaldi.fbank(
  *           waveform * 2**15, num_mel_bins=128, sample_frequency=16000, frame_length=25, frame_shift=10) [defaults:

@@ -2,7 +2,7 @@
 at the shapes BASELINE.json configs[0]/[1] and scripts/quick_start.py really use, and keep compact samples of every
 stage so that the oracle and the CUDA path can both be pinned at those shapes on a box that has no reference.
 
-    python -m oracle.make_golden_full        # ~10 min, ~20 GB RAM; writes tests/golden/llama_full.pt (~2 MB)
+    python -m oracle.make_golden_full        # ~10 min, ~20 GB RAM; writes tests/golden/full_llama7b.pt (~2 MB)
 
 Shapes (SURVEY.md §8 head): CLIP ViT-L/14 at 224^2, 24 layers, taps hidden_states[14|22|23] (configs/unified_config.py:14);
 BEATs 12 layers; both Q-Formers at bert-base widths; LLaMA-2-7B-dim decoder layers (hidden 4096, ff 11008, 32 heads),
@@ -143,8 +143,8 @@ def main():
         o["hf_bf16_argmax"] = lg.argmax(-1)
         print(f"{vname}: HF-bf16 vs fp32 logits rel_l2 {o['hf_bf16_logits_rel_l2'].tolist()} ({time.time() - t0:.0f} s)", flush=True)
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    torch.save(out, GOLDEN / "llama_full.pt")
-    print(f"wrote {(GOLDEN / 'llama_full.pt').stat().st_size / 1e6:.2f} MB")
+    torch.save(out, GOLDEN / "full_llama7b.pt")
+    print(f"wrote {(GOLDEN / 'full_llama7b.pt').stat().st_size / 1e6:.2f} MB")
 
 
 if __name__ == "__main__":

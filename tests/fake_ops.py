@@ -316,6 +316,53 @@ def gemm_skinny(x, w, *, bias=None, residual=None, act=ACT_NONE, out=None, out_d
     return out
 
 
+def pack_chain_stats(ra, gamma=None):
+    """stands for ops.pack_chain_stats: keeps the dense (gamma-folded) router/A rows; the swizzled stream is a layout detail."""
+    d = ra.float() if gamma is None else ra.float() * gamma.float()[None, :]
+    return d.to(torch.bfloat16)
+
+
+class ChainPhase:
+    def __init__(self, x, w, out, *, k, z=None, kext=0, stats=None, stats_linears=0, norm=False, eps=0.0, lora_scale=1.0,
+                 rstd=None, bias=None, residual=None, act=ACT_NONE, n=None):
+        assert isinstance(w, PackedWeight) and w.K == k + kext and x.shape[1] >= k and x.stride(0) % 8 == 0 and k % 64 == 0 or MIN_K < 64
+        assert stats_linears == 0 or (stats is not None and kext >= 24 * stats_linears and z is not None)
+        assert not norm or rstd is not None
+        self.x, self.w, self.out, self.k, self.z, self.kext = x, w, out, k, z, kext
+        self.stats, self.stats_linears, self.norm, self.eps, self.lora_scale = stats, stats_linears, norm, eps, lora_scale
+        self.rstd, self.bias, self.residual, self.act, self.n = rstd, bias, residual, act, (n if n is not None else w.N)
+
+
+def decode_chain(phases, M, counters, cluster=0, max_clusters=0, tag="crab_decode_chain"):
+    """crab_decode_chain: dependent M <= 32 linears; RMSNorm as rstd in the epilogue (gamma folded into the weights by the
+    caller), hyper-LoRA pre-pass from the statistics rows, z' = scale * softmax(rstd * logits) * u un-normalised."""
+    assert 1 <= len(phases) <= 4 and M <= 32
+    for ph in phases:
+        x = ph.x[:M, : ph.k].float()
+        rstd = torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + ph.eps) if ph.norm else torch.ones(M, 1)
+        if ph.stats_linears:
+            t = (x @ ph.stats[: 11 * ph.stats_linears].float().t()).view(M, ph.stats_linears, 11)
+            r = torch.softmax(t[..., :3] * rstd.unsqueeze(-1), -1) * ph.lora_scale
+            zz = (r.unsqueeze(-1) * t[..., 3:].unsqueeze(-2)).reshape(M, ph.stats_linears * 24)
+            ph.z[:M, : ph.stats_linears * 24] = zz.to(torch.bfloat16)
+        W = ph.w.data
+        y = x @ W[: ph.w.N, : ph.k].float().t()
+        if ph.kext:
+            kx = min(ph.kext, ph.z.shape[1])
+            y = y + ph.z[:M, :kx].float() @ W[: ph.w.N, ph.k: ph.k + kx].float().t()
+        y = y * rstd
+        if ph.act == ACT_SWIGLU:
+            assert ph.w.swiglu and ph.bias is None and ph.residual is None
+            y = _swiglu_packed(y)
+        else:
+            y = y[:, : ph.n]
+            if ph.bias is not None:
+                y = y + ph.bias[: ph.n]
+            if ph.residual is not None:
+                y = y + ph.residual[:M, : ph.n].float()
+        ph.out[:M, : y.shape[1]] = y.to(ph.out.dtype)
+
+
 def argmax(logits, V, out=None):
     r = logits[:, :V].argmax(-1)
     if out is None:

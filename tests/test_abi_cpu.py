@@ -34,14 +34,19 @@ def test_header_is_plain_c_and_struct_layouts_match(lib, tmp_path):
                    ' offsetof(crab_gemm_args, max_ctas), sizeof(crab_attn_args), offsetof(crab_attn_args, B),'
                    ' offsetof(crab_attn_args, bias_table));'
                    'printf("%zu %zu %zu %zu\\n", sizeof(crab_decode_fused_args), offsetof(crab_decode_fused_args, B),'
-                   ' offsetof(crab_decode_fused_args, scale), offsetof(crab_decode_fused_args, lora_counters)); return 0;}\n')
+                   ' offsetof(crab_decode_fused_args, scale), offsetof(crab_decode_fused_args, lora_counters));'
+                   'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(crab_chain_phase), offsetof(crab_chain_phase, rstd),'
+                   ' offsetof(crab_chain_phase, ldr), sizeof(crab_chain_args), offsetof(crab_chain_args, n_phases),'
+                   ' offsetof(crab_chain_args, counters)); return 0;}\n')
     exe = tmp_path / "t"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     got = list(map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()))
     G, A = lib.GemmArgs, lib.AttnArgs
     D = lib.DecodeFusedArgs
+    P, CA = lib.ChainPhase, lib.ChainArgs
     assert got == [ctypes.sizeof(G), G.M.offset, G.max_ctas.offset, ctypes.sizeof(A), A.B.offset, A.bias_table.offset,
-                   ctypes.sizeof(D), D.B.offset, D.scale.offset, D.lora_counters.offset]
+                   ctypes.sizeof(D), D.B.offset, D.scale.offset, D.lora_counters.offset,
+                   ctypes.sizeof(P), P.rstd.offset, P.ldr.offset, ctypes.sizeof(CA), CA.n_phases.offset, CA.counters.offset]
 
 
 def test_error_reporting_without_gpu(lib):

@@ -2,9 +2,11 @@
 real reference and (b) the CPU oracle, stage by stage, on the small golden cases.
 
 Tolerance contract: the GPU path stores bf16 and accumulates fp32; against the fp32 reference the
-expected error is a few bf16 ulps per op, compounding with depth.  Each stage asserts a relative L2 bound and the
-measured value is printed (pytest -s).  Token ids: teacher-forced arg-max must agree wherever the reference's top-2
-logit margin exceeds 4x the measured logit error; free-running ids are compared and reported.
+expected error is a few bf16 ulps per op, compounding with depth.  Each stage asserts a relative L2 bound of 2x the value
+measured on B200 (printed with pytest -s; measured: CLIP tap 5.8e-3, VL 8.8e-3, BEATs 7.1e-3, AL 8.3e-3, inputs_embeds
+7e-3, logits 6.6e-3 / 7.0e-3).  Token ids: teacher-forced arg-max must agree wherever the reference's top-2 logit margin
+exceeds 4x the measured logit error; free-running ids must equal the reference's up to the first non-decisive step.
+The same checks at BASELINE's full shapes live in tests/test_full_shape_gpu.py.
 """
 import pytest
 import torch
@@ -32,20 +34,20 @@ def test_encoders_vs_reference(setup, cuda_dev):
     clip = eng.clip_forward(v).view(v.shape[0], tokens, -1)[:, 1:].reshape(-1, ocfg.clip.hidden)
     e = rel_l2(clip, g["vit_taps"][-1])
     print(f"clip last tap rel_l2={e:.3e}")
-    assert e < 2e-2
+    assert e < 1.2e-2
     vl = eng.encode_video(v)
     e = rel_l2(vl, g["vl_out"])
     print(f"vl_projector rel_l2={e:.3e}")
-    assert e < 3e-2
+    assert e < 1.8e-2
     a = X[0]["<audio>"].to(cuda_dev)
     b, T = eng.beats_forward(a)
     e = rel_l2(b.view(a.shape[0], T, -1), g["beats_out"])
     print(f"beats rel_l2={e:.3e}")
-    assert e < 2e-2
+    assert e < 1.5e-2
     al = eng.encode_audio(a)
     e = rel_l2(al, g["al_out"])
     print(f"al_projector rel_l2={e:.3e}")
-    assert e < 3e-2
+    assert e < 1.7e-2
 
 
 def test_prepare_inputs_vs_reference(setup):
@@ -55,7 +57,7 @@ def test_prepare_inputs_vs_reference(setup):
     assert torch.equal(mask, g["attention_mask"]) and torch.equal(pos, g["position_ids"])
     e = rel_l2(emb, g["inputs_embeds"])
     print(f"inputs_embeds rel_l2={e:.3e}")
-    assert e < 3e-2
+    assert e < 1.5e-2
     # text rows are exact bf16 roundings of the embedding table (pure gather)
     tab = sd["model.embed_tokens.weight"].to(torch.bfloat16)
     assert torch.equal(emb[0, -3:].cpu(), tab[ids[0][-3:]])
@@ -75,7 +77,7 @@ def test_prefill_and_decode_vs_reference(setup, cuda_dev):
     e0 = rel_l2(logits[0], g["prefill_last_logits"])
     e1 = rel_l2(logits[1], g["step1_logits"])
     print(f"prefill logits rel_l2={e0:.3e}; step-1 logits rel_l2={e1:.3e}")
-    assert e0 < 4e-2 and e1 < 4e-2
+    assert e0 < 1.4e-2 and e1 < 1.4e-2
     err = (logits - ref_logits).abs().max().item()
     top2 = ref_logits.topk(2, dim=-1).values
     margin = top2[..., 0] - top2[..., 1]  # (n, b)
@@ -92,11 +94,24 @@ def test_prefill_and_decode_vs_reference(setup, cuda_dev):
 def test_generate_end_to_end(setup):
     g, case, sd, ocfg, ids, X, eng = setup
     n_new = g["generated_ids"].shape[1]
+    ref_ids = g["generated_ids"]
     out = eng.generate(ids, X, n_new).cpu()
-    match = (out == g["generated_ids"]).float().mean().item()
-    print(f"free-running greedy ids: {out.tolist()} vs reference {g['generated_ids'].tolist()} (match {match:.2f})")
-    assert out.shape == g["generated_ids"].shape
-    assert torch.equal(out[:, 0], g["generated_ids"][:, 0]) or match > 0.5
+    match = (out == ref_ids).float().mean().item()
+    print(f"free-running greedy ids: {out.tolist()} vs reference {ref_ids.tolist()} (match {match:.2f})")
+    assert out.shape == ref_ids.shape
+    # every row must reproduce the reference's ids up to its first NON-decisive step: a step is decisive when the fp32
+    # oracle's top-2 margin (teacher-forced on the reference's ids) exceeds 4x the max |dlogit| measured for this engine
+    with torch.no_grad():
+        _, ref_logits = O.greedy_generate(sd, g["inputs_embeds"], ocfg.decoder, n_new, teacher_tokens=ref_ids)
+    _, logits = eng.generate_from_embeds(g["inputs_embeds"].to(eng.dev).to(torch.bfloat16), n_new, return_logits=True,
+                                         teacher_tokens=ref_ids.to(eng.dev))
+    err = (logits.cpu() - ref_logits).abs().max().item()
+    top2 = ref_logits.topk(2, dim=-1).values
+    decisive = ((top2[..., 0] - top2[..., 1]) > 4 * err).t()          # (b, n)
+    for b in range(out.shape[0]):
+        bad = (~decisive[b]).nonzero()
+        k = int(bad[0]) if bad.numel() else n_new
+        assert torch.equal(out[b, :k], ref_ids[b, :k]), (b, k, out[b].tolist(), ref_ids[b].tolist())
 
 
 def test_qwen_decoder_vs_reference(cuda_dev):
@@ -126,7 +141,7 @@ def test_qwen_decoder_vs_reference(cuda_dev):
     logits = logits.cpu()
     e0, e1 = rel_l2(logits[0], g["prefill_last_logits"]), rel_l2(logits[1], g["step1_logits"])
     print(f"qwen prefill logits rel_l2={e0:.3e}; step-1 rel_l2={e1:.3e}")
-    assert e0 < 4e-2 and e1 < 4e-2
+    assert e0 < 1.5e-2 and e1 < 1.5e-2   # measured 7e-3
     err = (logits - ref_logits).abs().max().item()
     top2 = ref_logits.topk(2, dim=-1).values
     decisive = (top2[..., 0] - top2[..., 1]) > 4 * err
@@ -155,7 +170,7 @@ def test_full_width_decoder_layer_vs_oracle(cuda_dev):
                                            teacher_tokens=ref_ids.to(cuda_dev))
     e = [rel_l2(logits[i], ref_logits[i]) for i in range(3)]
     print("full-width logits rel_l2 per step:", ["%.3e" % v for v in e])
-    assert max(e) < 4e-2
+    assert max(e) < 2e-2
 
 
 def test_full_width_qwen7b_layer_vs_oracle(cuda_dev):
@@ -180,7 +195,7 @@ def test_full_width_qwen7b_layer_vs_oracle(cuda_dev):
                                            teacher_tokens=ref_ids.to(cuda_dev))
     e = [rel_l2(logits[i], ref_logits[i]) for i in range(3)]
     print("qwen-7B-width logits rel_l2 per step:", ["%.3e" % v for v in e])
-    assert max(e) < 4e-2
+    assert max(e) < 2e-2
 
 
 def test_batched_generate_with_eos_and_unequal_prompts(cuda_dev):

@@ -3,7 +3,7 @@
 (hidden 4096, ff 11008, 32 heads x 128, vocab 32017) with hyper-LoRA on all seven linears (non-zero lora_B).
 
 Three parties on the same seeded weights / inputs:
-  golden  = outputs of the REAL reference at these shapes (tests/golden/llama_full.pt, oracle/make_golden_full.py),
+  golden  = outputs of the REAL reference at these shapes (tests/golden/full_llama7b.pt, oracle/make_golden_full.py),
   oracle  = oracle/crab_oracle.py run live on the host cores (fp32),
   ours    = crab_b200 on the GPU through the C ABI (bf16 storage, fp32 accumulation).
 Checks: (1) oracle == golden to 2e-4 on every sampled stage (pins the oracle AT FULL SHAPE); (2) ours vs oracle per stage
@@ -44,7 +44,7 @@ def close(a, b, tol=2e-4):
 def full(cuda_dev):
     from crab_b200.engine import CrabEngine
 
-    g = torch.load(GOLDEN / "llama_full.pt", weights_only=False)
+    g = torch.load(GOLDEN / "full_llama7b.pt", weights_only=False)
     case = g["case"]
     sd = O.strip_peft_prefix(synth.synth_state_dict(g["manifest"], case["weight_seed"]))
     ocfg = oracle_cfg(case, g["special_ids"])
@@ -117,8 +117,9 @@ def test_full_shape_single_sample(full, cuda_dev, monkeypatch, vname):
     print(f"[{vname}] rel_l2 ours vs oracle: clip tap23 {e_tap:.3e}  vl_out {e_vl:.3e}  beats {e_beats:.3e}  al_out {e_al:.3e}  "
           f"inputs_embeds {e_emb:.3e}")
     assert torch.equal(mask, prep["attention_mask"]) and torch.equal(pos, prep["position_ids"])
-    # bounds = 2x the values measured on B200 (round 2): tap 1.1e-2, vl 1.0e-2, beats 9e-3, al 9e-3, embeds 9e-3
-    assert e_tap < 2.2e-2 and e_vl < 2.0e-2 and e_beats < 1.8e-2 and e_al < 1.8e-2 and e_emb < 1.8e-2
+    # bounds = 2x the values measured on B200 (round 2, both variants): tap 1.06e-2, vl 8.5e-3, beats 1.17e-2, al 8.5e-3,
+    # inputs_embeds 7.6e-3
+    assert e_tap < 2.2e-2 and e_vl < 1.7e-2 and e_beats < 2.4e-2 and e_al < 1.7e-2 and e_emb < 1.6e-2
 
     # ---- (3) decoder on the oracle's inputs_embeds: prompt pass + 16 teacher-forced steps -------------------------------
     out, logits = eng.generate_from_embeds(emb_o.to(cuda_dev).to(torch.bfloat16), n_new, use_graph=True, return_logits=True,
@@ -175,7 +176,7 @@ def test_full_shape_bs4_unequal_prompts(full, cuda_dev, monkeypatch):
     assert torch.equal(mask, prep["attention_mask"]) and torch.equal(pos, prep["position_ids"])
     e_emb = [rel_l2(emb[b], emb_o[b]) for b in range(4)]
     print("bs4 inputs_embeds rel_l2 per sample:", ["%.3e" % e for e in e_emb])
-    assert max(e_emb) < 1.8e-2
+    assert max(e_emb) < 1.1e-2   # measured 5.1e-3 (most rows of a 512-token prompt are exact embedding gathers)
     n_new = 4
     with torch.no_grad():
         o_ids, o_logits = O.greedy_generate(sd, emb_o, ocfg.decoder, n_new)
