@@ -514,7 +514,7 @@ def main():
         # Decode split: the streaming kernels (>= 20 us each: GEMMs, attention) keep their measured device time; the event
         # pair around a 3 us kernel mostly measures launch gaps, so the light kernels share whatever the graph step has left.
         def _heavy(tag):
-            return ("gemm" in tag) or ("attn" in tag)
+            return ("gemm" in tag) or ("attn" in tag) or ("chain" in tag)
         heavy_ms = sum(d["ms"] for k, d in kd.items() if _heavy(k))
         light_ms = sum(d["ms"] for k, d in kd.items() if not _heavy(k))
         if heavy_ms < graph_step_ms and light_ms > 0:
@@ -534,7 +534,7 @@ def main():
         if top.startswith("decode:"):
             d = kd[top[len("decode:"):]]
             scale = graph_step_ms / max(dec_eager_ms, 1e-9)
-            if "gemm" in top:
+            if "gemm" in top or "chain" in top:
                 ach = d["bytes"] / (d["ms"] * scale * 1e-3) / 1e9
             else:
                 ach = kv_bytes / (d["ms"] * scale * 1e-3) / 1e9 if "attn_decode" in top else 0.0
@@ -575,7 +575,7 @@ def main():
         rooflines = {
             "prefill_gemm_tcgen05<256>": _roof("gemm_bf16_tcgen05<256>", kt),
             "prefill_flash_attn_tcgen05<128>": _roof("crab_flash_attn_tcgen05<128>", kt),
-            "decode_gemm_skinny_tcgen05": _roof("gemm_skinny_tcgen05", kd_step, dscale, "hbm"),
+            "decode_gemm_chain": _roof("crab_decode_chain", kd_step, dscale, "hbm"),
             "decode_attention": _roof("crab_attn_decode_fused" if "crab_attn_decode_fused" in kd_step else "crab_attn_decode",
                                       kd_step, dscale, "hbm"),
         }

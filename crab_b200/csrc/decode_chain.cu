@@ -7,9 +7,14 @@
 //
 // Structure
 //   * persistent clusters of S CTAs (1 CTA / SM, ~220 KB smem).  A work item = one 128-row weight tile; the S ranks of the
-//     cluster split its K range, accumulate D[128 rows, 32 batch] in TMEM (swap-AB tcgen05.mma M128 N32 K16, double-buffered
-//     accumulator) and reduce-scatter the partials through distributed shared memory (rank j owns 128/S rows), exactly like
-//     gemm_skinny.cu but with mbarriers instead of cluster barriers so the pipeline never drains between items.
+//     cluster split its K range, accumulate D[batch (32 of 128 lanes), 128 weight rows] in TMEM (tcgen05.mma M128 N128 K16,
+//     double-buffered accumulator) and reduce-scatter the partials through distributed shared memory (rank j owns 128/S
+//     rows) with mbarriers instead of cluster barriers, so the pipeline never drains between items.
+//     The weights are the B (N-side) operand on purpose: with the weights on the M side (swap-AB, N = 32 batch columns, as in
+//     gemm_skinny.cu) every K=16 MMA re-reads its 128 x 32 B A slice from shared memory at ~32 B/clk and the issue loop, not
+//     HBM, bounds the stream (measured: 0.31 us per 16 KB k-block = 52 GB/s per SM; profiles/r03_chain_trace.txt); as the B
+//     operand the same 16 KB go through in 4 x 64 clk.  The 96 unused A rows are whatever follows the 4 KB X tile in shared
+//     memory: their D lanes are never read.
 //   * warp roles: warp 0 streams WEIGHTS (1-D cp.async.bulk of pre-swizzled 16 KB blocks, crab_pack_skinny_weight layout)
 //     through a 7-stage ring and never waits for anything but a free slot — weights do not depend on activations, so the ring
 //     keeps filling across phase boundaries; warp 6 loads the ACTIVATION tiles (TMA 2-D, 4 KB) into the same stages and is the
@@ -20,7 +25,7 @@
 //     the phases in the same order, so the waits cannot cycle.
 //   * RMSNorm never materialises: gamma is folded into the packed weights at load time and rstd[b] scales the accumulator
 //     column in the epilogue.  rstd and the hyper-LoRA pre-pass  t = x . [R;A]^T  (11 dots per wrapped linear) come from a
-//     STATS ITEM, the first item of the phase: its A tile is [x rows (32) ; gamma*[R;A] rows (<= 33)], so one extra MMA chain
+//     STATS ITEM, the first item of the phase: its B tile is [x rows (32) ; gamma*[R;A] rows (<= 33)], so one extra MMA chain
 //     gives  diag(x x^T) = sum x^2  and all the dots; rank 0 of that cluster turns them into rstd and z' = scale * softmax(rstd
 //     * logits)_i * u_j (un-normalised u: the epilogue's rstd multiplies the whole accumulator, z' included), writes them to
 //     global memory and raises zflag[phase].  The K-EXTENSION k-blocks of every other item (B_0|B_1|B_2 columns of the packed
@@ -33,23 +38,28 @@
 namespace crab {
 
 static constexpr int DC_BM = 128, DC_MB = 32, DC_BK = 64;
-static constexpr int DC_STAGES = 7;
+static constexpr int DC_MAX_STAGES = 10;   // ring depth is a launch parameter: as many 20 KB stages as fit next to the buffers below
 static constexpr int DC_W_BYTES = DC_BM * DC_BK * 2;      // 16 KB
 static constexpr int DC_X_BYTES = DC_MB * DC_BK * 2;      // 4 KB
 static constexpr int DC_STAGE_BYTES = DC_W_BYTES + DC_X_BYTES;
-static constexpr int DC_PSTRIDE = 36;                     // floats per partial row (32 + pad, 16-byte aligned)
-static constexpr int DC_PART_BYTES = DC_BM * DC_PSTRIDE * 4;
 static constexpr int DC_SROWS = 40;                       // router/A rows streamed per k-block of a stats item (33 used)
 static constexpr int DC_S_BYTES = DC_SROWS * DC_BK * 2;   // 5 KB
 static constexpr int DC_MAX_S = 8;
-static constexpr int DC_SBUF_ROW_BYTES = DC_SROWS * DC_PSTRIDE * 4;            // per source rank
-static constexpr int DC_SBUF_BYTES = DC_MAX_S * (DC_SBUF_ROW_BYTES + 32 * 4);  // rows + diag
+static constexpr int DC_SGROUPS = 11;                     // stats buffer per source rank: [11 groups of 4][batch row 32][4]: 40 dots, sum x^2, pad
+static constexpr int DC_SBUF_PER_RANK = DC_SGROUPS * 32 * 16;
+// partial buffer of a reduce-scatter owner: [source rank][R / 4 row groups][batch row 32][4 floats], R = 128 / S rows owned.
+// One warp-wide 16-byte store (lane = batch row) covers 512 CONTIGUOUS bytes of the owner's shared memory: DSMEM moves whole
+// 128-byte lines, a row-major [batch][row] layout sends 32 lines for the same 512 bytes (measured: 2.0 us -> per scatter).
+__host__ __device__ constexpr int dc_part_bytes(int) { return DC_BM * 32 * 4; }
 static constexpr int DC_THREADS = 7 * 32;
-static constexpr int DC_OFF_PART = DC_STAGES * DC_STAGE_BYTES;
-static constexpr int DC_OFF_SBUF = DC_OFF_PART + 2 * DC_PART_BYTES;
-static constexpr int DC_OFF_BAR = DC_OFF_SBUF + DC_SBUF_BYTES;
-static constexpr int DC_SMEM = DC_OFF_BAR + 256 + 1024;
+static constexpr int DC_BAR_BYTES = 256;
+static constexpr int DC_SMEM_MAX = 227 * 1024;
 static constexpr int DC_MAX_PHASES = 4;
+// dynamic shared memory: [ring: stages x 20 KB][partials: 2 x ~18 KB][stats: S x 5.5 KB][barriers]
+__host__ __device__ constexpr int dc_off_part(int stages) { return stages * DC_STAGE_BYTES; }
+__host__ __device__ constexpr int dc_off_sbuf(int stages, int S) { return dc_off_part(stages) + 2 * dc_part_bytes(S); }
+__host__ __device__ constexpr int dc_off_bar(int stages, int S) { return dc_off_sbuf(stages, S) + S * DC_SBUF_PER_RANK; }
+__host__ __device__ constexpr int dc_smem(int stages, int S) { return dc_off_bar(stages, S) + DC_BAR_BYTES + 1024; }
 
 struct alignas(64) DcPhase {
   CUtensorMap tmap_x;              // main activation [M, K]
@@ -70,8 +80,14 @@ struct alignas(64) DcPhase {
 struct DcParams {
   DcPhase ph[DC_MAX_PHASES];
   int n_phases, M;
-  int* counters;   // [0..3] done, [4..7] zflag, [8] exit count; all zero on entry, left zero on exit
+  int stages;      // ring depth
+  int lag;         // items by which the K-extension runs trail their item (env CRAB_CHAIN_LAG, default 2; 4 accumulators allow <= 2)
+  int debug;       // timing experiments only (env CRAB_CHAIN_DEBUG): 1 skip publish (fence + counter), 2 skip X loads, 4 skip MMAs
+  unsigned long long* trace;   // diagnostics (env CRAB_CHAIN_TRACE = device address): [cta][32 items][16] globaltimer stamps
+  int* counters;   // slots of DC_CSTRIDE ints (one 128-byte line each, so pollers of one flag do not queue behind the atomics of
+                   // another): [0..3] done, [4..7] zflag, [8] exit count; all zero on entry, left zero on exit
 };
+static constexpr int DC_CSTRIDE = 32;
 
 __device__ __forceinline__ uint32_t dc_rank() {
   uint32_t r;
@@ -149,6 +165,7 @@ __device__ __forceinline__ float dc_ld_cg_f32(const float* p) {
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void dc_arrive_remote_n(uint32_t cluster_addr) { dc_arrive_remote(cluster_addr); }
 __device__ __forceinline__ uint2 dc_ld_cg_u2(const void* p) {
   uint2 v;
   asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
@@ -158,34 +175,127 @@ __device__ __forceinline__ void dc_named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// One run of k-blocks of one item, issued back to back by this CTA.
+struct DcSeg {
+  int ph, tile, kb0, kb1;
+  uint32_t it;                      // running item index of this CTA: accumulator it & 3, barrier parity (it >> 2) & 1
+  bool stats, ext, first, last;     // first: starts the item's accumulation; last: the accumulator is complete after this run
+};
+// The static block sequence of one CTA, shared by the weight producer, the activation producer and the MMA issuer.
+// Items are dealt to clusters round-robin, continuing across phases.  The rank that owns the K-extension k-blocks (the last
+// one) runs them ONE ITEM LATE:  main(0) main(1) ext(0) main(2) ext(1) ... ext(m-1)  — the z' columns they need appear only
+// after the phase's statistics item has gone through the whole MMA -> DSMEM -> softmax -> flag chain (4-7 us), and in item
+// order that rank (and, through the reduce-scatter, its whole cluster) would sit idle for it at the start of every phase.
+// Four TMEM accumulators keep the deferred item, the running one and the one being drained apart.
+struct DcSeq {
+  const DcParams* p;
+  int rank, S, C, cluster_id;
+  int ph, m, first, s, nseg;
+  uint32_t it0;
+  bool lag;
+  __device__ void open_phase() {
+    const DcPhase& P = p->ph[ph];
+    const int n_items = P.n_tiles + P.has_stats;
+    first = cluster_id - P.first_cluster;
+    if (first < 0) first += C;
+    m = first < n_items ? (n_items - 1 - first) / C + 1 : 0;
+    lag = (rank == S - 1) && (P.kb_total > P.kb_main) && m > 0;
+    nseg = lag ? 2 * m : m;
+    s = 0;
+  }
+  __device__ void init(const DcParams* p_, int rank_, int S_, int C_, int cluster_id_) {
+    p = p_; rank = rank_; S = S_; C = C_; cluster_id = cluster_id_;
+    ph = 0; it0 = 0;
+    open_phase();
+  }
+  __device__ bool next(DcSeg& g) {
+    for (;;) {
+      while (s >= nseg) {
+        it0 += (uint32_t)m;
+        if (++ph >= p->n_phases) return false;
+        open_phase();
+      }
+      const DcPhase& P = p->ph[ph];
+      // lagged order with LAG = 2:  M0 M1 M2 E0 M3 E1 M4 E2 ... E(m-1): slot s holds M(s) while s < min(m, LAG + 1); after
+      // that main and extension runs alternate (extension first) until the mains run out, then the remaining extensions.
+      int k;
+      bool ext_part = false;
+      if (!lag) {
+        k = s;
+      } else {
+        const int lead = m < p->lag + 1 ? m : p->lag + 1;     // mains issued before the first extension
+        if (s < lead) {
+          k = s;
+        } else {
+          const int r = s - lead;                              // 0: E0, 1: M(lead), 2: E1, 3: M(lead+1), ...
+          const int mains_left = m - lead;
+          if (r < 2 * mains_left) {
+            if (r & 1) k = lead + (r >> 1);
+            else { k = r >> 1; ext_part = true; }
+          } else {
+            k = mains_left + (r - 2 * mains_left);
+            ext_part = true;
+          }
+        }
+      }
+      ++s;
+      const int item = first + k * C;
+      g.ph = ph;
+      g.it = it0 + (uint32_t)k;
+      g.stats = P.has_stats && item == 0;
+      g.tile = item - P.has_stats;
+      if (g.stats) {
+        if (ext_part) continue;                     // a statistics item has no K-extension
+        g.kb0 = rank * P.kb_main / S; g.kb1 = (rank + 1) * P.kb_main / S;
+        g.ext = false; g.first = true; g.last = true;
+      } else if (!lag) {
+        g.kb0 = rank * P.kb_total / S; g.kb1 = (rank + 1) * P.kb_total / S;
+        g.ext = false; g.first = true; g.last = true;
+      } else if (!ext_part) {
+        g.kb0 = rank * P.kb_total / S; g.kb1 = P.kb_main;
+        g.ext = false; g.first = true; g.last = false;
+      } else {
+        g.kb0 = P.kb_main; g.kb1 = P.kb_total;
+        g.ext = true; g.first = false; g.last = true;
+      }
+      return true;
+    }
+  }
+};
+
+// warps 0-3: epilogue (warp 0 owns TMEM lanes 0..31 = the batch rows and drains the accumulator), warp 4: weight producer,
+// warp 5: MMA issuer + TMEM owner, warp 6: activation producer
 __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __grid_constant__ DcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + DC_OFF_BAR;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (DC_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * DC_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * DC_STAGES + 2 + a); };
-  auto pfull_bar = [&](int b) { return bar_base + 8u * (2 * DC_STAGES + 4 + b); };
-  const uint32_t sfull_bar = bar_base + 8u * (2 * DC_STAGES + 6);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * DC_STAGES + 7);
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = (int)dc_nrank();
+  const int NST = p.stages;
+  const int OFF_PART = dc_off_part(NST), OFF_SBUF = dc_off_sbuf(NST, S), PART_BYTES = dc_part_bytes(S);
+  const uint32_t bar_base = smem_base + dc_off_bar(NST, S);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (DC_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * DC_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * DC_MAX_STAGES + 4 + a); };
+  auto pfull_bar = [&](int b) { return bar_base + 8u * (2 * DC_MAX_STAGES + 8 + b); };
+  const uint32_t sfull_bar = bar_base + 8u * (2 * DC_MAX_STAGES + 10);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * DC_MAX_STAGES + 11);
   const int rank = (int)dc_rank();
   const int cluster_id = blockIdx.x / S;
   const int C = gridDim.x / S;
-  const int R = DC_BM / S;   // tile rows owned by one rank in the reduce-scatter
+  const int R = DC_BM / S;    // tile rows owned by one rank in the reduce-scatter
+  const int RG = R >> 2;      // 4-row groups per rank
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     for (int i = 0; i < p.n_phases; ++i) { tma_prefetch_desc(&p.ph[i].tmap_x); tma_prefetch_desc(&p.ph[i].tmap_z); }
-    for (int s = 0; s < DC_STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); mbar_init(pfull_bar(a), 128); }
-    mbar_init(sfull_bar, 128u * (uint32_t)S);
+    for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 4; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 1); }
+    for (int a = 0; a < 2; ++a) mbar_init(pfull_bar(a), (uint32_t)S);
+    mbar_init(sfull_bar, (uint32_t)S);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
+  if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   dc_cluster_sync();   // every CTA's barriers exist before anybody signals across the cluster
@@ -193,125 +303,136 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0) {
+  if (warp == 4) {
     if (lane == 0) {
       // ===================== weight producer: never waits for activations =====================
-      uint32_t stage = 0, phase = 0;
-      for (int ph = 0; ph < p.n_phases; ++ph) {
+      // The statistics item heads every phase's critical path and its stream is tiny: pull it into L2 now, so that its
+      // ring refills do not queue behind the weight stream's HBM traffic when the phase opens.
+      for (int ph = 1; ph < p.n_phases; ++ph) {
         const DcPhase& P = p.ph[ph];
-        const int n_items = P.n_tiles + P.has_stats;
-        int first = cluster_id - P.first_cluster;
-        if (first < 0) first += C;
-        for (int item = first; item < n_items; item += C) {
-          const bool is_stats = P.has_stats && item == 0;
-          const int tile = item - P.has_stats;
-          const int KBx = is_stats ? P.kb_main : P.kb_total;
-          const int kb0 = rank * KBx / S, kb1 = (rank + 1) * KBx / S;
-          for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            const uint32_t slot = smem_base + stage * DC_STAGE_BYTES;
-            if (is_stats) {
-              if (P.stats_w) {
-                mbar_arrive_expect_tx(full_bar(stage), DC_S_BYTES);
-                bulk_load_1d_hint(slot + DC_X_BYTES, P.stats_w + (size_t)kb * (DC_SROWS * DC_BK), DC_S_BYTES, full_bar(stage), kEvictFirst);
-              } else {
-                mbar_arrive(full_bar(stage));
-              }
+        int f = cluster_id - P.first_cluster;
+        if (f < 0) f += C;
+        if (P.has_stats && P.stats_w && f == 0) {
+          const int kb0 = rank * P.kb_main / S, kb1 = (rank + 1) * P.kb_main / S;
+          for (int kb = kb0; kb < kb1; kb += 3)
+            bulk_prefetch_l2(P.stats_w + (size_t)kb * (DC_SROWS * DC_BK), (uint32_t)((kb1 - kb < 3 ? kb1 - kb : 3) * DC_S_BYTES));
+        }
+      }
+      DcSeq seq;
+      seq.init(&p, rank, S, C, cluster_id);
+      DcSeg g;
+      uint32_t stage = 0, phase = 0;
+      while (seq.next(g)) {
+        const DcPhase& P = p.ph[g.ph];
+        for (int kb = g.kb0; kb < g.kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t slot = smem_base + stage * DC_STAGE_BYTES;
+          if (g.stats) {
+            if (P.stats_w) {
+              mbar_arrive_expect_tx(full_bar(stage), DC_S_BYTES);
+              bulk_load_1d_hint(slot + DC_X_BYTES, P.stats_w + (size_t)kb * (DC_SROWS * DC_BK), DC_S_BYTES, full_bar(stage), kEvictFirst);
             } else {
-              mbar_arrive_expect_tx(full_bar(stage), DC_W_BYTES);
-              bulk_load_1d_hint(slot, P.w + ((size_t)tile * P.kb_total + kb) * (DC_BM * DC_BK), DC_W_BYTES, full_bar(stage), kEvictFirst);
+              mbar_arrive(full_bar(stage));
             }
-            if (++stage == DC_STAGES) { stage = 0; phase ^= 1; }
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), DC_W_BYTES);
+            bulk_load_1d_hint(slot, P.w + ((size_t)g.tile * P.kb_total + kb) * (DC_BM * DC_BK), DC_W_BYTES, full_bar(stage), kEvictFirst);
           }
+          if (++stage == (uint32_t)NST) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 6) {
     if (lane == 0) {
       // ===================== activation producer: the only role that waits for other CTAs' results =====================
+      DcSeq seq;
+      seq.init(&p, rank, S, C, cluster_id);
+      DcSeg g;
       uint32_t stage = 0, phase = 0;
-      for (int ph = 0; ph < p.n_phases; ++ph) {
-        const DcPhase& P = p.ph[ph];
-        const int n_items = P.n_tiles + P.has_stats;
-        int first = cluster_id - P.first_cluster;
-        if (first < 0) first += C;
-        bool dep_ok = (P.expected_prev == 0), z_ok = !P.has_stats;
-        for (int item = first; item < n_items; item += C) {
-          const bool is_stats = P.has_stats && item == 0;
-          const int KBx = is_stats ? P.kb_main : P.kb_total;
-          const int kb0 = rank * KBx / S, kb1 = (rank + 1) * KBx / S;
-          for (int kb = kb0; kb < kb1; ++kb) {
-            if (!dep_ok) {   // the previous phase's outputs (this phase's activations) are complete and visible
-              dc_spin_ge(p.counters + (ph - 1), P.expected_prev);
-              dc_fence_proxy_async();
-              dep_ok = true;
-            }
-            const bool ext = kb >= P.kb_main;
-            if (ext && !z_ok) {   // z' of this phase comes from its stats item
-              dc_spin_ge(p.counters + 4 + ph, 1);
-              dc_fence_proxy_async();
-              z_ok = true;
-            }
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            const uint32_t slot = smem_base + stage * DC_STAGE_BYTES;
-            if (is_stats) {
-              mbar_arrive_expect_tx(full_bar(stage), 2 * DC_X_BYTES);
-              tma_load_2d_hint(slot + DC_W_BYTES, &P.tmap_x, full_bar(stage), kb * DC_BK, 0, kEvictLast);   // B operand
-              tma_load_2d_hint(slot, &P.tmap_x, full_bar(stage), kb * DC_BK, 0, kEvictLast);                // A rows 0..31
-            } else {
-              mbar_arrive_expect_tx(full_bar(stage), DC_X_BYTES);
-              if (ext) tma_load_2d_hint(slot + DC_W_BYTES, &P.tmap_z, full_bar(stage), (kb - P.kb_main) * DC_BK, 0, kEvictLast);
-              else tma_load_2d_hint(slot + DC_W_BYTES, &P.tmap_x, full_bar(stage), kb * DC_BK, 0, kEvictLast);
-            }
-            if (++stage == DC_STAGES) { stage = 0; phase ^= 1; }
+      int dep_ph = 0, z_ph = -1;   // phases whose inputs / z' are known to be complete
+      while (seq.next(g)) {
+        const DcPhase& P = p.ph[g.ph];
+        if (g.ph > dep_ph) {   // the previous phase's outputs (this phase's activations) are complete and visible
+          dc_spin_ge(p.counters + DC_CSTRIDE * (g.ph - 1), P.expected_prev);
+          dc_fence_proxy_async();
+          dep_ph = g.ph;
+        }
+        if (g.ext && P.has_stats && z_ph < g.ph) {   // z' of this phase comes from its statistics item
+          dc_spin_ge(p.counters + DC_CSTRIDE * (4 + g.ph), 1);
+          dc_fence_proxy_async();
+          z_ph = g.ph;
+        }
+        for (int kb = g.kb0; kb < g.kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t slot = smem_base + stage * DC_STAGE_BYTES;
+          if (p.debug & 2) {
+            mbar_arrive(full_bar(stage));
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), DC_X_BYTES);
+            if (g.ext) tma_load_2d_hint(slot + DC_W_BYTES, &P.tmap_z, full_bar(stage), (kb - P.kb_main) * DC_BK, 0, kEvictLast);
+            else tma_load_2d_hint(slot + DC_W_BYTES, &P.tmap_x, full_bar(stage), kb * DC_BK, 0, kEvictLast);
           }
+          if (++stage == (uint32_t)NST) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc_bf16_f32(DC_BM, DC_MB);
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (int ph = 0; ph < p.n_phases; ++ph) {
-        const DcPhase& P = p.ph[ph];
-        const int n_items = P.n_tiles + P.has_stats;
-        int first = cluster_id - P.first_cluster;
-        if (first < 0) first += C;
-        for (int item = first; item < n_items; item += C, ++it) {
-          const bool is_stats = P.has_stats && item == 0;
-          const int KBx = is_stats ? P.kb_main : P.kb_total;
-          const int kb0 = rank * KBx / S, kb1 = (rank + 1) * KBx / S;
-          const uint32_t acc = it & 1;
-          mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+      // ===================== MMA issuer: D[batch lanes, 128 weight rows] += X_tile[128 (32 valid), 64] . W_tile[128, 64]^T ====
+      constexpr uint32_t idesc = make_idesc_bf16_f32(DC_BM, DC_BM);
+      constexpr uint32_t idesc_x = make_idesc_bf16_f32(DC_BM, 32);        // statistics: x x^T        -> columns 0..31
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(DC_BM, 48);        // statistics: x [R;A]^T   -> columns 32..79
+      DcSeq seq;
+      seq.init(&p, rank, S, C, cluster_id);
+      DcSeg g;
+      uint32_t stage = 0, phase = 0;
+      while (seq.next(g)) {
+        const uint32_t acc = g.it & 3;
+        unsigned long long* tr = (p.trace && g.it < 32) ? p.trace + ((size_t)blockIdx.x * 32 + g.it) * 16 : nullptr;
+        if (g.first) {
+          if (tr) tr[8] = globaltimer_ns();
+          mbar_wait(tempty_bar(acc), ((g.it >> 2) & 1) ^ 1);   // the epilogue has drained this accumulator
+          if (tr) tr[9] = globaltimer_ns();
           tc_fence_after();
-          const uint32_t d_addr = tmem_base + acc * DC_MB;
-          for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint32_t slot = smem_base + stage * DC_STAGE_BYTES;
-            const uint64_t da = make_sdesc_sw128(slot);
-            const uint64_t db = make_sdesc_sw128(slot + DC_W_BYTES);
+        }
+        const uint32_t d_addr = tmem_base + acc * DC_BM;
+        for (int kb = g.kb0; kb < g.kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t slot = smem_base + stage * DC_STAGE_BYTES;
+          const uint64_t da = make_sdesc_sw128(slot + DC_W_BYTES);   // activations: rows 0..31 valid
+          const uint32_t fresh = (g.first && kb == g.kb0) ? 0u : 1u;
+          if (!(p.debug & 4)) {
+            if (g.stats) {
+              const uint64_t dbs = make_sdesc_sw128(slot + DC_X_BYTES);   // gamma*[R;A] rows
 #pragma unroll
-            for (int k = 0; k < DC_BK / 16; ++k) umma_bf16_ss(d_addr, da + 2u * k, db + 2u * k, idesc, (kb > kb0) | (k > 0));
-            umma_commit(empty_bar(stage));
-            if (++stage == DC_STAGES) { stage = 0; phase ^= 1; }
+              for (int k = 0; k < DC_BK / 16; ++k) {
+                umma_bf16_ss(d_addr, da + 2u * k, da + 2u * k, idesc_x, fresh | (k > 0));
+                umma_bf16_ss(d_addr + 32, da + 2u * k, dbs + 2u * k, idesc_s, fresh | (k > 0));
+              }
+            } else {
+              const uint64_t db = make_sdesc_sw128(slot);
+#pragma unroll
+              for (int k = 0; k < DC_BK / 16; ++k) umma_bf16_ss(d_addr, da + 2u * k, db + 2u * k, idesc, fresh | (k > 0));
+            }
           }
+          umma_commit(empty_bar(stage));
+          if (++stage == (uint32_t)NST) { stage = 0; phase ^= 1; }
+        }
+        if (g.last) {
           umma_commit(tfull_bar(acc));
+          if (tr) { tr[10] = globaltimer_ns(); tr[12] = (unsigned long long)(g.kb1 - g.kb0); }
         }
       }
     }
   } else {
-    // ===================== epilogue warps 2..5 =====================
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;        // tile row = TMEM lane of this thread
-    const int tt = (warp - 2) * 32 + lane;      // 0..127
-    const int eb = lane;                        // batch column this thread finishes
-    const int eq = warp - 2;                    // row sub-group
-    const int RP = R >> 2;                      // rows per thread in the reduce
-    float* const part = reinterpret_cast<float*>(smem_gen + DC_OFF_PART);
-    float* const sbuf = reinterpret_cast<float*>(smem_gen + DC_OFF_SBUF);
-    float* const sdiag = sbuf + DC_MAX_S * (DC_SROWS * DC_PSTRIDE);
+    // ===================== epilogue warps 0..3 =====================
+    const int tt = threadIdx.x;                 // 0..127
+    const int eb = lane;                        // batch row this thread finishes
+    const int eq = warp;                        // row sub-group
+    const int RP = R >> 2;                      // tile rows per thread in the reduce
+    float* const part = reinterpret_cast<float*>(smem_gen + OFF_PART);
+    float* const sbuf = reinterpret_cast<float*>(smem_gen + OFF_SBUF);
     uint32_t it = 0, nn = 0, ns = 0;
     for (int ph = 0; ph < p.n_phases; ++ph) {
       const DcPhase& P = p.ph[ph];
@@ -323,35 +444,71 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
       for (int item = first; item < n_items; item += C, ++it) {
         const bool is_stats = P.has_stats && item == 0;
         const int tile = item - P.has_stats;
-        const uint32_t acc = it & 1;
-        uint32_t r[32];
-        mbar_wait(tfull_bar(acc), (it >> 1) & 1);
-        tc_fence_after();
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * DC_MB, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
-        if (is_stats) {
-          // ---- all ranks: partial sums of squares (diagonal of x x^T) and partial router/A dots -> rank 0 ----
-          if (row < 32) {
+        const uint32_t acc = it & 3;
+        const uint32_t buf = nn & 1;
+        unsigned long long* tr = (p.trace && it < 32 && tt == 0) ? p.trace + ((size_t)blockIdx.x * 32 + it) * 16 : nullptr;
+        if (tr) { tr[0] = globaltimer_ns(); tr[7] = (unsigned long long)(ph * 1000 + item); }
+        if (warp == 0) {
+          // ---- drain the accumulator (TMEM lane = batch row) and scatter the partials to their owners ----
+          mbar_wait(tfull_bar(acc), (it >> 2) & 1);
+          if (tr) tr[1] = globaltimer_ns();
+          tc_fence_after();
+          const uint32_t t_addr = tmem_base + acc * DC_BM;
+          uint32_t r[32];
+          if (is_stats) {
+            // columns 0..31: x x^T (the diagonal is sum x^2); columns 32..71: router/A dots.  Everything goes to rank 0.
+            const uint32_t remote = dc_mapa(smem_base + OFF_SBUF + (uint32_t)(rank * DC_SBUF_PER_RANK + lane * 16), 0u);
+            tmem_ld_32x32b_x32(t_addr, r);
+            tmem_ld_wait();
             float d = 0.f;
 #pragma unroll
             for (int c = 0; c < 32; ++c) d = (c == lane) ? __uint_as_float(r[c]) : d;
-            dc_st_remote_f1(dc_mapa(smem_base + DC_OFF_SBUF + (uint32_t)((DC_MAX_S * DC_SROWS * DC_PSTRIDE + rank * 32 + row) * 4), 0u), d);
-          } else if (row < 32 + DC_SROWS) {
-            const uint32_t remote = dc_mapa(smem_base + DC_OFF_SBUF + (uint32_t)(((rank * DC_SROWS + (row - 32)) * DC_PSTRIDE) * 4), 0u);
+            tmem_ld_32x32b_x32(t_addr + 32, r);
+            tmem_ld_wait();
 #pragma unroll
             for (int g = 0; g < 8; ++g)
-              dc_st_remote_f4(remote + g * 16, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+              dc_st_remote_f4(remote + g * 512, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
                               __uint_as_float(r[4 * g + 3]));
+            tmem_ld_32x32b_x32(t_addr + 64, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              dc_st_remote_f4(remote + (8 + g) * 512, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                              __uint_as_float(r[4 * g + 3]));
+            dc_st_remote_f4(remote + 10 * 512, d, 0.f, 0.f, 0.f);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(tempty_bar(acc)); dc_arrive_remote(dc_mapa(sfull_bar, 0u)); }
+          } else {
+            const uint32_t pbase = smem_base + OFF_PART + buf * PART_BYTES + (uint32_t)(rank * RG * 512 + lane * 16);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld_32x32b_x32(t_addr + c * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const int row0 = c * 32 + g * 4;
+                const int dst = row0 / R;
+                const uint32_t remote = dc_mapa(pbase + (uint32_t)(((row0 - dst * R) >> 2) * 512), (uint32_t)dst);
+                dc_st_remote_f4(remote, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                                __uint_as_float(r[4 * g + 3]));
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane < S) dc_arrive_remote(dc_mapa(pfull_bar(buf), (uint32_t)lane));
           }
-          dc_arrive_remote(dc_mapa(sfull_bar, 0u));
+          if (tr) tr[2] = globaltimer_ns();
+        }
+        if (is_stats) {
           const int L = P.stats_linears;
           const int nw = L > 1 ? L : 1;   // warps of rank 0 that finish the statistics
           if (rank == 0 && eq < nw) {
             dc_mbar_wait_cluster(sfull_bar, ns & 1);
             float ss = 0.f;
-            for (int s = 0; s < S; ++s) ss += sdiag[s * 32 + eb];
+            auto sval = [&](int s_, int i) { return sbuf[((s_ * DC_SGROUPS + (i >> 2)) * 32 + eb) * 4 + (i & 3)]; };
+            for (int s = 0; s < S; ++s) ss += sval(s, 40);
             const float rs = P.norm ? rsqrtf(ss / (float)P.k_main + P.eps) : 1.0f;
             if (eq == 0 && P.norm && eb < p.M) P.rstd[eb] = rs;
             if (eq < L && eb < p.M) {
@@ -359,7 +516,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
 #pragma unroll
               for (int j = 0; j < 11; ++j) {
                 float a = 0.f;
-                for (int s = 0; s < S; ++s) a += sbuf[(s * DC_SROWS + eq * 11 + j) * DC_PSTRIDE + eb];
+                for (int s = 0; s < S; ++s) a += sval(s, eq * 11 + j);
                 t[j] = a;
               }
               const float l0 = t[0] * rs, l1 = t[1] * rs, l2 = t[2] * rs;
@@ -381,91 +538,82 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
             __threadfence();
             dc_fence_proxy_async();
             dc_named_bar(2, 32 * nw);
-            if (tt == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.counters + 4 + ph), "r"(1) : "memory");
+            if (tt == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.counters + DC_CSTRIDE * (4 + ph)), "r"(1) : "memory");
           }
+          // keep the four epilogue warps in the same item: a warp that ran a whole item ahead would wait on the NEXT use of
+          // sfull / pfull with a parity that the not-yet-completed current use makes look satisfied
+          dc_named_bar(1, 128);
           ++ns;
           continue;
         }
-        // ---- reduce-scatter of the split-K partials through distributed shared memory ----
-        const uint32_t buf = nn & 1;
-        {
-          const int dst_rank = row / R;
-          const int row_in = row - dst_rank * R;
-          const uint32_t local = smem_base + DC_OFF_PART + buf * DC_PART_BYTES + (uint32_t)((rank * R + row_in) * DC_PSTRIDE * 4);
-          const uint32_t remote = dc_mapa(local, (uint32_t)dst_rank);
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            dc_st_remote_f4(remote + g * 16, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
-                            __uint_as_float(r[4 * g + 3]));
-          dc_arrive_remote(dc_mapa(pfull_bar(buf), (uint32_t)dst_rank));
-        }
-        if (P.norm && !rstd_ok) {   // rstd of this phase is published together with zflag
-          dc_spin_ge(p.counters + 4 + ph, 1);
+        if (P.norm && !rstd_ok) {   // rstd of this phase is published together with zflag; ONE thread per CTA polls
+          if (tt == 0) dc_spin_ge(p.counters + DC_CSTRIDE * (4 + ph), 1);
+          dc_named_bar(1, 128);
           rstd = (eb < p.M) ? dc_ld_cg_f32(P.rstd + eb) : 0.f;
           rstd_ok = true;
         }
         dc_mbar_wait_cluster(pfull_bar(buf), (nn >> 1) & 1);
-        const float* pb = part + buf * (DC_BM * DC_PSTRIDE);
+        if (tr) tr[3] = globaltimer_ns();
+        // ---- this rank's R rows: sum the S partials in rank order (deterministic), finish, store ----
+        const float* pb = part + buf * (PART_BYTES / 4);
         const int rl0 = eq * RP;
         const int n0 = tile * DC_BM + rank * R + rl0;
-        if (P.swiglu) {
-          // interleaved rows: 2i = gate_i, 2i+1 = up_i -> output column (tile*128 + row) / 2
-          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(P.out) + (size_t)eb * P.ldc + (n0 >> 1);
-          for (int c = 0; c < RP; c += 4) {
-            float v[4];
+        for (int c = 0; c < RP; c += 4) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int s = 0; s < S; ++s) {
+            const float4 q = *reinterpret_cast<const float4*>(pb + ((s * RG + ((rl0 + c) >> 2)) * 32 + eb) * 4);
+            a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+          }
+          float v[4] = {a.x, a.y, a.z, a.w};
+          if (P.norm) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a = 0.f;
-              for (int s = 0; s < S; ++s) a += pb[(s * R + rl0 + c + e) * DC_PSTRIDE + eb];
-              v[e] = a * rstd;
-            }
-            if (eb < p.M && n0 + c + 3 < P.N) {
-              const float o0 = v[0] / (1.0f + __expf(-v[0])) * v[1];
-              const float o1 = v[2] / (1.0f + __expf(-v[2])) * v[3];
-              *reinterpret_cast<uint32_t*>(orow + (c >> 1)) = pack_bf16x2(o0, o1);
+            for (int e = 0; e < 4; ++e) v[e] *= rstd;
+          }
+          const int n = n0 + c;
+          if (eb >= p.M || n >= P.N) continue;
+          if (P.swiglu) {
+            // interleaved rows: 2i = gate_i, 2i+1 = up_i -> output column (tile*128 + row) / 2
+            const float o0 = v[0] / (1.0f + __expf(-v[0])) * v[1];
+            const float o1 = v[2] / (1.0f + __expf(-v[2])) * v[3];
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(P.out) + (size_t)eb * P.ldc + (n >> 1)) = pack_bf16x2(o0, o1);
+            continue;
+          }
+          const bool vec = (n + 3 < P.N);
+          if (P.bias) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (n + e < P.N) v[e] += __ldg(P.bias + n + e);
+          }
+          if (P.resid) {
+            const __nv_bfloat16* rr = P.resid + (size_t)eb * P.ldr + n;
+            if (vec) {
+              const uint2 q = dc_ld_cg_u2(rr);   // written by an earlier phase of THIS launch on another SM: L2, not L1
+              v[0] += bf16lo(q.x); v[1] += bf16hi(q.x); v[2] += bf16lo(q.y); v[3] += bf16hi(q.y);
+            } else {
+              for (int e = 0; e < 4; ++e) if (n + e < P.N) v[e] += __bfloat162float(*reinterpret_cast<const volatile __nv_bfloat16*>(rr + e));
             }
           }
-        } else {
-          for (int c = 0; c < RP; c += 4) {
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a = 0.f;
-              for (int s = 0; s < S; ++s) a += pb[(s * R + rl0 + c + e) * DC_PSTRIDE + eb];
-              v[e] = P.norm ? a * rstd : a;
-            }
-            const int n = n0 + c;
-            if (eb >= p.M || n >= P.N) continue;
-            const bool vec = (n + 3 < P.N);
-            if (P.bias) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) if (n + e < P.N) v[e] += __ldg(P.bias + n + e);
-            }
-            if (P.resid) {
-              const __nv_bfloat16* rr = P.resid + (size_t)eb * P.ldr + n;
-              if (vec) {
-                const uint2 q = dc_ld_cg_u2(rr);   // written by an earlier phase of THIS launch on another SM: L2, not L1
-                v[0] += bf16lo(q.x); v[1] += bf16hi(q.x); v[2] += bf16lo(q.y); v[3] += bf16hi(q.y);
-              } else {
-                for (int e = 0; e < 4; ++e) if (n + e < P.N) v[e] += __bfloat162float(*reinterpret_cast<const volatile __nv_bfloat16*>(rr + e));
-              }
-            }
-            if (P.out_f32) {
-              float* o = reinterpret_cast<float*>(P.out) + (size_t)eb * P.ldc + n;
-              if (vec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-              else for (int e = 0; e < 4; ++e) if (n + e < P.N) o[e] = v[e];
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + (size_t)eb * P.ldc + n;
-              if (vec) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-              else for (int e = 0; e < 4; ++e) if (n + e < P.N) o[e] = __float2bfloat16_rn(v[e]);
-            }
+          if (P.out_f32) {
+            float* o = reinterpret_cast<float*>(P.out) + (size_t)eb * P.ldc + n;
+            if (vec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            else for (int e = 0; e < 4; ++e) if (n + e < P.N) o[e] = v[e];
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + (size_t)eb * P.ldc + n;
+            if (vec) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+            else for (int e = 0; e < 4; ++e) if (n + e < P.N) o[e] = __float2bfloat16_rn(v[e]);
           }
         }
-        // publish: outputs visible at gpu scope (and to the async proxy: the next phase reads them with TMA), then count
-        __threadfence();
-        dc_fence_proxy_async();
+        if (tr) tr[4] = globaltimer_ns();
+        // publish (CUTLASS arrive_inc pattern): every epilogue thread's stores happen-before the barrier, ONE thread then makes
+        // them visible at gpu scope (and to the async proxy: the next phase reads them with TMA) and bumps the phase counter;
+        // the other 127 threads move on.  The barrier also orders this item's reads of the partial buffer before the drainer
+        // warp's next scatter round can make a peer overwrite it two items later.
         dc_named_bar(1, 128);
-        if (tt == 0) atomicAdd(p.counters + ph, 1);
+        if (tt == 32 && !(p.debug & 1)) {
+          __threadfence();
+          dc_fence_proxy_async();
+          atomicAdd(p.counters + DC_CSTRIDE * ph, 1);
+        }
+        if (tr) tr[5] = globaltimer_ns();
         ++nn;
       }
     }
@@ -474,25 +622,35 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   dc_cluster_sync();   // nobody leaves while a peer may still store into its shared memory or signal its barriers
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+  if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
   // self-cleaning counters: the last CTA to get here zeroes them for the next launch (every wait above is over by then)
   if (threadIdx.x == 0) {
     __threadfence();
-    const int prev = atomicAdd(p.counters + 8, 1);
+    const int prev = atomicAdd(p.counters + DC_CSTRIDE * 8, 1);
     if (prev == (int)gridDim.x - 1) {
-      for (int i = 0; i < 9; ++i) p.counters[i] = 0;
+      for (int i = 0; i < 9; ++i) p.counters[DC_CSTRIDE * i] = 0;
       __threadfence();
     }
   }
 }
 
-static int dc_max_clusters(int S) {
+static int dc_pick_stages(int S) {
+  const char* e = getenv("CRAB_CHAIN_STAGES");   // read per call: tools sweep it
+  const int env = e ? atoi(e) : 0;
+  int st = DC_MAX_STAGES;
+  while (st > 2 && dc_smem(st, S) > DC_SMEM_MAX) --st;
+  if (env >= 2 && env < st) st = env;
+  return st;
+}
+
+static int dc_max_clusters(int S, int smem) {
   static int cache[DC_MAX_S + 1] = {0};
-  if (cache[S] > 0) return cache[S];
+  static int cache_smem[DC_MAX_S + 1] = {0};
+  if (cache[S] > 0 && cache_smem[S] == smem) return cache[S];
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(S * 148));
   cfg.blockDim = dim3(DC_THREADS);
-  cfg.dynamicSmemBytes = DC_SMEM;
+  cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)S;
@@ -506,6 +664,7 @@ static int dc_max_clusters(int S) {
     return 0;
   }
   cache[S] = n;
+  cache_smem[S] = smem;
   return n;
 }
 
@@ -523,10 +682,10 @@ extern "C" int crab_decode_chain_max_clusters(int cluster, int* n) {
   CRAB_REQUIRE(n && (cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8), "crab_decode_chain_max_clusters: cluster must be 1, 2, 4 or 8");
   static bool attr_set = false;
   if (!attr_set) {
-    CRAB_CHECK_CUDA(cudaFuncSetAttribute(decode_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM));
+    CRAB_CHECK_CUDA(cudaFuncSetAttribute(decode_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_MAX));
     attr_set = true;
   }
-  *n = dc_max_clusters(cluster);
+  *n = dc_max_clusters(cluster, dc_smem(dc_pick_stages(cluster), cluster));
   CRAB_REQUIRE(*n > 0, "crab_decode_chain_max_clusters: occupancy query failed for cluster size %d", cluster);
   return CRAB_OK;
 }
@@ -535,7 +694,7 @@ extern "C" int crab_decode_chain(const crab_chain_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CRAB_REQUIRE(a && a->n_phases >= 1 && a->n_phases <= DC_MAX_PHASES, "crab_decode_chain: 1..4 phases");
   CRAB_REQUIRE(a->M > 0 && a->M <= DC_MB, "crab_decode_chain: M must be in 1..32 (got %d)", a->M);
-  CRAB_REQUIRE(a->counters && ((uintptr_t)a->counters % 4 == 0), "crab_decode_chain: counters (9 zeroed ints) required");
+  CRAB_REQUIRE(a->counters && ((uintptr_t)a->counters % 128 == 0), "crab_decode_chain: counters (288 zeroed ints, 128-byte aligned) required");
   const int S = a->cluster > 0 ? a->cluster : 4;
   CRAB_REQUIRE(S == 1 || S == 2 || S == 4 || S == 8, "crab_decode_chain: cluster must be 1, 2, 4 or 8");
   int maxc = 0;
@@ -546,6 +705,19 @@ extern "C" int crab_decode_chain(const crab_chain_args* a, void* stream_) {
 
   DcParams p;
   memset(&p, 0, sizeof(p));
+  p.stages = dc_pick_stages(S);
+  {
+    const char* le = getenv("CRAB_CHAIN_LAG");
+    p.lag = le ? atoi(le) : 2;
+    if (p.lag < 0) p.lag = 0;
+    if (p.lag > 2) p.lag = 2;
+  }
+  {
+    const char* e = getenv("CRAB_CHAIN_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+    const char* t = getenv("CRAB_CHAIN_TRACE");
+    p.trace = t ? reinterpret_cast<unsigned long long*>(strtoull(t, nullptr, 0)) : nullptr;
+  }
   p.n_phases = a->n_phases;
   p.M = a->M;
   p.counters = a->counters;
@@ -602,7 +774,7 @@ extern "C" int crab_decode_chain(const crab_chain_args* a, void* stream_) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(C * S));
   cfg.blockDim = dim3(DC_THREADS);
-  cfg.dynamicSmemBytes = DC_SMEM;
+  cfg.dynamicSmemBytes = dc_smem(p.stages, S);
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;

@@ -98,6 +98,10 @@ __device__ __forceinline__ void bulk_load_1d_hint(uint32_t smem_dst, const void*
       : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar), "l"(hint)
       : "memory");
 }
+// L2-only prefetch of a contiguous global span (bytes multiple of 16): no shared-memory destination, no completion signal
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes) : "memory");
+}
 // L2 eviction-priority policies (same encodings CUTLASS uses for TMA::CacheHintSm90)
 static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 static constexpr uint64_t kEvictLast = 0x14F0000000000000ull;

@@ -717,7 +717,7 @@ class CrabEngine:
         ops.argmax(logits, self.vocab, out=next_ids)
 
     def _chain_counters(self) -> torch.Tensor:
-        return self._buf("dec_chain_cnt", (16,), torch.int32, zero=True)   # the kernel leaves them zero
+        return self._buf("dec_chain_cnt", (288,), torch.int32, zero=True)   # the kernel leaves them zero
 
     def prefill(self, inputs_embeds: torch.Tensor):
         """inputs_embeds bf16 [B,S,D] (consumed in place) -> (last-position logits fp32 [B, vocab], next ids [B])."""

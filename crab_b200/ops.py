@@ -585,7 +585,7 @@ class ChainPhase:
 
 def decode_chain(phases, M: int, counters: torch.Tensor, cluster: int = 0, max_clusters: int = 0, tag: str = "crab_decode_chain"):
     """One persistent launch over up to four dependent decode-step linears (M <= 32 rows)."""
-    assert 1 <= len(phases) <= 4 and counters.dtype == torch.int32 and counters.numel() >= 9
+    assert 1 <= len(phases) <= 4 and counters.dtype == torch.int32 and counters.numel() >= 288
     _req_cuda(counters)
     a = _l.ChainArgs()
     for i, ph in enumerate(phases):

@@ -236,7 +236,7 @@ int crab_row_norm_loraz(const void* x, int ldx, const float* gamma, float eps, v
  *     stats_linears == 0 with Kext > 0 means Z was filled by an earlier kernel (the fused decode attention writes o_proj's z);
  *   - act CRAB_ACT_SWIGLU (N_out = N / 2), bias fp32 [N], residual bf16 [M, ldr] (may alias C), bf16 or fp32 output.
  * Phase i + 1 may read what phase i wrote (X / residual); phases of one launch must not write a buffer an earlier phase still
- * reads.  counters: 9 ints, zero on entry (the kernel leaves them zero).  cluster: K-split = thread-block-cluster size
+ * reads.  counters: 288 ints (nine 128-byte slots), 128-byte aligned, zero on entry (the kernel leaves them zero).  cluster: K-split = thread-block-cluster size
  * (1, 2, 4, 8; 0 = 4).  The launch is cooperative in effect: grid = (max co-resident clusters) x cluster, so it must not be
  * launched concurrently with other work on the same device.
  * ---------------------------------------------------------------------------------------------------------------- */

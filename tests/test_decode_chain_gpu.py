@@ -102,7 +102,7 @@ def test_single_phase_plain_and_residual(cuda_dev, cluster, M):
     x = mk((M, 4096), cuda_dev, 2).to(torch.bfloat16)
     res = mk((M, 4096), cuda_dev, 3).to(torch.bfloat16)
     out = res.clone()
-    cnt = torch.zeros(16, dtype=torch.int32, device=cuda_dev)
+    cnt = torch.zeros(288, dtype=torch.int32, device=cuda_dev)
     ops.decode_chain([lin.phase(x, out, residual=out)], M, cnt, cluster)
     torch.cuda.synchronize()
     e = rel(out, lin.ref(x, res))
@@ -124,7 +124,7 @@ def test_norm_stats_lora_bias_phase(cuda_dev, cluster):
         out = torch.empty((M, lin.N), device=cuda_dev, dtype=torch.bfloat16)
         z = torch.zeros((32, 128), device=cuda_dev, dtype=torch.bfloat16)
         rstd = torch.zeros(32, device=cuda_dev, dtype=torch.float32)
-        cnt = torch.zeros(16, dtype=torch.int32, device=cuda_dev)
+        cnt = torch.zeros(288, dtype=torch.int32, device=cuda_dev)
         ops.decode_chain([lin.phase(x, out, zbuf=z, rstd=rstd)], M, cnt, cluster)
         torch.cuda.synchronize()
         r_ref = torch.rsqrt(x.float().pow(2).mean(-1) + 1e-6)
@@ -143,7 +143,7 @@ def test_ragged_n_fp32_head_phase(cuda_dev):
     x = mk((M, 4096), cuda_dev, 22, 5.0).to(torch.bfloat16)
     out = torch.full((M, 32024), -7.0, device=cuda_dev, dtype=torch.float32)
     rstd = torch.zeros(32, device=cuda_dev, dtype=torch.float32)
-    cnt = torch.zeros(16, dtype=torch.int32, device=cuda_dev)
+    cnt = torch.zeros(288, dtype=torch.int32, device=cuda_dev)
     ops.decode_chain([ops.ChainPhase(x, lin.packed, out, k=4096, norm=True, eps=1e-6, rstd=rstd, n=32017)], M, cnt, 4)
     torch.cuda.synchronize()
     e = rel(out[:, :32017], lin.ref(x))
@@ -177,7 +177,7 @@ def test_layer_chain_four_phases(cuda_dev, dims, cluster):
         out_qkv = torch.empty((M, qkv.N), device=dev, dtype=torch.bfloat16)
         zb = {k: torch.zeros((32, 128), device=dev, dtype=torch.bfloat16) for k in ("gu", "d", "qkv")}
         rs = {k: torch.zeros(32, device=dev, dtype=torch.float32) for k in ("gu", "qkv")}
-        cnt = torch.zeros(16, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(288, dtype=torch.int32, device=dev)
         phases = [o.phase(at, x, residual=x, external_z=at[:, nq:]),
                   gu.phase(x, hh, zbuf=zb["gu"], rstd=rs["gu"]),
                   dn.phase(hh, x, zbuf=zb["d"], residual=x),
@@ -211,7 +211,7 @@ def test_chain_inside_cuda_graph(cuda_dev):
     out = torch.empty((M, 4096), device=cuda_dev, dtype=torch.bfloat16)
     z = torch.zeros((32, 128), device=cuda_dev, dtype=torch.bfloat16)
     rstd = torch.zeros(32, device=cuda_dev, dtype=torch.float32)
-    cnt = torch.zeros(16, dtype=torch.int32, device=cuda_dev)
+    cnt = torch.zeros(288, dtype=torch.int32, device=cuda_dev)
     ph = [lin.phase(x, out, zbuf=z, rstd=rstd)]
     ops.decode_chain(ph, M, cnt, 4)
     torch.cuda.synchronize()
