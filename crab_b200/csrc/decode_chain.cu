@@ -253,10 +253,11 @@ struct DcSeq {
         g.ext = false; g.first = true; g.last = true;
       } else if (!ext_part) {
         g.kb0 = rank * P.kb_total / S; g.kb1 = P.kb_main;
+        if (g.kb0 >= g.kb1) continue;               // tiny K: this rank's slice is all extension, its run below starts the item
         g.ext = false; g.first = true; g.last = false;
       } else {
         g.kb0 = P.kb_main; g.kb1 = P.kb_total;
-        g.ext = true; g.first = false; g.last = true;
+        g.ext = true; g.first = (rank * P.kb_total / S >= P.kb_main); g.last = true;
       }
       return true;
     }

@@ -47,7 +47,34 @@ struct SkinnyParams {
   int M, N, K, ldc, ldr;
   int act, out_dtype;
   int splits, kb_per_tile, rows_per_rank;
+  // ---- in-launch statistics (RMSNorm as an epilogue scale + hyper-LoRA pre-pass), see crab_skinny_args ----
+  const __nv_bfloat16* stats_w;  // packed [kb_main][40 x 64] router/A rows (gamma folded) or null
+  __nv_bfloat16* zbuf;           // z' columns [M, ldz]: written by the statistics cluster, read through tmap_z
+  float* rstd;                   // [32]
+  int* flags;                    // [0] z / rstd published, [32] CTAs that have left (self-cleaning)
+  int n_tiles, kb_main, ldz, has_stats, norm, stats_linears, ext_from_z;
+  float eps, lora_scale;
 };
+static constexpr int SK_SROWS = 40;                       // router/A rows per statistics k-block (33 used)
+static constexpr int SK_S_BYTES = SK_SROWS * SK_BK * 2;   // 5 KB
+static constexpr int SK_SSROWS = 32 + SK_SROWS;           // tile rows of a statistics item that carry data: x x^T, then the dots
+__device__ __forceinline__ int sk_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sk_wait_flag(const int* p) {
+  if (sk_ld_acquire(p) > 0) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (sk_ld_acquire(p) <= 0) {
+    __nanosleep(32);
+    if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > CRAB_MBAR_TIMEOUT_NS) {
+      printf("crab: skinny statistics flag timeout block=%d thread=%d\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -68,7 +95,7 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
 
 __global__ void __launch_bounds__(SK_THREADS, 2)
 gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-                           const SkinnyParams p) {
+                           const __grid_constant__ CUtensorMap tmap_z, const SkinnyParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + SK_STAGES * SK_STAGE_BYTES;
@@ -79,9 +106,16 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.splits;
-  const int tile = blockIdx.x / S;
+  const int tile = (int)blockIdx.x / S - p.has_stats;   // weight tile of this cluster (-1: the statistics cluster)
   const int rank = (S > 1) ? (int)cluster_ctarank() : 0;
-  const int KB = p.kb_per_tile;
+  // One cluster of the launch is the STATISTICS cluster (when the launch has one): its A tile is
+  // [x rows (32) ; gamma*[R;A] rows], so the same MMA chain yields diag(x x^T) = sum x^2 and the hyper-LoRA router / A dots;
+  // its rank 0 publishes rstd and z' = scale * softmax(rstd * logits)_i * u_j and raises flags[0].  The other clusters read
+  // z' (their K-extension k-blocks, the last ones of the last rank) and rstd (epilogue scale) only after that flag.
+  // It is the FIRST cluster of the grid: clusters are placed in block order, so it is resident before any cluster that will
+  // wait for its flag (a last-placed statistics cluster can be starved of a contiguous slot by the very CTAs that spin on it).
+  const bool is_stats = p.has_stats && blockIdx.x < (unsigned)S;
+  const int KB = is_stats ? p.kb_main : p.kb_per_tile;
   const int kb0 = rank * KB / S, kb1 = (rank + 1) * KB / S;
 
   if (warp == 0 && lane == 0) {
@@ -104,23 +138,45 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
       // ===================== producer =====================
       // Weights never depend on an earlier kernel: the ring is filled with W tiles before the PDL wait.
       const int npre = min(SK_STAGES, kb1 - kb0);
-      const size_t blk0 = (size_t)tile * KB;
-      for (int i = 0; i < npre; ++i) {
-        mbar_arrive_expect_tx(full_bar(i), SK_STAGE_BYTES);
-        if (p.w_tiled) bulk_load_1d_hint(smem_base + i * SK_STAGE_BYTES, p.w_tiled + (blk0 + kb0 + i) * (SK_BM * SK_BK), SK_W_BYTES, full_bar(i), kEvictFirst);
-        else tma_load_2d_hint(smem_base + i * SK_STAGE_BYTES, &tmap_w, full_bar(i), (kb0 + i) * SK_BK, tile * SK_BM, kEvictFirst);
-      }
+      const size_t blk0 = (size_t)tile * p.kb_per_tile;
+      auto load_w = [&](int slot_i, int kb) {
+        const uint32_t sw = smem_base + slot_i * SK_STAGE_BYTES;
+        if (is_stats) {
+          // x tile twice (A rows 0..31 and the B operand) + the router/A rows: armed here, the x loads follow the PDL wait
+          mbar_arrive_expect_tx(full_bar(slot_i), 2 * SK_X_BYTES + (p.stats_w ? SK_S_BYTES : 0));
+          if (p.stats_w) bulk_load_1d_hint(sw + SK_X_BYTES, p.stats_w + (size_t)kb * (SK_SROWS * SK_BK), SK_S_BYTES, full_bar(slot_i), kEvictFirst);
+        } else {
+          mbar_arrive_expect_tx(full_bar(slot_i), SK_STAGE_BYTES);
+          if (p.w_tiled) bulk_load_1d_hint(sw, p.w_tiled + (blk0 + kb) * (SK_BM * SK_BK), SK_W_BYTES, full_bar(slot_i), kEvictFirst);
+          else tma_load_2d_hint(sw, &tmap_w, full_bar(slot_i), kb * SK_BK, tile * SK_BM, kEvictFirst);
+        }
+      };
+      bool z_ok = false;
+      auto load_x = [&](int slot_i, int kb) {
+        const uint32_t sw = smem_base + slot_i * SK_STAGE_BYTES;
+        if (is_stats) {
+          tma_load_2d_hint(sw + SK_W_BYTES, &tmap_x, full_bar(slot_i), kb * SK_BK, 0, kEvictLast);
+          tma_load_2d_hint(sw, &tmap_x, full_bar(slot_i), kb * SK_BK, 0, kEvictLast);
+        } else if (p.ext_from_z && kb >= p.kb_main) {
+          if (p.has_stats && !z_ok) {   // z' comes from this launch's statistics cluster
+            sk_wait_flag(p.flags);
+            asm volatile("fence.proxy.async;" ::: "memory");
+            z_ok = true;
+          }
+          tma_load_2d_hint(sw + SK_W_BYTES, &tmap_z, full_bar(slot_i), (kb - p.kb_main) * SK_BK, 0, kEvictLast);
+        } else {
+          tma_load_2d_hint(sw + SK_W_BYTES, &tmap_x, full_bar(slot_i), kb * SK_BK, 0, kEvictLast);
+        }
+      };
+      for (int i = 0; i < npre; ++i) load_w(i, kb0 + i);
       pdl_wait();
-      for (int i = 0; i < npre; ++i)
-        tma_load_2d_hint(smem_base + i * SK_STAGE_BYTES + SK_W_BYTES, &tmap_x, full_bar(i), (kb0 + i) * SK_BK, 0, kEvictLast);
+      for (int i = 0; i < npre; ++i) load_x(i, kb0 + i);
       uint32_t stage = 0, phase = 1;  // ring position after the prefill (npre == SK_STAGES wraps to stage 0)
+      if (npre < SK_STAGES) { stage = (uint32_t)npre; phase = 0; }
       for (int kb = kb0 + npre; kb < kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
-        mbar_arrive_expect_tx(full_bar(stage), SK_STAGE_BYTES);
-        const uint32_t sw = smem_base + stage * SK_STAGE_BYTES;
-        if (p.w_tiled) bulk_load_1d_hint(sw, p.w_tiled + (blk0 + kb) * (SK_BM * SK_BK), SK_W_BYTES, full_bar(stage), kEvictFirst);
-        else tma_load_2d_hint(sw, &tmap_w, full_bar(stage), kb * SK_BK, tile * SK_BM, kEvictFirst);
-        tma_load_2d_hint(sw + SK_W_BYTES, &tmap_x, full_bar(stage), kb * SK_BK, 0, kEvictLast);
+        load_w((int)stage, kb);
+        load_x((int)stage, kb);
         if (++stage == SK_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -159,7 +215,74 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
     tmem_ld_wait();
   }
 
-  if (S == 1) {
+  __shared__ float rstd_s[32];
+  if (is_stats) {
+    // ---- statistics cluster: partial x x^T rows / router-A dots of every rank -> rank 0 -> rstd, z', flag ----
+    cluster_sync_all();   // every CTA of the cluster has finished its MMAs: the TMA ring is free to hold partials
+    if (epi && row < SK_SSROWS) {
+      const uint32_t local = smem_base + (uint32_t)((rank * SK_SSROWS + row) * SK_PSTRIDE * 4);
+      const uint32_t remote = map_to_rank(local, 0u);
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        st_cluster_f4(remote + g * 16, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                      __uint_as_float(r[4 * g + 3]));
+    }
+    cluster_sync_all();
+    if (rank == 0 && epi) {
+      const int tt = (warp - 2) * 32 + lane;
+      const int b = tt & 31, l = tt >> 5;
+      const int L = p.stats_linears;
+      const int nw = L > 1 ? L : 1;
+      const float* part = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+      if (l < nw) {
+        float ss = 0.f;
+        for (int s = 0; s < S; ++s) ss += part[(s * SK_SSROWS + b) * SK_PSTRIDE + b];   // diagonal of x x^T
+        const float rs = p.norm ? rsqrtf(ss / (float)(p.kb_main * SK_BK) + p.eps) : 1.0f;
+        if (l == 0 && p.norm && b < p.M) p.rstd[b] = rs;
+        if (l < L && b < p.M) {
+          float t[11];
+#pragma unroll
+          for (int j = 0; j < 11; ++j) {
+            float a = 0.f;
+            for (int s = 0; s < S; ++s) a += part[(s * SK_SSROWS + 32 + l * 11 + j) * SK_PSTRIDE + b];
+            t[j] = a;
+          }
+          const float l0 = t[0] * rs, l1 = t[1] * rs, l2 = t[2] * rs;
+          const float mx = fmaxf(l0, fmaxf(l1, l2));
+          const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx), e2 = __expf(l2 - mx);
+          const float inv = p.lora_scale / (e0 + e1 + e2);
+          const float rw[3] = {e0 * inv, e1 * inv, e2 * inv};
+          __nv_bfloat16* zrow = p.zbuf + (size_t)b * p.ldz + l * 24;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {   // z' is NOT normalised: the consumers' epilogue multiplies the whole accumulator by rstd
+            uint4 v;
+            v.x = pack_bf16x2(rw[i] * t[3], rw[i] * t[4]);
+            v.y = pack_bf16x2(rw[i] * t[5], rw[i] * t[6]);
+            v.z = pack_bf16x2(rw[i] * t[7], rw[i] * t[8]);
+            v.w = pack_bf16x2(rw[i] * t[9], rw[i] * t[10]);
+            *reinterpret_cast<uint4*>(zrow + i * 8) = v;
+          }
+        }
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"r"(32 * nw) : "memory");
+        if (tt == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags), "r"(1) : "memory");
+      }
+    }
+  } else if (p.norm && epi) {
+    // RMSNorm as an epilogue scale: gamma is folded into the packed weights, rstd[b] comes from the statistics cluster
+    if (warp == 2) {
+      if (lane == 0) sk_wait_flag(p.flags);
+      __syncwarp();
+      float v;
+      asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p.rstd + lane) : "memory");
+      rstd_s[lane] = lane < p.M ? v : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+
+  if (is_stats) {
+  } else if (S == 1) {
     if (epi) {
       // ---- no split: finish straight from registers (thread = weight row, 32 batch values) ----
       if (swiglu) {
@@ -167,7 +290,7 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
         const int n = tile * 64 + (row >> 1);
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
-          const float mine = __uint_as_float(r[b]);
+          const float mine = __uint_as_float(r[b]) * (p.norm ? rstd_s[b] : 1.0f);
           const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
           if (!(row & 1) && b < p.M && n < (p.N >> 1))
             reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(mine / (1.0f + __expf(-mine)) * other);
@@ -183,7 +306,7 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
 #pragma unroll
           for (int b = 0; b < 32; ++b) {
             if (b < p.M) {
-              const float v = __uint_as_float(r[b]) + bias + resv[b];
+              const float v = __uint_as_float(r[b]) * (p.norm ? rstd_s[b] : 1.0f) + bias + resv[b];
               if (p.out_dtype == CRAB_BF16) reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(v);
               else reinterpret_cast<float*>(p.C)[(size_t)b * p.ldc + n] = v;
             }
@@ -222,6 +345,7 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
             g += part[(s * R + 2 * pr) * SK_PSTRIDE + b];
             u += part[(s * R + 2 * pr + 1) * SK_PSTRIDE + b];
           }
+          if (p.norm) { g *= rstd_s[b]; u *= rstd_s[b]; }
           const int n = tile * 64 + ((row0 + 2 * pr) >> 1);
           if (b < p.M && n < (p.N >> 1))
             reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(g / (1.0f + __expf(-g)) * u);
@@ -232,6 +356,7 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
           const int n = tile * SK_BM + row0 + rl;
           float a = 0.f;
           for (int s = 0; s < S; ++s) a += part[(s * R + rl) * SK_PSTRIDE + b];
+          if (p.norm) a *= rstd_s[b];
           if (b < p.M && n < p.N) {
             a += p.bias ? p.bias[n] : 0.f;
             if (p.residual) a += __bfloat162float(p.residual[(size_t)b * p.ldr + n]);
@@ -245,6 +370,16 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
+  // self-cleaning flags: the last CTA to get here (every flag wait is over by then) zeroes them for the next launch
+  if (p.has_stats && threadIdx.x == 0) {
+    __threadfence();
+    const int prev = atomicAdd(p.flags + 32, 1);
+    if (prev == (int)gridDim.x - 1) {
+      p.flags[0] = 0;
+      p.flags[32] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // Pre-pack a row-major weight [N, ldw] into the streaming layout: block f = tile * KB + kb holds the 128 x 64 tile
@@ -330,33 +465,57 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
   if (a->act == CRAB_ACT_SWIGLU)
     CRAB_REQUIRE(a->N % 128 == 0 && !a->bias && !a->residual && a->out_dtype == CRAB_BF16 && a->W_packed,
                  "crab_gemm_skinny_bf16: SWIGLU needs N %% 128 == 0, bf16 out, no bias/residual and a weight packed with swiglu_interleave");
+  // ---- optional: K-extension columns from a separate buffer, RMSNorm as an epilogue scale, in-launch hyper-LoRA pre-pass ----
+  const bool ext_z = a->Z != nullptr && a->Kext > 0;
+  const bool has_stats = a->norm != 0 || a->stats_linears > 0;
+  if (ext_z || has_stats) {
+    CRAB_REQUIRE(a->W_packed && a->K % SK_BK == 0, "crab_gemm_skinny_bf16: Z / norm / stats need a packed weight and K %% 64 == 0");
+    CRAB_REQUIRE(!ext_z || (a->Kext <= 128 && a->ldz % 8 == 0 && a->ldz >= a->Kext && ((uintptr_t)a->Z % 16 == 0)),
+                 "crab_gemm_skinny_bf16: bad K-extension (Kext=%d ldz=%d)", a->Kext, a->ldz);
+    CRAB_REQUIRE(a->stats_linears >= 0 && a->stats_linears <= 3 &&
+                 (a->stats_linears == 0 || (a->stats_packed && ext_z && a->Kext >= 24 * a->stats_linears && ((uintptr_t)a->stats_packed % 128 == 0))),
+                 "crab_gemm_skinny_bf16: a LoRA pre-pass needs stats_packed, Z and Kext >= 24 per linear");
+    CRAB_REQUIRE(!a->norm || a->rstd, "crab_gemm_skinny_bf16: norm needs an rstd scratch buffer (32 floats)");
+    CRAB_REQUIRE(!has_stats || (a->flags && ((uintptr_t)a->flags % 128 == 0)), "crab_gemm_skinny_bf16: norm / stats need `flags` (64 zeroed ints, 128-byte aligned)");
+  }
   const int tiles = (a->N + SK_BM - 1) / SK_BM;
-  const int kb = (a->K + SK_BK - 1) / SK_BK;
-  int splits = a->splits > 0 ? a->splits : choose_splits(a->N, a->K);
+  const int kb_main = (a->K + SK_BK - 1) / SK_BK;
+  const int kb = kb_main + (ext_z ? (a->Kext + SK_BK - 1) / SK_BK : 0);
+  int splits = a->splits > 0 ? a->splits : choose_splits(a->N, kb * SK_BK);
   if (splits > SK_MAX_SPLIT) splits = SK_MAX_SPLIT;
-  if (splits > kb) splits = kb;
+  if (splits > kb_main) splits = kb_main;
   static bool attr_set = false;
   if (!attr_set) {
     CRAB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
     attr_set = true;
   }
-  CUtensorMap tw, tx;
+  CUtensorMap tw, tx, tz;
   int rc = 0;
   if (a->W_packed) memset(&tw, 0, sizeof(tw));
   else rc = encode_tmap_bf16_2d(&tw, a->W, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldw, SK_BM, SK_BK);
   if (rc != 0) return rc;
   rc = encode_tmap_bf16_2d(&tx, a->X, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->ldx, SK_MB, SK_BK);
   if (rc != 0) return rc;
+  if (ext_z) rc = encode_tmap_bf16_2d(&tz, a->Z, (uint64_t)a->M, (uint64_t)a->Kext, (uint64_t)a->ldz, SK_MB, SK_BK);
+  else tz = tx;
+  if (rc != 0) return rc;
   SkinnyParams p;
+  memset(&p, 0, sizeof(p));
   p.C = a->C; p.bias = a->bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
   p.w_tiled = reinterpret_cast<const __nv_bfloat16*>(a->W_packed);
   p.M = a->M; p.N = a->N; p.K = a->K; p.ldc = a->ldc; p.ldr = a->ldr;
   p.act = a->act; p.out_dtype = a->out_dtype;
   p.splits = splits; p.kb_per_tile = kb;
   p.rows_per_rank = 2 * ((64 + splits - 1) / splits);  // even, so SwiGLU (gate, up) row pairs never straddle two ranks
-
+  p.stats_w = reinterpret_cast<const __nv_bfloat16*>(a->stats_packed);
+  p.zbuf = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(a->Z));
+  p.rstd = a->rstd;
+  p.flags = a->flags;
+  p.n_tiles = tiles; p.kb_main = kb_main; p.ldz = a->ldz;
+  p.has_stats = has_stats ? 1 : 0; p.norm = a->norm != 0; p.stats_linears = a->stats_linears; p.ext_from_z = ext_z ? 1 : 0;
+  p.eps = a->eps; p.lora_scale = a->lora_scale;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(tiles * splits));
+  cfg.gridDim = dim3((unsigned)((tiles + p.has_stats) * splits));
   cfg.blockDim = dim3(SK_THREADS);
   cfg.dynamicSmemBytes = SK_SMEM;
   cfg.stream = stream;
@@ -376,6 +535,6 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  CRAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_tcgen05_kernel, tw, tx, p));
+  CRAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_tcgen05_kernel, tw, tx, tz, p));
   return CRAB_OK;
 }

@@ -22,7 +22,7 @@ import torch
 from . import ops
 
 SD = Dict[str, torch.Tensor]
-DEFAULT_PDL_PLAN = "0,0"  # the persistent GEMM chain owns every SM: its neighbours are plain (fully ordered) launches
+DEFAULT_PDL_PLAN = "19,17"  # streaming GEMM + light kernels launch programmatically; attention / RoPE stay plain launches
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -182,6 +182,9 @@ class CrabEngine:
         # decode attention).  Env CRAB_PDL_PLAN="chain,after_attn" overrides; see profiles/r02_pdl_plans.txt for the A/B.
         plan = os.environ.get("CRAB_PDL_PLAN", DEFAULT_PDL_PLAN).split(",")
         self.pdl_chain, self.pdl_after_attn = int(plan[0]), int(plan[-1])
+        # decode step for <= 32 rows: "skinny" = one fused weight-streaming launch per linear (5 launches per layer, default);
+        # "chain" = the persistent o -> gate/up -> down -> qkv kernel (2 launches per layer; slower today)
+        self.decode_mode = os.environ.get("CRAB_DECODE_MODE", "skinny")
         # K-split (= thread-block-cluster size) of the persistent decode GEMM chain
         self.chain_cluster = int(os.environ.get("CRAB_CHAIN_CLUSTER", "4"))
         # decode step: RoPE + KV append + o_proj LoRA pre-pass inside the attention kernel (8 launches per layer, not 10)
@@ -710,7 +713,9 @@ class CrabEngine:
         """final RMSNorm -> lm_head (fp32 logits) -> greedy arg-max."""
         c = self.cfg.decoder
         if x_last.shape[0] <= 32 and self.lm_head_c is not None:
-            ops.decode_chain([self._head_phase(x_last, logits)], x_last.shape[0], self._chain_counters(), self.chain_cluster)
+            # one launch: the statistics cluster computes rstd, the lm_head tiles apply it in their epilogue (gamma is in lm_head_c)
+            ops.gemm_skinny(x_last, self.lm_head_c, out=logits, n=self.vocab, norm=True, eps=c.eps,
+                            rstd=self._buf("dec_rstd_head", (32,), torch.float32), flags=self._flags("head"), tag="lm_head_skinny")
         else:
             hn = ops.rmsnorm(x_last, self.final_norm, c.eps, out=self._buf("head_hn", tuple(x_last.shape)))
             ops.gemm(hn, self.lm_head, out=logits)
@@ -718,6 +723,11 @@ class CrabEngine:
 
     def _chain_counters(self) -> torch.Tensor:
         return self._buf("dec_chain_cnt", (288,), torch.int32, zero=True)   # the kernel leaves them zero
+
+    def _flags(self, name: str) -> torch.Tensor:
+        """Per-GEMM flag words of the fused skinny launches (zero on entry, left zero).  One buffer per linear: with programmatic
+        dependent launch the next kernel's CTAs may poll before the previous launch has reset ITS flags."""
+        return self._buf("dec_flags_" + name, (64,), torch.int32, zero=True)
 
     def prefill(self, inputs_embeds: torch.Tensor):
         """inputs_embeds bf16 [B,S,D] (consumed in place) -> (last-position logits fp32 [B, vocab], next ids [B])."""
@@ -791,6 +801,83 @@ class CrabEngine:
         self._plan_key, self._plan = key, plan
         return plan
 
+    def _decode_attention(self, li: int, B: int, nsplit: int, ws, qkv, at, fused: bool, gqa_tc: bool, o_fused_lora: bool):
+        """The decode step's attention launch(es) of layer li: RoPE on q / new k, KV append, attention over past + 1 keys."""
+        c = self.cfg.decoder
+        H, KV, hd = c.heads, c.kv_heads, c.head_dim
+        nq, nk = H * hd, KV * hd
+        ctx = self.cfg.max_ctx
+        L = self.layers[li]
+        if gqa_tc:
+            # grouped-query decode with enough (batch x kv-head) problems to fill the SMs: the G query heads of a kv
+            # group are the Sq = G "rows" of one flash-attention problem, so QK^T / PV run on tensor cores
+            G = H // KV
+            ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, 1, H, KV, hd, past=0, past_dev=self.past_dev)
+            ops.flash_attn(qkv, self.k_cache[li], self.v_cache[li], at, B=B, H=KV, KVH=KV, Sq=G, Sk=ctx, head_dim=hd,
+                           q_strides=(nq + 2 * nk, hd, G * hd), k_strides=(KV * ctx * hd, hd, ctx * hd),
+                           v_strides=(KV * ctx * hd, hd, ctx * hd), o_strides=(nq + self.EXT_O, hd, G * hd),
+                           scale=1 / math.sqrt(hd), sk_dev=self.len_dev)
+        elif fused:
+            # one launch: RoPE on q / new k, cache append, attention over past + 1 keys, and (nsplit == 1) the o_proj
+            # LoRA pre-pass whose z columns land in at[:, nq:]
+            ops.attn_decode_fused(qkv, self.rope, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV,
+                                  head_dim=hd, scale=1 / math.sqrt(hd), past_dev=self.past_dev, nsplit=nsplit, workspace=ws,
+                                  ra=L["ra_o"] if o_fused_lora else None, z=at[:, nq:] if o_fused_lora else None, lora_scale=self.scaling,
+                                  lora_ws=self._buf("dec_lora_ws", (B * KV * 11,), torch.float32) if o_fused_lora else None,
+                                  lora_counters=self._buf("dec_lora_cnt", (B,), torch.int32, zero=True) if o_fused_lora else None)
+        else:
+            ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, 1, H, KV, hd, past=0, past_dev=self.past_dev)
+            ops.attn_decode(qkv, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV, head_dim=hd,
+                            scale=1 / math.sqrt(hd), len_dev=self.len_dev, nsplit=nsplit, workspace=ws)
+
+    def _decode_body_skinny(self, B: int, nsplit: int, ws):
+        """Decode step, 5 launches per layer: qkv | attention | o | gate/up | down, each linear ONE weight-streaming launch that
+        carries its own RMSNorm (gamma folded into the packed weight, rstd applied in the epilogue) and hyper-LoRA pre-pass (a
+        statistics cluster of the same launch) — the three row kernels per layer of round 1 are gone."""
+        c = self.cfg.decoder
+        D, F, H, KV, hd = c.hidden, c.inter, c.heads, c.kv_heads, c.head_dim
+        nq, nk = H * hd, KV * hd
+        lo, sc = self.lora, self.scaling
+        x = self._buf("dec_x", (B, D))
+        qkv = self._buf("dec_qkv", (B, nq + 2 * nk))
+        at = self._buf("dec_attn", (B, nq + self.EXT_O), zero=True)
+        hh = self._buf("dec_h", (B, F))
+        z = {n: self._buf("dec_z_" + n, (32, 128), zero=True) for n in ("qkv", "o", "gu", "d")}
+        rs = {n: self._buf("dec_rstd_" + n, (32,), torch.float32) for n in ("qkv", "gu")}
+        G = H // KV
+        gqa_tc = G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
+        fused = self.fuse_decode_attn and not gqa_tc
+        o_fused_lora = lo and fused and nsplit == 1     # the attention kernel writes o_proj's z columns into at[:, nq:]
+        ops.set_pdl(self.pdl_chain)
+        try:
+            ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)  # embed_tokens of the previous arg-max
+            for li, L in enumerate(self.layers):
+                ops.gemm_skinny(x, L["wqkv_c"], bias=L["bqkv"], out=qkv, z=z["qkv"] if lo else None, kext=self.EXT_QKV if lo else 0,
+                                stats=L.get("st_qkv"), stats_linears=3 if lo else 0, norm=True, eps=c.eps, lora_scale=sc, rstd=rs["qkv"],
+                                flags=self._flags("qkv"))
+                self._decode_attention(li, B, nsplit, ws, qkv, at, fused, gqa_tc, o_fused_lora)
+                # the kernel right after the decode attention is launched under its own PDL mask: early-resident streaming-GEMM
+                # CTAs must not squat on the SMs while the 1024-CTA attention kernel still runs
+                if self.pdl_after_attn != self.pdl_chain:
+                    ops.set_pdl(self.pdl_after_attn)
+                if o_fused_lora:
+                    ops.gemm_skinny(at, L["wo_c"], residual=x, out=x, z=at[:, nq:], kext=self.EXT_O)
+                else:
+                    ops.gemm_skinny(at, L["wo_c"], residual=x, out=x, z=z["o"] if lo else None, kext=self.EXT_O if lo else 0,
+                                    stats=L.get("st_o"), stats_linears=1 if lo else 0, lora_scale=sc, flags=self._flags("o") if lo else None)
+                if self.pdl_after_attn != self.pdl_chain:
+                    ops.set_pdl(self.pdl_chain)
+                ops.gemm_skinny(x, L["wgu_c"], act=ops.ACT_SWIGLU, out=hh, z=z["gu"] if lo else None, kext=self.EXT_GU if lo else 0,
+                                stats=L.get("st_gu"), stats_linears=2 if lo else 0, norm=True, eps=c.eps, lora_scale=sc, rstd=rs["gu"],
+                                flags=self._flags("gu"))
+                ops.gemm_skinny(hh, L["wd_c"], residual=x, out=x, z=z["d"] if lo else None, kext=self.EXT_D if lo else 0,
+                                stats=L.get("st_d"), stats_linears=1 if lo else 0, lora_scale=sc, flags=self._flags("d") if lo else None)
+            self._head(x, self.logits, self.next_ids)
+            ops.add_scalar_i32(self.past_dev, 1)
+            ops.add_scalar_i32(self.len_dev, 1)
+        finally:
+            ops.set_pdl(0)  # prefill / encoder launches are never PDL launches
+
     def _decode_body(self, B: int, nsplit: int, ws):
         c = self.cfg.decoder
         D, H, KV, hd = c.hidden, c.heads, c.kv_heads, c.head_dim
@@ -805,6 +892,8 @@ class CrabEngine:
             ops.add_scalar_i32(self.past_dev, 1)
             ops.add_scalar_i32(self.len_dev, 1)
             return
+        if self.decode_mode != "chain":
+            return self._decode_body_skinny(B, nsplit, ws)
         plan = self._chain_plan(B, nsplit)
         fused, gqa_tc, o_fused_lora = self._dec_mode
         x = self._buf("dec_x", (B, D))
@@ -812,36 +901,14 @@ class CrabEngine:
         at = self._buf("dec_attn", (B, nq + self.EXT_O), zero=True)
         cnt = self._chain_counters()
         sc = self.scaling
-        ops.set_pdl(self.pdl_chain)
+        ops.set_pdl(0)   # the persistent chain owns every SM: its neighbours are plain (fully ordered) launches
         try:
             ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)  # embed_tokens of the previous arg-max
             for kind, arg in plan:
                 if kind == "chain":
                     ops.decode_chain(arg, B, cnt, self.chain_cluster)
                     continue
-                li = arg
-                L = self.layers[li]
-                if gqa_tc:
-                    # grouped-query decode with enough (batch x kv-head) problems to fill the SMs: the G query heads of a kv
-                    # group are the Sq = G "rows" of one flash-attention problem, so QK^T / PV run on tensor cores
-                    G = H // KV
-                    ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, 1, H, KV, hd, past=0, past_dev=self.past_dev)
-                    ops.flash_attn(qkv, self.k_cache[li], self.v_cache[li], at, B=B, H=KV, KVH=KV, Sq=G, Sk=ctx, head_dim=hd,
-                                   q_strides=(nq + 2 * nk, hd, G * hd), k_strides=(KV * ctx * hd, hd, ctx * hd),
-                                   v_strides=(KV * ctx * hd, hd, ctx * hd), o_strides=(nq + self.EXT_O, hd, G * hd),
-                                   scale=1 / math.sqrt(hd), sk_dev=self.len_dev)
-                elif fused:
-                    # one launch: RoPE on q / new k, cache append, attention over past + 1 keys, and (nsplit == 1) the o_proj
-                    # LoRA pre-pass whose z columns land in at[:, nq:]
-                    ops.attn_decode_fused(qkv, self.rope, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV,
-                                          head_dim=hd, scale=1 / math.sqrt(hd), past_dev=self.past_dev, nsplit=nsplit, workspace=ws,
-                                          ra=L["ra_o"] if o_fused_lora else None, z=at[:, nq:] if o_fused_lora else None, lora_scale=sc,
-                                          lora_ws=self._buf("dec_lora_ws", (B * KV * 11,), torch.float32) if o_fused_lora else None,
-                                          lora_counters=self._buf("dec_lora_cnt", (B,), torch.int32, zero=True) if o_fused_lora else None)
-                else:
-                    ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, 1, H, KV, hd, past=0, past_dev=self.past_dev)
-                    ops.attn_decode(qkv, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV, head_dim=hd,
-                                    scale=1 / math.sqrt(hd), len_dev=self.len_dev, nsplit=nsplit, workspace=ws)
+                self._decode_attention(arg, B, nsplit, ws, qkv, at, fused, gqa_tc, o_fused_lora)
             ops.argmax(self.logits, self.vocab, out=self.next_ids)
             ops.add_scalar_i32(self.past_dev, 1)
             ops.add_scalar_i32(self.len_dev, 1)

@@ -80,6 +80,10 @@ class SkinnyArgs(C.Structure):
         ("residual", C.c_void_p),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("ldx", C.c_int32), ("ldw", C.c_int32), ("ldc", C.c_int32),
         ("ldr", C.c_int32), ("act", C.c_int32), ("out_dtype", C.c_int32), ("splits", C.c_int32),
+        ("Z", C.c_void_p), ("ldz", C.c_int32), ("Kext", C.c_int32),
+        ("stats_packed", C.c_void_p), ("stats_linears", C.c_int32), ("norm", C.c_int32),
+        ("eps", C.c_float), ("lora_scale", C.c_float),
+        ("rstd", C.c_void_p), ("flags", C.c_void_p),
     ]
 
 

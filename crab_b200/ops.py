@@ -488,19 +488,25 @@ def pack_skinny_weight(w: torch.Tensor, k: Optional[int] = None, swiglu: bool = 
 def gemm_skinny(x: torch.Tensor, w, *, bias: Optional[torch.Tensor] = None,
                 residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
                 out_dtype: torch.dtype = torch.bfloat16, k: Optional[int] = None, n: Optional[int] = None,
-                splits: int = 0) -> torch.Tensor:
-    """out[M, N'] = epilogue(x[M<=32, K] @ w[N, K]^T): the decode-step weight-streaming GEMM (swap-AB, split-K)."""
+                splits: int = 0, z: Optional[torch.Tensor] = None, kext: int = 0, stats: Optional[torch.Tensor] = None,
+                stats_linears: int = 0, norm: bool = False, eps: float = 0.0, lora_scale: float = 1.0,
+                rstd: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None, tag: str = "gemm_skinny_tcgen05") -> torch.Tensor:
+    """out[M, N'] = epilogue(x[M<=32, K] @ w[N, K]^T): the decode-step weight-streaming GEMM (swap-AB, split-K).
+    With z / kext the K-extension columns come from a separate buffer; norm / stats_linears fold the RMSNorm (as an epilogue scale
+    over a gamma-folded weight) and the hyper-LoRA router / A pre-pass into the same launch (see include/crab_b200.h)."""
     packed = isinstance(w, PackedWeight)
-    _req_cuda(x, w.data if packed else w, bias, residual, out)
+    _req_cuda(x, w.data if packed else w, bias, residual, out, z, stats, rstd, flags)
     assert x.dim() == 2 and x.dtype == torch.bfloat16
     M = x.shape[0]
     if packed:
-        K, N = w.K, w.N
+        K, N = w.K - kext, w.N
         assert x.shape[1] >= K
     else:
-        assert w.dim() == 2 and w.dtype == torch.bfloat16
+        assert w.dim() == 2 and w.dtype == torch.bfloat16 and kext == 0
         K = k if k is not None else x.shape[1]
         N = n if n is not None else w.shape[0]
+    if n is not None:
+        N = n
     n_out = N // 2 if act == ACT_SWIGLU else N
     if out is None:
         out = torch.empty((M, n_out), device=x.device, dtype=out_dtype)
@@ -510,8 +516,12 @@ def gemm_skinny(x: torch.Tensor, w, *, bias: Optional[torch.Tensor] = None,
                          bias=_ptr(bias), residual=_ptr(residual),
                          M=M, N=N, K=K, ldx=x.stride(0), ldw=0 if packed else w.stride(0), ldc=out.stride(0),
                          ldr=(residual.stride(0) if residual is not None else 0), act=act,
-                         out_dtype=(BF16 if out.dtype == torch.bfloat16 else F32), splits=splits)
-    with _timed("gemm_skinny_tcgen05", 2.0 * M * N * K, 2.0 * (M * K + N * K) + out.element_size() * M * n_out):
+                         out_dtype=(BF16 if out.dtype == torch.bfloat16 else F32), splits=splits,
+                         Z=_ptr(z), ldz=(z.stride(0) if z is not None else 0), Kext=kext, stats_packed=_ptr(stats),
+                         stats_linears=stats_linears, norm=1 if norm else 0, eps=eps, lora_scale=lora_scale, rstd=_ptr(rstd),
+                         flags=_ptr(flags))
+    wb = 2.0 * N * (K + kext) + (stats.numel() * 2.0 if stats is not None else 0.0)
+    with _timed(tag, 2.0 * M * N * (K + kext), 2.0 * M * K + wb + out.element_size() * M * n_out):
         _l.check(_l.load().crab_gemm_skinny_bf16(C.byref(args), _stream()), "crab_gemm_skinny_bf16")
     count_launches(1)
     return out

@@ -209,6 +209,19 @@ typedef struct crab_skinny_args {
   int32_t act;          /* CRAB_ACT_NONE or CRAB_ACT_SWIGLU (needs W_packed with swiglu_interleave) */
   int32_t out_dtype;
   int32_t splits;       /* K-split = cluster size, 1..8; 0 = auto */
+  /* ---- optional (all zero = plain GEMM): the decode step's fused form of LlamaRMSNorm + hyper-LoRA Linear.forward ----
+   * Z / Kext: K-extension activations (z' columns, bf16 [M, ldz]) multiplied against columns K .. K+Kext of the packed weight
+   *      ([W' | B_0 B_1 B_2] per wrapped linear); K must be a multiple of 64.
+   * norm: RMSNorm as an epilogue scale — the packed W' already carries gamma (W * diag(gamma)), C = rstd[b] * acc (+bias, ...).
+   * stats_linears (0..3) + stats_packed (crab_decode_chain_stats_bytes layout): ONE extra cluster of the launch computes
+   *      rstd[b] = rsqrt(mean(X[b]^2) + eps) and, per wrapped linear, t = X . [R;A]^T, z' = lora_scale * softmax(rstd * t[0:3])_i *
+   *      t[3+j] -> Z[b, 24*linear + 8*i + j]; the K-extension k-blocks and the epilogues of the other clusters wait for it.
+   *      replaces the separate crab_row_norm_loraz launch (peft_hyper/tuners/lora.py:344-350, models/modeling_llama.py:103-117).
+   * rstd: 32 floats of scratch; flags: 64 ints, 128-byte aligned, zero on entry (left zero). */
+  const void* Z; int32_t ldz; int32_t Kext;
+  const void* stats_packed; int32_t stats_linears; int32_t norm;
+  float eps; float lora_scale;
+  float* rstd; int* flags;
 } crab_skinny_args;
 int crab_gemm_skinny_plan(int N, int K, int* splits, int64_t* workspace_bytes, int* n_counters);
 int crab_skinny_packed_bytes(int N, int K, int64_t* bytes);

@@ -295,11 +295,49 @@ def pack_skinny_weight(w, k=None, swiglu=False):
     return PackedWeight(w, w.shape[0], k if k is not None else w.shape[1], swiglu)
 
 
-def gemm_skinny(x, w, *, bias=None, residual=None, act=ACT_NONE, out=None, out_dtype=torch.bfloat16, k=None, n=None, splits=0):
+def _fused_linear(x, w, k, z, kext, stats, L, norm, eps, scale, bias, residual, act, out, n, M):
+    """One decode linear with the RMSNorm as an epilogue scale and the hyper-LoRA pre-pass from the statistics rows."""
+    xf = x[:M, :k].float()
+    rstd = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps) if norm else torch.ones(M, 1)
+    if L:
+        t = (xf @ stats[: 11 * L].float().t()).view(M, L, 11)
+        r = torch.softmax(t[..., :3] * rstd.unsqueeze(-1), -1) * scale
+        z[:M, : L * 24] = (r.unsqueeze(-1) * t[..., 3:].unsqueeze(-2)).reshape(M, L * 24).to(torch.bfloat16)
+    W = w.data
+    y = xf @ W[: w.N, :k].float().t()
+    if kext:
+        kx = min(kext, z.shape[1])
+        y = y + z[:M, :kx].float() @ W[: w.N, k: k + kx].float().t()
+    y = y * rstd
+    if act == ACT_SWIGLU:
+        assert w.swiglu and bias is None and residual is None
+        y = _swiglu_packed(y)
+    else:
+        y = y[:, :n]
+        if bias is not None:
+            y = y + bias[:n]
+        if residual is not None:
+            y = y + residual[:M, :n].float()
+    out[:M, : y.shape[1]] = y.to(out.dtype)
+
+
+def gemm_skinny(x, w, *, bias=None, residual=None, act=ACT_NONE, out=None, out_dtype=torch.bfloat16, k=None, n=None, splits=0,
+                z=None, kext=0, stats=None, stats_linears=0, norm=False, eps=0.0, lora_scale=1.0, rstd=None, flags=None, tag=""):
     packed = isinstance(w, PackedWeight)
+    if packed and (kext or norm or stats_linears):
+        assert (not norm and not stats_linears) or flags is not None
+        K, N = w.K - kext, (n if n is not None else w.N)
+        assert x.shape[0] <= 32 and K % 64 == 0 or MIN_K < 64
+        n_out = N // 2 if act == ACT_SWIGLU else N
+        if out is None:
+            out = torch.empty((x.shape[0], n_out), dtype=out_dtype)
+        _fused_linear(x, w, K, z, kext, stats, stats_linears, norm, eps, lora_scale, bias, residual, act, out, N, x.shape[0])
+        return out
     W = w.data if packed else w
     K = w.K if packed else (k if k is not None else x.shape[1])
     N = w.N if packed else (n if n is not None else W.shape[0])
+    if n is not None:
+        N = n
     assert x.shape[0] <= 32 and x.stride(0) % 8 == 0 and x.shape[1] >= K
     y = x[:, :K].float() @ W[:N, :K].float().t()
     if act == ACT_SWIGLU:
@@ -338,29 +376,8 @@ def decode_chain(phases, M, counters, cluster=0, max_clusters=0, tag="crab_decod
     caller), hyper-LoRA pre-pass from the statistics rows, z' = scale * softmax(rstd * logits) * u un-normalised."""
     assert 1 <= len(phases) <= 4 and M <= 32
     for ph in phases:
-        x = ph.x[:M, : ph.k].float()
-        rstd = torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + ph.eps) if ph.norm else torch.ones(M, 1)
-        if ph.stats_linears:
-            t = (x @ ph.stats[: 11 * ph.stats_linears].float().t()).view(M, ph.stats_linears, 11)
-            r = torch.softmax(t[..., :3] * rstd.unsqueeze(-1), -1) * ph.lora_scale
-            zz = (r.unsqueeze(-1) * t[..., 3:].unsqueeze(-2)).reshape(M, ph.stats_linears * 24)
-            ph.z[:M, : ph.stats_linears * 24] = zz.to(torch.bfloat16)
-        W = ph.w.data
-        y = x @ W[: ph.w.N, : ph.k].float().t()
-        if ph.kext:
-            kx = min(ph.kext, ph.z.shape[1])
-            y = y + ph.z[:M, :kx].float() @ W[: ph.w.N, ph.k: ph.k + kx].float().t()
-        y = y * rstd
-        if ph.act == ACT_SWIGLU:
-            assert ph.w.swiglu and ph.bias is None and ph.residual is None
-            y = _swiglu_packed(y)
-        else:
-            y = y[:, : ph.n]
-            if ph.bias is not None:
-                y = y + ph.bias[: ph.n]
-            if ph.residual is not None:
-                y = y + ph.residual[:M, : ph.n].float()
-        ph.out[:M, : y.shape[1]] = y.to(ph.out.dtype)
+        _fused_linear(ph.x, ph.w, ph.k, ph.z, ph.kext, ph.stats, ph.stats_linears, ph.norm, ph.eps, ph.lora_scale, ph.bias,
+                      ph.residual, ph.act, ph.out, ph.n, M)
 
 
 def argmax(logits, V, out=None):

@@ -229,3 +229,80 @@ def test_chain_inside_cuda_graph(cuda_dev):
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, eager)
+
+
+# ---- the same fused linears as ONE crab_gemm_skinny_bf16 launch each (the default decode path) -----------------------------
+def _flags(dev):
+    return torch.zeros(64, dtype=torch.int32, device=dev)
+
+
+@pytest.mark.parametrize("M", [32, 6])
+def test_fused_skinny_qkv_like(cuda_dev, M):
+    """RMSNorm as epilogue scale + three LoRA linears from the in-launch statistics cluster + bias (auto split = 2)."""
+    from crab_b200 import ops
+
+    lin = Lin(cuda_dev, 51, 4096, [4096, 4096, 4096], lora=True, gamma=True, bias=True, kext=96)
+    x = mk((M, 4096), cuda_dev, 52, 3.0).to(torch.bfloat16)
+    out = torch.empty((M, lin.N), device=cuda_dev, dtype=torch.bfloat16)
+    z = torch.zeros((32, 128), device=cuda_dev, dtype=torch.bfloat16)
+    rstd = torch.zeros(32, device=cuda_dev, dtype=torch.float32)
+    fl = _flags(cuda_dev)
+    for _ in range(2):   # second launch: the flags must have been left clean
+        ops.gemm_skinny(x, lin.packed, bias=lin.bias, out=out, z=z, kext=96, stats=lin.stats, stats_linears=3, norm=True, eps=1e-6,
+                        lora_scale=lin.scale, rstd=rstd, flags=fl)
+        torch.cuda.synchronize()
+        assert int(fl.abs().sum()) == 0
+        assert torch.allclose(rstd[:M], torch.rsqrt(x.float().pow(2).mean(-1) + 1e-6), rtol=1e-5, atol=0)
+        e = rel(out, lin.ref(x))
+        assert e < 6e-3, e
+
+
+def test_fused_skinny_gate_up_down_head(cuda_dev):
+    """gate/up (SwiGLU, norm, 2 LoRA linears, no K split) -> down (K = 11008, 8-way split, 1 LoRA linear, in-place residual) ->
+    final norm + lm_head (ragged N, fp32 out), each one launch, chained through bf16 buffers like the decode step."""
+    from crab_b200 import ops
+
+    dev = cuda_dev
+    D, F = 4096, 11008
+    gu = Lin(dev, 61, D, [F, F], lora=True, gamma=True, swiglu=True, kext=64)
+    dn = Lin(dev, 62, F, [D], lora=True)
+    hd = Lin(dev, 63, D, [32017], lora=False, gamma=True)
+    for M in (32, 2):
+        x0 = mk((M, D), dev, 64, 2.0).to(torch.bfloat16)
+        x = x0.clone()
+        hh = torch.empty((M, F), device=dev, dtype=torch.bfloat16)
+        logits = torch.zeros((M, 32024), device=dev, dtype=torch.float32)
+        zb = {k: torch.zeros((32, 128), device=dev, dtype=torch.bfloat16) for k in ("gu", "d")}
+        rs = {k: torch.zeros(32, device=dev, dtype=torch.float32) for k in ("gu", "h")}
+        ops.gemm_skinny(x, gu.packed, act=ops.ACT_SWIGLU, out=hh, z=zb["gu"], kext=64, stats=gu.stats, stats_linears=2, norm=True, eps=1e-6,
+                        lora_scale=gu.scale, rstd=rs["gu"], flags=_flags(dev))
+        ops.gemm_skinny(hh, dn.packed, residual=x, out=x, z=zb["d"], kext=32, stats=dn.stats, stats_linears=1, lora_scale=dn.scale,
+                        flags=_flags(dev))
+        ops.gemm_skinny(x, hd.packed, out=logits, n=32017, norm=True, eps=1e-6, rstd=rs["h"], flags=_flags(dev))
+        torch.cuda.synchronize()
+        h1 = gu.ref(x0).to(torch.bfloat16)
+        x1 = dn.ref(h1, x0).to(torch.bfloat16)
+        lg = hd.ref(x1)
+        e = (rel(hh, h1), rel(x, x1), rel(logits[:, :32017], lg))
+        print(f"fused skinny M {M}: h {e[0]:.3e} x {e[1]:.3e} logits {e[2]:.3e}")
+        assert max(e) < 8e-3, e
+
+
+def test_engine_decode_modes_agree(cuda_dev):
+    """The two decode-step organisations (one fused launch per linear / the persistent chain) run the same arithmetic: on the small
+    golden case their teacher-forced logits agree to bf16 round-off and both stay within the engine's parity bound of the oracle."""
+    from helpers import engine_cfg, load_golden
+    from crab_b200.engine import CrabEngine
+
+    g, case, sd, ocfg, ids, X = load_golden("llama_small")
+    emb = g["inputs_embeds"].to(cuda_dev).to(torch.bfloat16)
+    ref_ids = g["generated_ids"].to(cuda_dev)
+    outs = {}
+    for mode in ("skinny", "chain"):
+        eng = CrabEngine(sd, engine_cfg(case, ocfg), cuda_dev, load_encoders=False)
+        eng.decode_mode = mode
+        _, logits = eng.generate_from_embeds(emb.clone(), ref_ids.shape[1], return_logits=True, teacher_tokens=ref_ids)
+        outs[mode] = logits.float().cpu()
+    e = rel(outs["chain"], outs["skinny"])
+    print(f"decode modes: chain vs skinny logits rel_l2 {e:.3e}")
+    assert e < 1.2e-2   # measured 6.5e-3: two bf16 roundings of the same arithmetic (different split-K / reduction orders)
