@@ -142,8 +142,8 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
       auto load_w = [&](int slot_i, int kb) {
         const uint32_t sw = smem_base + slot_i * SK_STAGE_BYTES;
         if (is_stats) {
-          // x tile twice (A rows 0..31 and the B operand) + the router/A rows: armed here, the x loads follow the PDL wait
-          mbar_arrive_expect_tx(full_bar(slot_i), 2 * SK_X_BYTES + (p.stats_w ? SK_S_BYTES : 0));
+          // x tile (it is both the B operand and, for x x^T, an A operand) + the router/A rows: armed here, x follows the PDL wait
+          mbar_arrive_expect_tx(full_bar(slot_i), SK_X_BYTES + (p.stats_w ? SK_S_BYTES : 0));
           if (p.stats_w) bulk_load_1d_hint(sw + SK_X_BYTES, p.stats_w + (size_t)kb * (SK_SROWS * SK_BK), SK_S_BYTES, full_bar(slot_i), kEvictFirst);
         } else {
           mbar_arrive_expect_tx(full_bar(slot_i), SK_STAGE_BYTES);
@@ -156,7 +156,6 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
         const uint32_t sw = smem_base + slot_i * SK_STAGE_BYTES;
         if (is_stats) {
           tma_load_2d_hint(sw + SK_W_BYTES, &tmap_x, full_bar(slot_i), kb * SK_BK, 0, kEvictLast);
-          tma_load_2d_hint(sw, &tmap_x, full_bar(slot_i), kb * SK_BK, 0, kEvictLast);
         } else if (p.ext_from_z && kb >= p.kb_main) {
           if (p.has_stats && !z_ok) {   // z' comes from this launch's statistics cluster
             sk_wait_flag(p.flags);
@@ -191,8 +190,12 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
         const uint32_t sw = smem_base + stage * SK_STAGE_BYTES;
         const uint64_t da = make_sdesc_sw128(sw);
         const uint64_t db = make_sdesc_sw128(sw + SK_W_BYTES);
+        // Statistics cluster: the A tile starts 4 KB into the slot, so its rows 0..39 are the gamma*[R;A] rows and its rows
+        // 96..127 are the x tile itself (slot + 16 KB): ONE MMA chain gives the router / A dots (TMEM lanes 0..39) and
+        // x x^T (lanes 96..127, diagonal = sum x^2) from a single copy of x.
+        const uint64_t da_ = is_stats ? make_sdesc_sw128(sw + SK_X_BYTES) : da;
 #pragma unroll
-        for (int k = 0; k < SK_BK / 16; ++k) umma_bf16_ss(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb > kb0) | (k > 0));
+        for (int k = 0; k < SK_BK / 16; ++k) umma_bf16_ss(tmem_base, da_ + 2u * k, db + 2u * k, idesc, (kb > kb0) | (k > 0));
         umma_commit(empty_bar(stage));
         if (++stage == SK_STAGES) { stage = 0; phase ^= 1; }
       }
@@ -219,13 +222,22 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   if (is_stats) {
     // ---- statistics cluster: partial x x^T rows / router-A dots of every rank -> rank 0 -> rstd, z', flag ----
     cluster_sync_all();   // every CTA of the cluster has finished its MMAs: the TMA ring is free to hold partials
-    if (epi && row < SK_SSROWS) {
-      const uint32_t local = smem_base + (uint32_t)((rank * SK_SSROWS + row) * SK_PSTRIDE * 4);
+    if (epi && row < SK_SROWS) {
+      // dots row `row` -> slot 32 + row of rank 0's buffer
+      const uint32_t local = smem_base + (uint32_t)((rank * SK_SSROWS + 32 + row) * SK_PSTRIDE * 4);
       const uint32_t remote = map_to_rank(local, 0u);
 #pragma unroll
       for (int g = 0; g < 8; ++g)
         st_cluster_f4(remote + g * 16, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
                       __uint_as_float(r[4 * g + 3]));
+    } else if (epi && row >= 96) {
+      // x x^T row of batch row b = row - 96: only its diagonal element is needed -> slot b, column b
+      const int b = row - 96;
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) d = (c == b) ? __uint_as_float(r[c]) : d;
+      const uint32_t dl = smem_base + (uint32_t)(((rank * SK_SSROWS + b) * SK_PSTRIDE + b) * 4);
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(map_to_rank(dl, 0u)), "f"(d) : "memory");
     }
     cluster_sync_all();
     if (rank == 0 && epi) {

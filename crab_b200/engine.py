@@ -22,6 +22,7 @@ import torch
 from . import ops
 
 SD = Dict[str, torch.Tensor]
+DEFAULT_DECODE_MODE = "skinny"
 DEFAULT_PDL_PLAN = "19,17"  # streaming GEMM + light kernels launch programmatically; attention / RoPE stay plain launches
 
 
@@ -162,6 +163,11 @@ class CrabEngine:
         ops.init(self.dev.index or 0)
         self.cfg = cfg
         self.decode_packed = decode_packed
+        # decode step for <= 32 rows (CRAB_DECODE_MODE): "rows" = round-1 organisation, a cluster row kernel (RMSNorm + hyper-LoRA
+        # pre-pass) in front of every weight-streaming GEMM (8 launches per layer); "skinny" = one fused launch per linear, the norm
+        # as an epilogue scale and the pre-pass by an in-launch statistics cluster (5 per layer); "chain" = the persistent
+        # o -> gate/up -> down -> qkv kernel (2 per layer).  Measured on B200 at bs 32: see DEFAULT_DECODE_MODE.
+        self.decode_mode = os.environ.get("CRAB_DECODE_MODE", DEFAULT_DECODE_MODE)
         sd = {(k[len("base_model.model."):] if k.startswith("base_model.model.") else k): v for k, v in sd.items()}
         self._pack_decoder(sd)
         self.seg = None
@@ -182,9 +188,6 @@ class CrabEngine:
         # decode attention).  Env CRAB_PDL_PLAN="chain,after_attn" overrides; see profiles/r02_pdl_plans.txt for the A/B.
         plan = os.environ.get("CRAB_PDL_PLAN", DEFAULT_PDL_PLAN).split(",")
         self.pdl_chain, self.pdl_after_attn = int(plan[0]), int(plan[-1])
-        # decode step for <= 32 rows: "skinny" = one fused weight-streaming launch per linear (5 launches per layer, default);
-        # "chain" = the persistent o -> gate/up -> down -> qkv kernel (2 launches per layer; slower today)
-        self.decode_mode = os.environ.get("CRAB_DECODE_MODE", "skinny")
         # K-split (= thread-block-cluster size) of the persistent decode GEMM chain
         self.chain_cluster = int(os.environ.get("CRAB_CHAIN_CLUSTER", "4"))
         # decode step: RoPE + KV append + o_proj LoRA pre-pass inside the attention kernel (8 launches per layer, not 10)
@@ -223,10 +226,14 @@ class CrabEngine:
         lm[:V] = _bf(sd["lm_head.weight"], dev)
         self.lm_head = lm
         # decode / last-position head: final-norm gamma folded into the streaming copy (the chain applies rstd in its epilogue)
-        lmf = lm.clone()
-        lmf[:] = (lm.float() * self.final_norm[None, :]).to(torch.bfloat16)
-        self.lm_head_c = ops.pack_skinny_weight(lmf) if self.decode_packed else None
-        del lmf
+        self.lm_head_c = self.lm_head_p = None
+        if self.decode_packed and self.decode_mode == "rows":
+            self.lm_head_p = ops.pack_skinny_weight(lm)
+        elif self.decode_packed:
+            lmf = lm.clone()
+            lmf[:] = (lm.float() * self.final_norm[None, :]).to(torch.bfloat16)
+            self.lm_head_c = ops.pack_skinny_weight(lmf)
+            del lmf
         self.scaling = c.lora_alpha / c.lora_r
         nl, r = c.lora_nums, c.lora_r
         zw = nl * r  # 24 z columns per linear
@@ -291,7 +298,13 @@ class CrabEngine:
             L["wd"] = wd
             L["ln1"] = _f32(sd[lp + "input_layernorm.weight"], dev)
             L["ln2"] = _f32(sd[lp + "post_attention_layernorm.weight"], dev)
-            if self.decode_packed:
+            if self.decode_packed and self.decode_mode == "rows":
+                lo = self.lora
+                L["wqkv_p"] = ops.pack_skinny_weight(wq, k=D + (self.EXT_QKV if lo else 0))
+                L["wo_p"] = ops.pack_skinny_weight(wo, k=nq + (self.EXT_O if lo else 0))
+                L["wgu_p"] = ops.pack_skinny_weight(L["wgu"], k=D + (self.EXT_GU if lo else 0), swiglu=True)
+                L["wd_p"] = ops.pack_skinny_weight(wd, k=F + (self.EXT_D if lo else 0))
+            elif self.decode_packed:
                 # second copy of the decode-step weights in the streaming layout (contiguous pre-swizzled 16 KB tile
                 # blocks): the prefill GEMM wants row-major K-extended rows, the M<=32 chain wants sequential HBM.
                 # The chain applies RMSNorm as rstd[b] in its epilogue, so gamma is folded into the columns here; the
@@ -712,7 +725,10 @@ class CrabEngine:
     def _head(self, x_last: torch.Tensor, logits: torch.Tensor, next_ids: torch.Tensor):
         """final RMSNorm -> lm_head (fp32 logits) -> greedy arg-max."""
         c = self.cfg.decoder
-        if x_last.shape[0] <= 32 and self.lm_head_c is not None:
+        if x_last.shape[0] <= 32 and self.lm_head_p is not None:
+            hn = ops.rmsnorm(x_last, self.final_norm, c.eps, out=self._buf("head_hn", tuple(x_last.shape)))
+            ops.gemm_skinny(hn, self.lm_head_p, out=logits, n=self.vocab)
+        elif x_last.shape[0] <= 32 and self.lm_head_c is not None:
             # one launch: the statistics cluster computes rstd, the lm_head tiles apply it in their epilogue (gamma is in lm_head_c)
             ops.gemm_skinny(x_last, self.lm_head_c, out=logits, n=self.vocab, norm=True, eps=c.eps,
                             rstd=self._buf("dec_rstd_head", (32,), torch.float32), flags=self._flags("head"), tag="lm_head_skinny")
@@ -878,6 +894,51 @@ class CrabEngine:
         finally:
             ops.set_pdl(0)  # prefill / encoder launches are never PDL launches
 
+    def _decode_body_rows(self, B: int, nsplit: int, ws):
+        """Decode step, round-1 organisation (8 launches per layer): a cluster row kernel (RMSNorm + hyper-LoRA router / A pre-pass
+        -> normalised row + z columns) in front of each weight-streaming GEMM, whose K-extension columns sit behind the row."""
+        c = self.cfg.decoder
+        D, F, H, KV, hd = c.hidden, c.inter, c.heads, c.kv_heads, c.head_dim
+        nq, nk = H * hd, KV * hd
+        lo, sc = self.lora, self.scaling
+        x = self._buf("dec_x", (B, D))
+        xn = self._buf("dec_xn", (B, D + self.EXT_QKV), zero=True)
+        qkv = self._buf("dec_qkv", (B, nq + 2 * nk))
+        at = self._buf("dec_attn", (B, nq + self.EXT_O), zero=True)
+        hh = self._buf("dec_hx", (B, F + self.EXT_D), zero=True)
+        G = H // KV
+        gqa_tc = G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
+        fused = self.fuse_decode_attn and not gqa_tc
+        o_fused_lora = lo and fused and nsplit == 1
+        ops.set_pdl(self.pdl_chain)
+        try:
+            ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)
+            for li, L in enumerate(self.layers):
+                ops.row_norm_loraz(x, gamma=L["ln1"], eps=c.eps, y=xn[:, :D], ra=L.get("ra_qkv"), groups=3 if lo else 0,
+                                   z=xn[:, D:] if lo else None, scale=sc)
+                ops.gemm_skinny(xn, L["wqkv_p"], bias=L["bqkv"], out=qkv)
+                self._decode_attention(li, B, nsplit, ws, qkv, at, fused, gqa_tc, o_fused_lora)
+                if self.pdl_after_attn != self.pdl_chain:
+                    ops.set_pdl(self.pdl_after_attn)
+                if lo and not o_fused_lora:
+                    ops.row_norm_loraz(at[:, :nq], ra=L["ra_o"], groups=1, z=at[:, nq:], scale=sc)
+                    if self.pdl_after_attn != self.pdl_chain:
+                        ops.set_pdl(self.pdl_chain)
+                ops.gemm_skinny(at, L["wo_p"], residual=x, out=x)
+                if self.pdl_after_attn != self.pdl_chain:
+                    ops.set_pdl(self.pdl_chain)
+                ops.row_norm_loraz(x, gamma=L["ln2"], eps=c.eps, y=xn[:, :D], ra=L.get("ra_gu"), groups=2 if lo else 0,
+                                   z=xn[:, D:] if lo else None, scale=sc)
+                ops.gemm_skinny(xn, L["wgu_p"], act=ops.ACT_SWIGLU, out=hh[:, :F])
+                if lo:
+                    ops.row_norm_loraz(hh[:, :F], ra=L["ra_d"], groups=1, z=hh[:, F:], scale=sc)
+                ops.gemm_skinny(hh, L["wd_p"], residual=x, out=x)
+            self._head(x, self.logits, self.next_ids)
+            ops.add_scalar_i32(self.past_dev, 1)
+            ops.add_scalar_i32(self.len_dev, 1)
+        finally:
+            ops.set_pdl(0)
+
     def _decode_body(self, B: int, nsplit: int, ws):
         c = self.cfg.decoder
         D, H, KV, hd = c.hidden, c.heads, c.kv_heads, c.head_dim
@@ -892,6 +953,8 @@ class CrabEngine:
             ops.add_scalar_i32(self.past_dev, 1)
             ops.add_scalar_i32(self.len_dev, 1)
             return
+        if self.decode_mode == "rows":
+            return self._decode_body_rows(B, nsplit, ws)
         if self.decode_mode != "chain":
             return self._decode_body_skinny(B, nsplit, ws)
         plan = self._chain_plan(B, nsplit)
