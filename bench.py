@@ -98,13 +98,15 @@ class LazySynthSD:
         return r / math.sqrt(n // shape[0])
 
 
-def make_inputs(bs, frames, audio_segs, audio_len, prompt_len, base_vocab, ids_map, rank):
+def make_inputs(bs, frames, audio_segs, audio_len, prompt_len, base_vocab, ids_map, rank, pin=True):
     """Pinned host tensors, per-sample seeds 1000+i."""
     ids, X = [], []
     for i in range(bs):
         g = torch.Generator(device="cpu").manual_seed(1000 + i + 100000 * rank)
-        video = torch.randn(frames, 3, 224, 224, generator=g).pin_memory()
-        audio = (0.5 * torch.randn(audio_segs, audio_len, 128, generator=g)).pin_memory()
+        video = torch.randn(frames, 3, 224, 224, generator=g)
+        audio = 0.5 * torch.randn(audio_segs, audio_len, 128, generator=g)
+        if pin:
+            video, audio = video.pin_memory(), audio.pin_memory()
         t = torch.randint(3, base_vocab, (prompt_len,), generator=g)
         t[10] = ids_map["<video>"]
         t[20] = ids_map["<audio>"]
@@ -176,33 +178,35 @@ def algorithmic_prefill_tflop(b, S):
 
 # CPU arm: the oracle port on the host cores, on a bounded sample of the same workload
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_port_run(args, threads):
-    """Times oracle/crab_oracle.py (the CPU restatement of the reference's path; the reference itself is Python +
-    HF and cannot travel to the GPU box).  Bounded sample: ONE sample of the batch, `cpu_layers` of each stack, and
-    `cpu_steps` decode steps, scaled to the full depth / 128 steps (every layer of a stack costs the same).
-    Returns (tokens_per_s, sample_description, detail)."""
-    from oracle import crab_oracle as O
-    from oracle import synth
-
-    torch.set_num_threads(threads)
-    Ls, steps = args.cpu_layers, args.cpu_steps
-    b = backbone(args)
-    dec = O.DecoderCfg(hidden=b["hidden"], inter=b["inter"], layers=Ls, heads=b["heads"], kv_heads=b["kv_heads"],
-                       head_dim=b["head_dim"], vocab=b["vocab"], rope_theta=b["rope_theta"], qkv_bias=b["qkv_bias"])
-    cfg = O.CrabCfg(decoder=dec, clip=O.ClipCfg(layers=Ls), beats=O.BeatsCfg(layers=Ls), qformer=O.QformerCfg(),
-                    select_layers=(Ls,), image_tokens=256, base_vocab=b["base_vocab"])
+def cpu_manifest(args, enc_layers_clip, enc_layers_beats, dec_layers):
     from crab_b200.engine import BeatsConfig, ClipConfig, CrabConfig, DecoderConfig, QformerConfig
     from crab_b200.models.unified_arch import full_manifest
 
-    ecfg = CrabConfig(decoder=DecoderConfig(hidden=b["hidden"], inter=b["inter"], layers=Ls, heads=b["heads"],
+    b = backbone(args)
+    ecfg = CrabConfig(decoder=DecoderConfig(hidden=b["hidden"], inter=b["inter"], layers=dec_layers, heads=b["heads"],
                                             kv_heads=b["kv_heads"], head_dim=b["head_dim"], vocab=b["vocab"],
                                             rope_theta=b["rope_theta"], qkv_bias=b["qkv_bias"]),
-                      clip=ClipConfig(layers=Ls), beats=BeatsConfig(layers=Ls), qformer=QformerConfig())
-    man = full_manifest(ecfg)
-    sd = synth.synth_state_dict(man, 42)
-    video, audio, ids = synth.synth_inputs(1000, frames=8, image=224, audio_segs=10, audio_len=98,
-                                           prompt_len=args.prompt_len, base_vocab=b["base_vocab"],
-                                           video_id=cfg.special_ids["<video>"], audio_id=cfg.special_ids["<audio>"])
+                      clip=ClipConfig(layers=enc_layers_clip), beats=BeatsConfig(layers=enc_layers_beats), qformer=QformerConfig())
+    return full_manifest(ecfg)
+
+
+def cpu_port_run(args, threads, sd, clip_layers, beats_layers, dec_layers, ids_list, media, pf_bs=2, keep=False):
+    """One bounded sample of the workload on the host cores through oracle/crab_oracle.py (fp32, `threads` threads), at the
+    arm's own configuration where batch size matters:
+      encoders + bridges of ONE sample (`clip_layers` of 23 / `beats_layers` of 12 layers, scaled per layer),
+      decoder prefill at bs `pf_bs` over S positions and `dec_layers` layers (GEMM-bound: per-token cost does not depend on bs),
+      `cpu_steps` decode steps at the FULL batch (args.bs rows, KV cache of the prefill tiled up to it), `dec_layers` layers,
+    all scaled to the full depths / 32 samples / 128 tokens.  Returns (tokens_per_s, sample_description, detail[, tensors])."""
+    from oracle import crab_oracle as O
+
+    torch.set_num_threads(threads)
+    b = backbone(args)
+    dec = O.DecoderCfg(hidden=b["hidden"], inter=b["inter"], layers=dec_layers, heads=b["heads"], kv_heads=b["kv_heads"],
+                       head_dim=b["head_dim"], vocab=b["vocab"], rope_theta=b["rope_theta"], qkv_bias=b["qkv_bias"])
+    cfg = O.CrabCfg(decoder=dec, clip=O.ClipCfg(layers=clip_layers), beats=O.BeatsCfg(layers=beats_layers), qformer=O.QformerCfg(),
+                    select_layers=(clip_layers,) if clip_layers < 23 else (14, 22, 23), image_tokens=256, base_vocab=b["base_vocab"])
+    video, audio = media
+    steps = args.cpu_steps
     with torch.no_grad():
         t0 = time.perf_counter()
         taps = O.visual_encoder(sd, video.unsqueeze(0), cfg.clip, cfg.select_layers)
@@ -217,31 +221,50 @@ def cpu_port_run(args, threads):
         al = O.al_projector(sd, be, cfg.qformer)[0]
         t_al = time.perf_counter() - t0
         emb = sd["model.embed_tokens.weight"]
-        x = torch.cat([emb[ids[:10]], vl, emb[ids[11:20]], al, emb[ids[21:]]], 0).unsqueeze(0)
+        rows = []
+        for ids in ids_list[:pf_bs]:   # same media, each sample's own prompt: placeholders at 10 (<video>) and 20 (<audio>)
+            rows.append(torch.cat([emb[ids[:10]], vl, emb[ids[11:20]], al, emb[ids[21:]]], 0))
+        x = torch.stack(rows, 0)
         S = x.shape[1]
         t0 = time.perf_counter()
         h, cache = O.decoder_forward(sd, x, dec)
         t_pf = time.perf_counter() - t0
         t0 = time.perf_counter()
-        logits = O.lm_head(sd, h[:, -1])
-        t_head = time.perf_counter() - t0
-        nxt = logits.argmax(-1)
+        logits0 = O.lm_head(sd, h[:, -1])
+        t_head_pf = time.perf_counter() - t0
+        rep = max(args.bs // pf_bs, 1)
+        cache.k = [k.repeat(rep, 1, 1, 1) for k in cache.k]
+        cache.v = [v.repeat(rep, 1, 1, 1) for v in cache.v]
+        nxt = logits0.argmax(-1).repeat(rep)
+        fed, dec_logits = [], []
+        t_head = 0.0
         t0 = time.perf_counter()
         for _ in range(steps):
+            fed.append(nxt)
             h, cache = O.decoder_forward(sd, emb[nxt].unsqueeze(1), dec, cache)
-            nxt = O.lm_head(sd, h[:, -1]).argmax(-1)
-        t_dec = (time.perf_counter() - t0) / steps
-    # scale the sampled depth to the full stacks: CLIP 23 layers, BEATs 12, decoder 32 (+ lm_head once per step)
-    t_dec_layers = max(t_dec - t_head, 0.0)
-    t_prefill = t_clip * 23 / Ls + t_vl + t_beats * 12 / Ls + t_al + t_pf * b["layers"] / Ls + t_head
-    t_step = t_dec_layers * b["layers"] / Ls + t_head
-    t_total = t_prefill + 127 * t_step
-    tok_s = (S + args.new_tokens) / t_total
-    detail = {"prefill_tok_s": S / t_prefill, "decode_tok_s": 1.0 / t_step, "t_prefill_s": t_prefill, "t_decode_step_s": t_step,
-              "S": S, "measured": {"clip_s": t_clip, "vl_s": t_vl, "beats_s": t_beats, "al_s": t_al, "prefill_s": t_pf,
-                                   "lm_head_s": t_head, "decode_step_s": t_dec}}
-    sample = (f"1 of {args.bs} samples (fp32, {threads} threads): {Ls} of 23 CLIP / {Ls} of 12 BEATs / {Ls} of {b['layers']} decoder "
-              f"layers at full width, S={S}, {steps} decode steps; times scaled by layer count and to 128 tokens")
+            th = time.perf_counter()
+            lg = O.lm_head(sd, h[:, -1])
+            t_head += time.perf_counter() - th
+            dec_logits.append(lg)
+            nxt = lg.argmax(-1)
+        t_dec = (time.perf_counter() - t0) / max(steps, 1)
+        t_head /= max(steps, 1)
+    L, bsf = b["layers"], args.bs
+    t_enc1 = t_clip * 23 / clip_layers + t_vl + t_beats * 12 / beats_layers + t_al
+    t_prefill = bsf * t_enc1 + (bsf / pf_bs) * (t_pf * L / dec_layers + t_head_pf)
+    t_step = (t_dec - t_head) * L / dec_layers + t_head
+    t_total = t_prefill + (args.new_tokens - 1) * t_step
+    tok_s = bsf * (S + args.new_tokens) / t_total
+    detail = {"prefill_tok_s": bsf * S / t_prefill, "decode_tok_s": bsf / t_step, "t_prefill_s": t_prefill, "t_decode_step_s": t_step,
+              "S": S, "batch": bsf,
+              "measured": {"clip_s": t_clip, "vl_s": t_vl, "beats_s": t_beats, "al_s": t_al, "prefill_s": t_pf, "prefill_bs": pf_bs,
+                           "lm_head_s": t_head, "decode_step_s": t_dec, "decode_bs": pf_bs * rep}}
+    sample = (f"fp32, {threads} threads: encoders + bridges of 1 sample ({clip_layers} of 23 CLIP / {beats_layers} of 12 BEATs layers), decoder "
+              f"prefill at bs {pf_bs} x S={S} and {steps} decode steps at bs {pf_bs * rep} (KV cache tiled), {dec_layers} of {L} decoder layers at "
+              f"full width; scaled per layer, to {bsf} samples and to {args.new_tokens} tokens")
+    if keep:
+        return tok_s, sample, detail, {"inputs_embeds": x, "prefill_logits": logits0, "fed": torch.stack(fed, 0), "decode_logits": torch.stack(dec_logits, 0),
+                                       "vl": vl, "al": al}
     return tok_s, sample, detail
 
 
@@ -249,24 +272,33 @@ _emit = lambda text: print(text, flush=True)  # main() re-points this at the rea
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference path's CPU restatement (oracle/crab_oracle.py, kind "port": the reference is Python + HF and
+    does not exist on the GPU box) timed on all host cores, one bounded sample per step, on the SAME config as our arm."""
+    from oracle import synth
+
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    b = backbone(args)
+    cl = bl = dl = args.ref_layers
+    man = cpu_manifest(args, cl, bl, dl)
+    sd = synth.synth_state_dict(man, 42)
+    ids_map = {"<video>": b["base_vocab"] + 3, "<audio>": b["base_vocab"] + 6}
+    ids, X = make_inputs(2, 8, 10, 98, args.prompt_len, b["base_vocab"], ids_map, 0, pin=False)
+    media = (X[0]["<video>"], X[0]["<audio>"])
     vals = []
     for _ in range(max(args.warmup, 0)):
-        cpu_port_run(args, threads)
+        cpu_port_run(args, threads, sd, cl, bl, dl, ids, media, pf_bs=1)
     t0 = time.perf_counter()
     for _ in range(max(args.steps, 1)):
-        vals.append(cpu_port_run(args, threads))
+        vals.append(cpu_port_run(args, threads, sd, cl, bl, dl, ids, media, pf_bs=1))
     wall = time.perf_counter() - t0
     v, sample, detail = sorted(vals, key=lambda z: z[0])[len(vals) // 2]
     line = {"metric": "AV-prompt prefill+decode tokens/sec", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": max(args.steps, 1), "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "impl": "reference",
-            "config": workload_config(args, note="CPU oracle port of the reference path (oracle/crab_oracle.py); "
-                                                 "bs-1 bounded sample, see cpu_baseline.sample"),
+            "impl": "reference", "config": workload_config(args),
             "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample, **detail},
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -279,11 +311,202 @@ def workload_config(args, note=None):
     c = {"workload": f"bs{args.bs}_avqa_10s-audio_8x224-video_{args.prompt_len}tok-prompt_{args.new_tokens}new_{args.backbone}7b-dims_hyperlora",
          "per_gpu_batch": args.bs, "frames": 8, "audio_segments": 10, "prompt_len": args.prompt_len,
          "seq_len_after_splice": args.prompt_len + 574, "new_tokens": args.new_tokens, "decoder_layers": b["layers"],
-         "backbone": args.backbone,
+         "backbone": args.backbone, "global_batch": getattr(args, "global_batch", args.bs),
          "l2_policy": f"working set per step (~14 GB weights + {kv_gb:.1f} GB KV) >> 126 MB L2; no explicit flush"}
     if note:
         c["note"] = note
     return c
+
+
+def traced_decode_split(eng, n_layers, steps=4):
+    """Per-kernel split of the decode step from a CUPTI trace (torch.profiler / Kineto activity records) of `steps` CUDA-graph
+    replays.  Returns {"classes": {name: {"launches", "excl_us", "dur_us"}}, "span_us", "sum_us", "idle_us", "launches"} per step,
+    or None when the profiler is unavailable.  Numbers from this pass explain the step; the step time itself is event-timed."""
+    import tempfile
+    try:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(steps):
+                eng.decode_step()
+            torch.cuda.synchronize()
+        path = tempfile.mktemp(suffix=".json")
+        prof.export_chrome_trace(path)
+        ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
+        os.remove(path)
+    except Exception as e:
+        sys.stderr.write(f"decode trace unavailable: {e!r}\n")
+        return None
+    ev.sort(key=lambda e: e["ts"])
+    if not ev or len(ev) % steps:
+        return None
+    per = len(ev) // steps
+
+    def cls_of(name, k_skinny):
+        if "gemm_skinny" in name:
+            return ("qkv", "o", "gate_up", "down")[k_skinny % 4] if k_skinny < 4 * n_layers else "lm_head"
+        if "decode_chain" in name:
+            return "chain"
+        if "attn_decode" in name or "flash_attn" in name or "rope_kv" in name:
+            return "attention"
+        if "row_loraz" in name:
+            return "row_norm_loraz"
+        return "light (gather / arg-max / counters / norm)"
+    classes, span, total, idle = {}, 0.0, 0.0, 0.0
+    for st in range(steps):
+        chunk = ev[st * per:(st + 1) * per]
+        owner_end, k_sk = chunk[0]["ts"], 0
+        for e in chunk:
+            c = cls_of(e["name"], k_sk)
+            if "gemm_skinny" in e["name"]:
+                k_sk += 1
+            end = e["ts"] + e["dur"]
+            start = max(e["ts"], owner_end)
+            if e["ts"] > owner_end:
+                idle += e["ts"] - owner_end
+            d = classes.setdefault(c, {"launches": 0, "excl_us": 0.0, "dur_us": 0.0})
+            d["launches"] += 1
+            d["dur_us"] += e["dur"]
+            d["excl_us"] += max(end - start, 0.0)
+            owner_end = max(owner_end, end)
+            total += e["dur"]
+        span += owner_end - chunk[0]["ts"]
+    for d in classes.values():
+        d["launches"] //= steps
+        d["excl_us"] /= steps
+        d["dur_us"] /= steps
+    return {"classes": classes, "span_us": span / steps, "sum_us": total / steps, "idle_us": idle / steps, "launches": per}
+
+
+def decode_weight_bytes(eng):
+    """Algorithmic bytes one decode step must read per weight-streaming linear class (packed bf16 weights incl. the hyper-LoRA
+    B columns, plus the router / A rows)."""
+    out = {"qkv": 0.0, "o": 0.0, "gate_up": 0.0, "down": 0.0}
+    key = {"qkv": ("wqkv", "ra_qkv"), "o": ("wo", "ra_o"), "gate_up": ("wgu", "ra_gu"), "down": ("wd", "ra_d")}
+    for L in eng.layers:
+        for k, (w, ra) in key.items():
+            out[k] += L[w].numel() * 2.0 + (L[ra].numel() * 2.0 if ra in L else 0.0)
+    out["lm_head"] = eng.lm_head.numel() * 2.0
+    if eng.decode_mode == "chain":
+        return {"chain": sum(out.values())}
+    return out
+
+
+def cpu_leg_and_parity(args, b, dev, cfg, ids, X_host, eng):
+    """The in-bench CPU leg: ONE bounded sample of the workload through the oracle port on the host cores, with the SAME weights as
+    the GPU engine (copied off the device), full-depth encoders and `--cpu-layers` decoder layers — it is both the `cpu_baseline`
+    and the reference side of `parity_check`: sample 0's inputs_embeds, the prompt-pass logits and `--cpu-steps` teacher-forced
+    decode steps at the full batch, against a `--cpu-layers`-deep GPU engine built from the same tensors."""
+    from crab_b200.engine import CrabConfig, CrabEngine, DecoderConfig
+    from crab_b200.models.unified_arch import decoder_manifest
+
+    threads = os.cpu_count() or 1
+    Lc = args.cpu_layers
+    man = cpu_manifest(args, 24, 12, Lc)
+    dsd = LazySynthSD(man, 42, dev)
+    sd = {k: dsd[k].cpu() for k in man}
+    media = (X_host[0]["<video>"], X_host[0]["<audio>"])
+    v, sample, detail, t = cpu_port_run(args, threads, sd, 23, 12, Lc, ids, media, pf_bs=2, keep=True)
+    del sd
+    cpu = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample, **detail}
+
+    def rel(a, r):
+        a, r = a.detach().float().cpu(), r.detach().float().cpu()
+        return float((a - r).norm() / (r.norm() + 1e-12))
+    # ours: sample 0 through the bench engine's encoders + splice; the decoder through an Lc-layer engine on the same weights
+    emb0, _, _ = eng.prepare_inputs(ids[:1], [{k: x.to(dev) for k, x in X_host[0].items()}])
+    e_emb = rel(emb0[0], t["inputs_embeds"][0])
+    dcfg = DecoderConfig(hidden=b["hidden"], inter=b["inter"], layers=Lc, heads=b["heads"], kv_heads=b["kv_heads"],
+                         head_dim=b["head_dim"], vocab=b["vocab"], rope_theta=b["rope_theta"], qkv_bias=b["qkv_bias"])
+    eng4 = CrabEngine(LazySynthSD(decoder_manifest(dcfg), 42, dev), CrabConfig(decoder=dcfg, max_ctx=cfg.max_ctx), dev, load_encoders=False)
+    rep = args.bs // 2
+    x32 = t["inputs_embeds"].to(dev).to(torch.bfloat16).repeat(rep, 1, 1)
+    n = t["fed"].shape[0] + 1
+    _, lg = eng4.generate_from_embeds(x32, n, return_logits=True, teacher_tokens=t["fed"].t().contiguous().to(dev))
+    lg = lg.float().cpu()
+    e_pf = rel(lg[0, :2], t["prefill_logits"])
+    e_dec = [rel(lg[i + 1], t["decode_logits"][i]) for i in range(n - 1)]
+    ref_all = torch.cat([t["prefill_logits"].repeat(rep, 1).unsqueeze(0), t["decode_logits"]], 0)
+    err = float((lg - ref_all).abs().max())
+    top2 = ref_all.topk(2, dim=-1).values
+    decisive = (top2[..., 0] - top2[..., 1]) > 4 * err
+    agree = lg.argmax(-1) == ref_all.argmax(-1)
+    del eng4
+    torch.cuda.empty_cache()
+    parity = {"against": "oracle/crab_oracle.py (fp32, host) on the same device-generated weights",
+              "inputs_embeds_rel_l2_sample0": e_emb, "decoder_layers": Lc, "prefill_logits_rel_l2": e_pf,
+              "decode_logits_rel_l2_max": max(e_dec) if e_dec else None, "decode_steps": n - 1, "decode_batch": int(x32.shape[0]),
+              "max_abs_dlogit": err, "decisive_positions": int(decisive.sum()), "argmax_agree_on_decisive": bool(agree[decisive].all()),
+              "argmax_agree_all": int(agree.sum()), "positions": int(agree.numel()),
+              "yardstick_hf_bf16_vs_fp32_4_layers": 0.0123,
+              "ok": bool(e_emb < 1.6e-2 and e_pf <= 1.5 * 0.0123 and (not e_dec or max(e_dec) <= 1.5 * 0.0123) and agree[decisive].all())}
+    return cpu, parity
+
+
+def run_leg(leg, args, dev, eng, peaks):
+    """Extra single-GPU configurations of BASELINE.json reported as keys of the same line (device-timed, inputs resident):
+    bs1 = configs[1] (one sample, 64-token prompt, S = 638, 128 new tokens, same LLaMA-7B-dim engine);
+    qwen = configs[4] (Qwen2-7B dims, bs 32, 512-token prompt), a second engine built for the occasion."""
+    import argparse as _ap
+    from crab_b200.engine import BeatsConfig, ClipConfig, CrabConfig, CrabEngine, DecoderConfig, QformerConfig
+    from crab_b200.models.unified_arch import full_manifest, special_token_ids
+
+    a2 = _ap.Namespace(**vars(args))
+    if leg == "bs1":
+        a2.bs, a2.prompt_len, a2.backbone = 1, 64, args.backbone
+        e = eng
+    else:
+        a2.backbone = "qwen"
+        b2 = backbone(a2)
+        S2 = a2.prompt_len + 574
+        c2 = CrabConfig(decoder=DecoderConfig(hidden=b2["hidden"], inter=b2["inter"], layers=b2["layers"], heads=b2["heads"],
+                                              kv_heads=b2["kv_heads"], head_dim=b2["head_dim"], vocab=b2["vocab"], rope_theta=b2["rope_theta"],
+                                              qkv_bias=b2["qkv_bias"]), clip=ClipConfig(), beats=BeatsConfig(), qformer=QformerConfig(),
+                        max_ctx=(S2 + a2.new_tokens + 7) // 8 * 8, special_ids=special_token_ids(b2["base_vocab"]))
+        e = CrabEngine(LazySynthSD(full_manifest(c2), 42, dev), c2, dev)
+    b2 = backbone(a2)
+    ids_map = special_token_ids(b2["base_vocab"])
+    ids, Xh = make_inputs(a2.bs, 8, 10, 98, a2.prompt_len, b2["base_vocab"], ids_map, 7)
+    Xd = [{k: v.to(dev) for k, v in x.items()} for x in Xh]
+    S2 = a2.prompt_len + 574
+    n_new = a2.new_tokens
+
+    def one(ev=None):
+        if ev:
+            ev[0].record()
+        emb, _, _ = e.prepare_inputs(ids, Xd)
+        _, nxt = e.prefill(emb)
+        if ev:
+            ev[1].record()
+        e.begin_decode(a2.bs)
+        for _ in range(1, n_new):
+            e.decode_step()
+        if ev:
+            ev[2].record()
+    reps = 3 if leg == "bs1" else 2
+    for _ in range(3 if leg == "bs1" else 2):
+        one()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
+    torch.cuda.synchronize()
+    for r_ in range(reps):
+        one(evs[r_])
+    torch.cuda.synchronize()
+    t_pf = sum(ev[0].elapsed_time(ev[1]) for ev in evs) / reps
+    t_dc = sum(ev[1].elapsed_time(ev[2]) for ev in evs) / reps
+    step_ms = t_dc / (n_new - 1)
+    ctx_mean = S2 + 1 + (n_new - 1) / 2.0
+    wbytes = sum(decode_weight_bytes(e).values())
+    kv = a2.bs * ctx_mean * 2 * b2["kv_heads"] * b2["head_dim"] * 2 * b2["layers"]
+    out = {"workload": workload_config(a2)["workload"], "value_tok_s": a2.bs * (S2 + n_new) / ((t_pf + t_dc) / 1e3),
+           "prefill_ms": t_pf, "prefill_tok_s": a2.bs * S2 / (t_pf / 1e3), "decode_step_ms": step_ms,
+           "decode_tok_s": a2.bs / (step_ms / 1e3), "decode_bytes_per_step": wbytes + kv,
+           "decode_frac_of_hbm_roofline": (wbytes + kv) / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+           "prefill_frac_of_tensor_roofline": algorithmic_prefill_tflop(b2, S2) * 1e12 * a2.bs / (t_pf / 1e3) / (peaks["bf16_tflops_sustained"] * 1e12),
+           "steps": reps, "timing": "CUDA events, inputs resident"}
+    if leg != "bs1":
+        del e
+        torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -298,8 +521,11 @@ def main():
     ap.add_argument("--new-tokens", type=int, default=128)
     ap.add_argument("--layers", type=int, default=0, help="decoder layers (0 = the backbone's own depth)")
     ap.add_argument("--backbone", default="llama", choices=sorted(BACKBONES), help="llama = configs[2], qwen = configs[4]")
-    ap.add_argument("--cpu-layers", type=int, default=4)
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--cpu-layers", type=int, default=4, help="decoder layers of the in-bench CPU leg / parity check (full-depth encoders)")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="decode steps of the CPU sample")
+    ap.add_argument("--ref-layers", type=int, default=2, help="layers per stack of one --impl reference step (kept short: the driver runs 25 of them)")
+    ap.add_argument("--legs", default="bs1,qwen", help="extra single-GPU legs reported as keys of the same line ('' = none)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --bs is the WHOLE-job batch, split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-pass", action="store_true",
                     help="for ncu launch lists: stop after the timed resident steps (NVTX range 'crab_timed'); prints no JSON")
@@ -327,6 +553,13 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+
+    # weak scaling (default): every rank runs its own --bs samples; strong: --bs is the whole job, split over the ranks
+    args.global_batch = args.bs if args.scaling == "strong" else args.bs * world
+    if args.scaling == "strong":
+        assert args.bs % world == 0, "--scaling strong needs --bs divisible by the number of ranks"
+        args.bs //= world
+    bs_local = args.bs
 
     from crab_b200 import ops
     from crab_b200.engine import BeatsConfig, ClipConfig, CrabConfig, CrabEngine, DecoderConfig, QformerConfig
@@ -477,145 +710,142 @@ def main():
                 "fbank_ms_per_step": kraw.get("crab_kaldi_fbank", {}).get("ms", 0.0) / args.steps,
                 "patchify_u8_ms_per_step": kraw.get("crab_patchify_u8", {}).get("ms", 0.0) / args.steps}
 
-    # ---- per-kernel split of one eager (un-graphed) decode step: same kernels as the graph -------------------------------
+    # ---- per-kernel split of the decode step: CUPTI trace of the CUDA-GRAPH REPLAY at the mean context ----------------------
     embeds, _, _ = eng.prepare_inputs(ids, X_dev)
     eng.prefill(embeds)
-    # take the split at the MEAN context of the timed decode (the cache rows up to there hold the previous run's keys:
-    # same bytes, same timing), so the attention share and kv_bytes below refer to the same context length
-    eng.cur_len = S + (args.new_tokens - 1) // 2 - 2
-    eng.begin_decode(args.bs, use_graph=False)
+    ctx_mean_i = S + (args.new_tokens - 1) // 2
+    eng.cur_len = ctx_mean_i   # the cache rows up to there hold the previous run's keys: same bytes, same timing
+    eng.begin_decode(bs_local, use_graph=True)
     eng.decode_step()
-    # Eager launches of 3-30 us kernels are host-bound (ctypes + two event records per launch): the device would idle between
-    # kernels and the event intervals would measure the host.  Queue ~40 ms of filler GEMMs first so the host runs ahead and
-    # the timed kernels execute back to back on the device.
-    fa = torch.empty((16384, 4096), device=dev, dtype=torch.bfloat16).normal_()
-    fw = torch.empty((8192, 4096), device=dev, dtype=torch.bfloat16).normal_()
-    fo = torch.empty((16384, 8192), device=dev, dtype=torch.bfloat16)
-    torch.cuda.synchronize()
-    for _ in range(40):
-        ops.gemm(fa, fw, out=fo)
-    ops.start_kernel_timing()
-    for _ in range(4):
-        eng.decode_step()
-    kd = ops.stop_kernel_timing()
-    del fa, fw, fo
-    for d in kd.values():
-        for k in ("ms", "flops", "bytes"):
-            d[k] /= 4
-        d["launches"] //= 4
+    trace = traced_decode_split(eng, n_layers, steps=4)
 
     if rank == 0:
-        # ---------------- roofline of the dominant kernel -----------------------------------------------------------
         for d in kt.values():
             for k in ("ms", "flops", "bytes"):
                 d[k] /= args.steps
             d["launches"] //= args.steps
-        graph_step_ms = t_dec / max(args.new_tokens - 1, 1)
-        # Decode split: the streaming kernels (>= 20 us each: GEMMs, attention) keep their measured device time; the event
-        # pair around a 3 us kernel mostly measures launch gaps, so the light kernels share whatever the graph step has left.
-        def _heavy(tag):
-            return ("gemm" in tag) or ("attn" in tag) or ("chain" in tag)
-        heavy_ms = sum(d["ms"] for k, d in kd.items() if _heavy(k))
-        light_ms = sum(d["ms"] for k, d in kd.items() if not _heavy(k))
-        if heavy_ms < graph_step_ms and light_ms > 0:
-            light_scale = (graph_step_ms - heavy_ms) / light_ms
-            for k, d in kd.items():
-                if not _heavy(k):
-                    d["ms"] *= light_scale
-        dec_eager_ms = sum(d["ms"] for d in kd.values())
-        shares = {k: d["ms"] for k, d in kt.items()}                      # encoders + prefill, measured in the timed region
-        for k, d in kd.items():                                           # decode kernels: per-step split x number of steps
-            shares["decode:" + k] = d["ms"] / max(dec_eager_ms, 1e-9) * t_dec
-        top = max(shares, key=shares.get)
+        n_dec = max(args.new_tokens - 1, 1)
+        graph_step_ms = t_dec / n_dec
         ctx_mean = S + 1 + (args.new_tokens - 1) / 2.0
-        kv_bytes = args.bs * ctx_mean * 2 * b["kv_heads"] * b["head_dim"] * 2 * n_layers
-        wbytes = sum(L[k].numel() * 2 for L in eng.layers for k in ("wqkv", "wo", "wgu", "wd")) + eng.lm_head.numel() * 2
-        decode_bytes = wbytes + kv_bytes
-        if top.startswith("decode:"):
-            d = kd[top[len("decode:"):]]
-            scale = graph_step_ms / max(dec_eager_ms, 1e-9)
-            if "gemm" in top or "chain" in top:
-                ach = d["bytes"] / (d["ms"] * scale * 1e-3) / 1e9
-            else:
-                ach = kv_bytes / (d["ms"] * scale * 1e-3) / 1e9 if "attn_decode" in top else 0.0
-            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "launches_per_step": d["launches"] * (args.new_tokens - 1),
-                    "avg_launch_ms": d["ms"] * scale / max(d["launches"], 1)}
-        else:
-            d = kt[top]
-            ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                    "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / max(d["launches"], 1)}
-        roof["peak_source"] = peaks_src
-        roof["share_of_step"] = shares[top] / ms_step
+        kv_bytes = bs_local * ctx_mean * 2 * b["kv_heads"] * b["head_dim"] * 2 * n_layers
+        wb = decode_weight_bytes(eng)
+        decode_bytes = sum(wb.values()) + kv_bytes
+        cls_bytes = dict(wb, attention=kv_bytes)
+        # decode classes: traced exclusive device time per step (kernels overlap under programmatic dependent launch: every
+        # instant of the step is attributed to the earliest-started kernel still running, so the classes partition the step)
+        dec_roof, shares = {}, {k: d["ms"] for k, d in kt.items()}
+        scale = graph_step_ms * 1e3 / max(trace["span_us"], 1e-9) if trace else 1.0   # traced span -> event-timed graph step
+        if trace:
+            for cname, c_ in trace["classes"].items():
+                us_step = c_["excl_us"] * scale
+                shares["decode:" + cname] = us_step * 1e-3 * n_dec
+                if cname in cls_bytes and us_step > 0:
+                    ach = cls_bytes[cname] / (us_step * 1e-6) / 1e9
+                    frac = ach / peaks["hbm_gbs"]
+                    dec_roof[cname] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                       "frac": frac if frac <= 1.05 else None, "us_per_step": us_step, "launches_per_step": c_["launches"],
+                                       "bytes_per_step": cls_bytes[cname]}
+                    if frac > 1.05:
+                        dec_roof[cname]["invalid"] = f"achieved / peak = {frac:.3f} > 1.05: not reported as a fraction"
+        # the dominant kernel class: the decode weight-streaming linears as ONE class (the kernel VERDICT r01 names), the decode
+        # attention, or the prefill GEMM — whichever holds the largest share of the step (ties within 5 %: the linears)
+        lin_names = [k for k in ("qkv", "o", "gate_up", "down", "lm_head", "chain") if k in dec_roof]
+        lin_us = sum(dec_roof[k]["us_per_step"] for k in lin_names)
+        lin_bytes = sum(cls_bytes[k] for k in lin_names)
+        cands = {"decode:weight_streaming_linears": lin_us * 1e-3 * n_dec,
+                 "decode:attention": dec_roof.get("attention", {}).get("us_per_step", 0.0) * 1e-3 * n_dec,
+                 "gemm_bf16_tcgen05<256>": kt.get("gemm_bf16_tcgen05<256>", {}).get("ms", 0.0)}
+        top = max(cands, key=cands.get)
+        if cands["decode:weight_streaming_linears"] >= 0.95 * cands[top]:
+            top = "decode:weight_streaming_linears"
         traffic = load_traffic()
-        tkey = top[len("decode:"):] if top.startswith("decode:") else top
+        if top == "decode:weight_streaming_linears":
+            ach = lin_bytes / (lin_us * 1e-6) / 1e9 if lin_us else 0.0
+            n_l = sum(dec_roof[k]["launches_per_step"] for k in lin_names)
+            roof = {"kernel": "decode:gemm_skinny_tcgen05 (qkv + o + gate/up + down + lm_head launches)" if "chain" not in lin_names else "decode:decode_chain",
+                    "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": None, "launches_per_step": n_l * n_dec, "avg_launch_ms": lin_us * 1e-3 / max(n_l, 1),
+                    "algorithmic_bytes_per_step": lin_bytes, "per_linear": {k: dec_roof[k] for k in lin_names}}
+            tkey = "gemm_skinny_tcgen05"
+        elif top == "decode:attention":
+            d_ = dec_roof["attention"]
+            roof = {"kernel": "decode:attention", "bound": "hbm", "achieved": d_["achieved"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": d_["frac"], "traffic": None, "launches_per_step": d_["launches_per_step"] * n_dec,
+                    "avg_launch_ms": d_["us_per_step"] * 1e-3 / max(d_["launches_per_step"], 1)}
+            tkey = "crab_attn_decode_fused"
+        else:
+            d_ = kt[top]
+            ach = d_["flops"] / (d_["ms"] * 1e-3) / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "launches_per_step": d_["launches"],
+                    "avg_launch_ms": d_["ms"] / max(d_["launches"], 1)}
+            tkey = top
+        roof["peak_source"] = peaks_src
+        roof["share_of_step"] = cands[top] / ms_step
         if tkey in traffic:
             roof["traffic"] = traffic[tkey]["traffic_bytes_per_launch"]
             roof["traffic_note"] = f"ncu dram bytes of one launch, {traffic[tkey]['shape']} ({traffic.get('_source', '')})"
-        # the other kernels that matter, same arithmetic (per kernel class, averaged over its launches in the step)
-        def _roof(tag, dct, scale=1.0, bound="tensor"):
+
+        def _roof(tag, dct):
             d_ = dct.get(tag)
             if not d_ or d_["ms"] <= 0:
                 return None
-            t_ms = d_["ms"] * scale
-            if bound == "tensor":
-                a_ = d_["flops"] / (t_ms * 1e-3) / 1e12
-                return {"bound": "tensor", "achieved": a_, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": a_ / peaks["bf16_tflops_sustained"], "ms_per_step": t_ms}
-            a_ = d_["bytes"] / (t_ms * 1e-3) / 1e9
-            return {"bound": "hbm", "achieved": a_, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a_ / peaks["hbm_gbs"],
-                    "ms_per_step": t_ms}
-        dscale = graph_step_ms / max(dec_eager_ms, 1e-9)
-        kd_step = {k: dict(v, ms=v["ms"] * (args.new_tokens - 1), bytes=v["bytes"] * (args.new_tokens - 1)) for k, v in kd.items()}
-        for tag in ("crab_attn_decode", "crab_attn_decode_fused"):
-            if tag in kd_step:
-                kd_step[tag]["bytes"] = kv_bytes * (args.new_tokens - 1)
-        rooflines = {
-            "prefill_gemm_tcgen05<256>": _roof("gemm_bf16_tcgen05<256>", kt),
-            "prefill_flash_attn_tcgen05<128>": _roof("crab_flash_attn_tcgen05<128>", kt),
-            "decode_gemm_chain": _roof("crab_decode_chain", kd_step, dscale, "hbm"),
-            "decode_attention": _roof("crab_attn_decode_fused" if "crab_attn_decode_fused" in kd_step else "crab_attn_decode",
-                                      kd_step, dscale, "hbm"),
-        }
+            a_ = d_["flops"] / (d_["ms"] * 1e-3) / 1e12
+            return {"bound": "tensor", "achieved": a_, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": a_ / peaks["bf16_tflops_sustained"], "ms_per_step": d_["ms"]}
+        rooflines = {"prefill_gemm_tcgen05<256>": _roof("gemm_bf16_tcgen05<256>", kt),
+                     "prefill_flash_attn_tcgen05<128>": _roof("crab_flash_attn_tcgen05<128>", kt)}
+        for k, v in dec_roof.items():
+            rooflines["decode_" + k] = v
         gemm_ms = sum(d["ms"] for k, d in kt.items() if k.startswith("gemm"))
         gemm_fl = sum(d["flops"] for k, d in kt.items() if k.startswith("gemm"))
         phases = {
             "encoders_bridge_splice_ms": t_enc, "decoder_prefill_ms": t_pf, "decode_127_steps_ms": t_dec,
-            "prefill_tok_s": world * args.bs * S / ((t_enc + t_pf) / 1e3),
-            "decoder_prefill_tok_s": world * args.bs * S / (t_pf / 1e3),
-            "decode_tok_s": world * args.bs * (args.new_tokens - 1) / (t_dec / 1e3),
-            "decode_step_ms": graph_step_ms,
+            "prefill_tok_s": world * bs_local * S / ((t_enc + t_pf) / 1e3),
+            "decoder_prefill_tok_s": world * bs_local * S / (t_pf / 1e3),
+            "decode_tok_s": world * bs_local * n_dec / (t_dec / 1e3),
+            "decode_step_ms": graph_step_ms, "decode_mode": eng.decode_mode,
             "prefill_gemm_tflops": gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
             "prefill_gemm_frac_of_peak": (gemm_fl / (gemm_ms * 1e-3) / 1e12) / peaks["bf16_tflops_sustained"] if gemm_ms else None,
-            "prefill_algorithmic_tflop": algorithmic_prefill_tflop(b, S) * args.bs,
-            "prefill_frac_of_tensor_roofline": (algorithmic_prefill_tflop(b, S) * 1e12 * args.bs / ((t_enc + t_pf) / 1e3))
+            "prefill_algorithmic_tflop": algorithmic_prefill_tflop(b, S) * bs_local,
+            "prefill_frac_of_tensor_roofline": (algorithmic_prefill_tflop(b, S) * 1e12 * bs_local / ((t_enc + t_pf) / 1e3))
             / (peaks["bf16_tflops_sustained"] * 1e12),
             "decode_bytes_per_step": decode_bytes, "decode_gbs": decode_bytes / (graph_step_ms * 1e-3) / 1e9,
             "decode_frac_of_hbm_roofline": decode_bytes / (graph_step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
             "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])},
-            "decode_split_note": "decode kernels: device time of 4 un-graphed steps at the mean context with the host running ahead; "
-                                 "GEMM / attention keep their measured time, light kernels share the rest of the graph step. HBM peak = "
-                                 "copy bandwidth (read + write); a read-only stream such as the decode attention can exceed it slightly",
+            "decode_trace": None if not trace else {
+                "method": "CUPTI activity records (torch.profiler) of 4 CUDA-graph replays of the decode step at the mean context; "
+                          "exclusive time = every instant attributed to the earliest-started kernel still running; scaled by "
+                          "(event-timed graph step) / (traced span)",
+                "launches_per_step": trace["launches"], "traced_span_us": trace["span_us"], "sum_of_durations_us": trace["sum_us"],
+                "idle_us": trace["idle_us"], "graph_step_us": graph_step_ms * 1e3},
         }
-        cpu = None
+        cpu = parity = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                threads = os.cpu_count() or 1
-                v, sample, detail = cpu_port_run(args, threads)
-                cpu = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample, **detail}
+                cpu, parity = cpu_leg_and_parity(args, b, dev, cfg, ids, X_host, eng)
             except Exception as e:  # the CPU leg must never take the GPU numbers down with it
+                import traceback
+                traceback.print_exc()
                 cpu = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
+        legs = {}
+        if world == 1 and args.legs and not args.layers:
+            for leg in [x for x in args.legs.split(",") if x]:
+                try:
+                    legs[leg] = run_leg(leg, args, dev, eng, peaks)
+                except Exception as e:
+                    import traceback
+                    traceback.print_exc()
+                    legs[leg] = {"failed": repr(e)}
         line = {
             "metric": "AV-prompt prefill+decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "crab_b200.models.unified_llama.UnifiedForCausalLM.generate", "ids_equal_resident_run": e2e_same},
-            "gpu_launches": int(launches), "roofline": roof, "rooflines": rooflines, "cpu_baseline": cpu, "phases": phases,
-            "frontend": frontend,
+            "gpu_launches": int(launches), "roofline": roof, "rooflines": rooflines, "cpu_baseline": cpu, "parity_check": parity,
+            "phases": phases, "frontend": frontend, "bs1_config1": legs.get("bs1"), "qwen7b_config4": legs.get("qwen"),
             "deterministic_across_steps": deterministic, "weights": "random-init (seeded), generated on device",
             "load_s": round(t_load, 1),
         }

@@ -188,6 +188,13 @@ class CrabEngine:
         # decode attention).  Env CRAB_PDL_PLAN="chain,after_attn" overrides; see profiles/r02_pdl_plans.txt for the A/B.
         plan = os.environ.get("CRAB_PDL_PLAN", DEFAULT_PDL_PLAN).split(",")
         self.pdl_chain, self.pdl_after_attn = int(plan[0]), int(plan[-1])
+        # K-split (cluster size) per decode linear, 0 = the library's choice; env CRAB_SKINNY_SPLITS="qkv:2,o:8,gu:1,d:8" overrides
+        # o_proj: 4 rather than the library's 8 — measured inside the step (tools/sweep_splits.sh): 14-15 us instead of 20.6 us per
+        # launch; its input arrives from the attention kernel all at once, so a shorter DSMEM reduce beats the extra CTAs
+        self.skinny_splits = {"qkv": 0, "o": 4, "gu": 0, "d": 0}
+        for kv in filter(None, os.environ.get("CRAB_SKINNY_SPLITS", "").split(",")):
+            k_, v_ = kv.split(":")
+            self.skinny_splits[k_] = int(v_)
         # K-split (= thread-block-cluster size) of the persistent decode GEMM chain
         self.chain_cluster = int(os.environ.get("CRAB_CHAIN_CLUSTER", "4"))
         # decode step: RoPE + KV append + o_proj LoRA pre-pass inside the attention kernel (8 launches per layer, not 10)
@@ -870,24 +877,26 @@ class CrabEngine:
             for li, L in enumerate(self.layers):
                 ops.gemm_skinny(x, L["wqkv_c"], bias=L["bqkv"], out=qkv, z=z["qkv"] if lo else None, kext=self.EXT_QKV if lo else 0,
                                 stats=L.get("st_qkv"), stats_linears=3 if lo else 0, norm=True, eps=c.eps, lora_scale=sc, rstd=rs["qkv"],
-                                flags=self._flags("qkv"))
+                                flags=self._flags("qkv"), splits=self.skinny_splits["qkv"])
                 self._decode_attention(li, B, nsplit, ws, qkv, at, fused, gqa_tc, o_fused_lora)
                 # the kernel right after the decode attention is launched under its own PDL mask: early-resident streaming-GEMM
                 # CTAs must not squat on the SMs while the 1024-CTA attention kernel still runs
                 if self.pdl_after_attn != self.pdl_chain:
                     ops.set_pdl(self.pdl_after_attn)
                 if o_fused_lora:
-                    ops.gemm_skinny(at, L["wo_c"], residual=x, out=x, z=at[:, nq:], kext=self.EXT_O)
+                    ops.gemm_skinny(at, L["wo_c"], residual=x, out=x, z=at[:, nq:], kext=self.EXT_O, splits=self.skinny_splits["o"])
                 else:
                     ops.gemm_skinny(at, L["wo_c"], residual=x, out=x, z=z["o"] if lo else None, kext=self.EXT_O if lo else 0,
-                                    stats=L.get("st_o"), stats_linears=1 if lo else 0, lora_scale=sc, flags=self._flags("o") if lo else None)
+                                    stats=L.get("st_o"), stats_linears=1 if lo else 0, lora_scale=sc, flags=self._flags("o") if lo else None,
+                                    splits=self.skinny_splits["o"])
                 if self.pdl_after_attn != self.pdl_chain:
                     ops.set_pdl(self.pdl_chain)
                 ops.gemm_skinny(x, L["wgu_c"], act=ops.ACT_SWIGLU, out=hh, z=z["gu"] if lo else None, kext=self.EXT_GU if lo else 0,
                                 stats=L.get("st_gu"), stats_linears=2 if lo else 0, norm=True, eps=c.eps, lora_scale=sc, rstd=rs["gu"],
-                                flags=self._flags("gu"))
+                                flags=self._flags("gu"), splits=self.skinny_splits["gu"])
                 ops.gemm_skinny(hh, L["wd_c"], residual=x, out=x, z=z["d"] if lo else None, kext=self.EXT_D if lo else 0,
-                                stats=L.get("st_d"), stats_linears=1 if lo else 0, lora_scale=sc, flags=self._flags("d") if lo else None)
+                                stats=L.get("st_d"), stats_linears=1 if lo else 0, lora_scale=sc, flags=self._flags("d") if lo else None,
+                                splits=self.skinny_splits["d"])
             self._head(x, self.logits, self.next_ids)
             ops.add_scalar_i32(self.past_dev, 1)
             ops.add_scalar_i32(self.len_dev, 1)
