@@ -1048,14 +1048,14 @@ class CrabEngine:
         norm): `self.hidden_prefill_tail` [B, min(t, S), D] (the last positions of the prompt pass) and `self.hidden_steps`
         [n - 1, B, D] (one row per decode step) — the inputs of generate_avs' mask-token pairing (unified_llama.py:335-345)."""
         B, S = inputs_embeds.shape[0], inputs_embeds.shape[1]
-        if sampling is not None:
-            raise NotImplementedError("sampling: see CrabEngine.sample_next (set up below)")
         if S + max_new_tokens > self.cfg.max_ctx:
             raise ops._l.CrabError(f"prompt of {S} positions + {max_new_tokens} new tokens exceeds the KV cache (max_ctx = "
                                    f"{self.cfg.max_ctx}): construct the model / CrabConfig with a larger max_ctx")
         self._tail_rows = min(int(capture_hidden), S) if capture_hidden else 0
         logits, nxt = self.prefill(inputs_embeds)
         self._tail_rows = 0
+        if sampling is not None:
+            nxt = self._sample(sampling)   # replaces the arg-max in self.next_ids, which the next decode step embeds
         pad = int(self.cfg.pad_token_id if pad_token_id is None else pad_token_id)
         eos = None
         if eos_token_id is not None:
@@ -1084,6 +1084,8 @@ class CrabEngine:
             if teacher_tokens is not None:
                 self.next_ids.copy_(teacher_tokens[:, step])
             logits, nxt = self.decode_step()
+            if sampling is not None:
+                nxt = self._sample(sampling)
             if return_logits:
                 all_logits.append(logits.clone())
             if capture_hidden:
@@ -1101,6 +1103,42 @@ class CrabEngine:
         if return_logits:
             return out, torch.stack(all_logits[: out.shape[1]], 0)
         return out
+
+    def _sample(self, sampling: dict) -> torch.Tensor:
+        """Temperature / top-k / top-p draw from self.logits into self.next_ids (HF generate(do_sample=True) semantics; the uniforms
+        come from torch's generator on this device, so runs are reproducible with a seeded `generator`)."""
+        B = self.logits.shape[0]
+        u = torch.rand(B, device=self.dev, dtype=torch.float32, generator=sampling.get("generator"))
+        ops.sample_top_k_top_p(self.logits, self.vocab, u, temperature=float(sampling.get("temperature", 1.0)),
+                               top_k=int(sampling.get("top_k", 0)), top_p=float(sampling.get("top_p", 1.0)), out=self.next_ids)
+        return self.next_ids
+
+    @torch.no_grad()
+    def forward_logits(self, inputs_embeds: torch.Tensor, labels: Optional[torch.Tensor] = None):
+        """UnifiedForCausalLM.forward over a whole sequence (models/unified_llama.py:129-160 -> HF LlamaForCausalLM.forward): fp32
+        logits for ALL positions [B, S, vocab] and, with `labels` [B, S] (ignore_index -100), the mean shifted cross-entropy.
+        The KV cache is left filled as after `prefill` (a decode step may follow)."""
+        B, S, D = inputs_embeds.shape
+        assert S < self.cfg.max_ctx
+        self._alloc_cache(B)
+        x = inputs_embeds.to(device=self.dev, dtype=torch.bfloat16).contiguous().clone().view(B * S, D)
+        self._decoder_layers(x, B, S, past=0)
+        self.cur_len = S
+        hn = ops.rmsnorm(x, self.final_norm, self.cfg.decoder.eps)
+        logits = torch.empty((B * S, self.vocab_pad), device=self.dev, dtype=torch.float32)
+        ops.gemm(hn, self.lm_head, out=logits)
+        loss = None
+        if labels is not None:
+            lab = torch.full((B, S), -100, device=self.dev, dtype=torch.int64)
+            lab[:, :-1] = labels.to(self.dev)[:, 1:]          # position t predicts token t + 1
+            per_row = ops.cross_entropy(logits, self.vocab, lab.view(-1).contiguous())
+            loss = per_row.sum() / (lab >= 0).sum().clamp(min=1)
+        # keep the greedy state consistent with prefill(): last-position logits / arg-max
+        self.logits = self._buf("logits", (B, self.vocab_pad), torch.float32)
+        self.next_ids = self._buf("next_ids", (B,), torch.int64)
+        self.logits.copy_(logits.view(B, S, -1)[:, -1])
+        ops.argmax(self.logits, self.vocab, out=self.next_ids)
+        return logits.view(B, S, self.vocab_pad)[:, :, : self.vocab], loss
 
     @torch.no_grad()
     def generate(self, batch_input_ids, batch_X_modals, max_new_tokens: int, use_graph: bool = True):

@@ -301,26 +301,36 @@ class UnifiedForCausalLM(UnifiedMetaForCausalLM, nn.Module):
     def forward(self, batch_input_ids=None, batch_labels=None, batch_X_modals=None, batch_task_names=None,
                 input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
                 labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
-                **kwargs):
-        """Inference forward: returns an object with `.logits` for the LAST position, fp32 (b, 1, vocab).
-        `inputs_embeds` / `batch_*` start a new sequence (prefill); a (b,1) `input_ids` continues it (decode step,
-        models/unified_llama.py:125-127).  Training (loss/backward) is out of scope."""
+                logits_to_keep: int = 0, **kwargs):
+        """Inference forward with the reference's contract (models/unified_llama.py:47-161): `batch_*` inputs go through
+        prepare_multimodal_inputs (which also builds the -100-masked labels), `inputs_embeds` / `input_ids` start a new sequence;
+        the result carries fp32 `.logits` for ALL positions (b, S, vocab) — `logits_to_keep=1` keeps only the last one, like HF —
+        and `.loss`, the shifted cross-entropy, when labels are given.  A (b, 1) `input_ids` after that continues the sequence
+        (decode step, :125-127) and returns (b, 1, vocab).  There is no backward: training is out of scope."""
         eng = self.engine()
-        if input_ids is not None and input_ids.shape[1] == 1 and getattr(eng, "cur_len", 0) > 0:
+        if input_ids is not None and input_ids.shape[1] == 1 and getattr(eng, "cur_len", 0) > 0 and inputs_embeds is None \
+                and batch_input_ids is None and past_key_values is not None:
             if not getattr(eng, "_fwd_decode", False):
                 eng.begin_decode(input_ids.shape[0], use_graph=False)
                 eng._fwd_decode = True
             eng.next_ids.copy_(input_ids[:, 0].to(eng.dev))
             logits, _ = eng.decode_step()
-        else:
-            if inputs_embeds is None and batch_input_ids is not None:
-                inputs_embeds = self.prepare_multimodal_inputs(batch_input_ids, None, batch_X_modals, batch_task_names)["inputs_embeds"]
-            elif inputs_embeds is None and input_ids is not None:
-                b, s = input_ids.shape
-                inputs_embeds = self.encode_ids(input_ids).view(b, s, -1)
-            eng._fwd_decode = False
+            return SimpleNamespace(logits=logits.unsqueeze(1).clone(), past_key_values=True, loss=None)
+        if inputs_embeds is None and batch_input_ids is not None:
+            prep = self.prepare_multimodal_inputs(batch_input_ids, batch_labels, batch_X_modals, batch_task_names)
+            inputs_embeds = prep["inputs_embeds"]
+            labels = prep["labels"] if labels is None else labels
+        elif inputs_embeds is None and input_ids is not None:
+            b, s = input_ids.shape
+            inputs_embeds = self.encode_ids(input_ids).view(b, s, -1)
+        eng._fwd_decode = False
+        if logits_to_keep == 1 and labels is None:
             logits, _ = eng.prefill(inputs_embeds.clone())
-        return SimpleNamespace(logits=logits.unsqueeze(1).clone(), past_key_values=True, loss=None)
+            return SimpleNamespace(logits=logits.unsqueeze(1).clone(), past_key_values=True, loss=None)
+        logits, loss = eng.forward_logits(inputs_embeds, labels)
+        if logits_to_keep:
+            logits = logits[:, -logits_to_keep:]
+        return SimpleNamespace(logits=logits, past_key_values=True, loss=loss)
 
     def _eos_ids(self, eos_token_id, ignore_eos: bool):
         """HF semantics: an explicit `eos_token_id` wins, else generation_config.eos_token_id (from the checkpoint's

@@ -451,6 +451,34 @@ def argmax(logits: torch.Tensor, V: int, out: Optional[torch.Tensor] = None) -> 
     return out
 
 
+def sample_top_k_top_p(logits: torch.Tensor, V: int, u: torch.Tensor, *, temperature: float = 1.0, top_k: int = 0, top_p: float = 1.0,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ids[row] drawn from softmax(top-p(top-k(logits[row, :V] / temperature))) by inverse CDF with u[row] in [0, 1)."""
+    _req_cuda(logits, u, out)
+    assert logits.dtype == torch.float32 and u.dtype == torch.float32 and logits.stride(1) == 1
+    rows = logits.shape[0]
+    if out is None:
+        out = torch.empty(rows, device=logits.device, dtype=torch.int64)
+    with _timed("crab_sample_top_k_top_p"):
+        _l.check(_l.load().crab_sample_top_k_top_p(_vp(logits), _i(logits.stride(0)), _i(rows), _i(V), C.c_float(temperature), _i(top_k),
+                                                   C.c_float(top_p), _vp(u), _vp(out), _stream()), "crab_sample_top_k_top_p")
+    count_launches(1)
+    return out
+
+
+def cross_entropy(logits: torch.Tensor, V: int, labels: torch.Tensor) -> torch.Tensor:
+    """Per-row loss (fp32) of fp32 logits [rows, >= V] against int64 labels [rows]; rows with a negative label give 0."""
+    _req_cuda(logits, labels)
+    assert logits.dtype == torch.float32 and labels.dtype == torch.int64 and logits.stride(1) == 1
+    rows = logits.shape[0]
+    loss = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    with _timed("crab_cross_entropy"):
+        _l.check(_l.load().crab_cross_entropy(_vp(logits), _i(logits.stride(0)), _i(rows), _i(V), _vp(labels), _vp(loss), _stream()),
+                 "crab_cross_entropy")
+    count_launches(1)
+    return loss
+
+
 def add_scalar_i32(p: torch.Tensor, v: int):
     _req_cuda(p)
     assert p.dtype == torch.int32

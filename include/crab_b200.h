@@ -186,6 +186,19 @@ int crab_argmax(const float* logits, int ld, int rows, int V, int64_t* out, void
 int crab_add_scalar_i32(int* p, int v, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Token choice and loss on fp32 logits
+ * crab_sample_top_k_top_p replaces: HF generate(do_sample=True)'s logits processors + multinomial draw for the checkpoint's
+ *           generation_config (LLaMA-2-chat: temperature 0.6, top_p 0.9, top_k 50; SURVEY.md 8c shim 7): logits / temperature ->
+ *           TopKLogitsWarper -> TopPLogitsWarper (keep the smallest set of most probable tokens whose mass reaches top_p) -> draw by
+ *           inverse CDF over the kept tokens in index order with the caller's uniform u[row] in [0, 1).  top_k 0 = off.
+ * crab_cross_entropy replaces: the CrossEntropyLoss of UnifiedForCausalLM.forward(labels=...) (models/unified_llama.py:150-160,
+ *           HF LlamaForCausalLM loss): loss[row] = logsumexp(logits[row]) - logits[row, labels[row]], 0 for labels < 0 (-100).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int crab_sample_top_k_top_p(const float* logits, int ld, int rows, int V, float temperature, int top_k, float top_p,
+                            const float* u, int64_t* out, void* stream);
+int crab_cross_entropy(const float* logits, int ld, int rows, int V, const int64_t* labels, float* loss, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Decode-step (M <= 32 rows) kernels
  * crab_gemm_skinny_bf16 replaces: the same nn.Linear / hyper-LoRA linears at q_len == 1 (HF generate's per-token
  *           forward, models/unified_llama.py:125-127): swap-AB tcgen05 weight streaming; K is split across the CTAs

@@ -380,6 +380,36 @@ def decode_chain(phases, M, counters, cluster=0, max_clusters=0, tag="crab_decod
                       ph.residual, ph.act, ph.out, ph.n, M)
 
 
+def cross_entropy(logits, V, labels):
+    loss = torch.zeros(logits.shape[0])
+    ok = labels >= 0
+    if ok.any():
+        loss[ok] = torch.nn.functional.cross_entropy(logits[ok, :V].float(), labels[ok], reduction="none")
+    return loss
+
+
+def sample_top_k_top_p(logits, V, u, *, temperature=1.0, top_k=0, top_p=1.0, out=None):
+    """HF order: temperature -> top-k -> top-p (keep the smallest most-probable set reaching top_p), inverse CDF in index order."""
+    ids = []
+    for r in range(logits.shape[0]):
+        s = logits[r, :V].float() / temperature
+        if 0 < top_k < V:
+            s = torch.where(s >= s.topk(top_k).values[-1], s, torch.full_like(s, -float("inf")))
+        if top_p < 1.0:
+            sv, si = s.sort(descending=False)
+            remove = sv.softmax(-1).cumsum(-1) <= (1 - top_p)
+            remove[-1] = False
+            s = s.masked_fill(torch.zeros_like(s, dtype=torch.bool).scatter(0, si, remove), -float("inf"))
+        p = (s - s.max()).exp()
+        c = p.cumsum(0)
+        ids.append(int((c > float(u[r]) * c[-1]).nonzero()[0]))
+    r_ = torch.tensor(ids, dtype=torch.int64)
+    if out is None:
+        return r_
+    out.copy_(r_)
+    return out
+
+
 def argmax(logits, V, out=None):
     r = logits[:, :V].argmax(-1)
     if out is None:
