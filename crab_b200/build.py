@@ -31,8 +31,24 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+DIAG_SOURCES = {"debug_stream.cu"}   # diagnostics for tools/ only: built into libcrab_diag.so, never into the product library
+
+
 def sources() -> list[Path]:
-    return sorted(CSRC.glob("*.cu"))
+    return sorted(p for p in CSRC.glob("*.cu") if p.name not in DIAG_SOURCES)
+
+
+def build_diag() -> Path:
+    """tools/bench_stream*.py: the pure-streaming probe kernel, in its own shared library."""
+    LIBDIR.mkdir(exist_ok=True)
+    out = LIBDIR / "libcrab_diag.so"
+    srcs = [CSRC / n for n in sorted(DIAG_SOURCES)] + [CSRC / "host_common.cu"]
+    if _stale(out, srcs):
+        cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], "-shared", *map(str, srcs), "-o", str(out), "-cudart", "static"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"diag build failed:\n{r.stdout}\n{r.stderr}")
+    return out
 
 
 def _stale(target: Path, deps: list[Path]) -> bool:

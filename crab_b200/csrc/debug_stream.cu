@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(64, 1) debug_stream_kernel(const uint8_t* __re
 
 }  // namespace crab
 
+// declared here, not in include/crab_b200.h: this file is only built into _lib/libcrab_diag.so (crab_b200/build.py::build_diag)
 extern "C" int crab_debug_stream(const void* src, int64_t bytes, int chunk_bytes, int stages, int ctas, void* sink, void* stream) {
   using namespace crab;
   CRAB_REQUIRE(src && sink && chunk_bytes % 1024 == 0 && stages >= 1 && ctas >= 1, "crab_debug_stream: bad args");

@@ -681,10 +681,9 @@ extern "C" int crab_decode_chain_stats_bytes(int K, int64_t* bytes) {
 
 extern "C" int crab_decode_chain_max_clusters(int cluster, int* n) {
   CRAB_REQUIRE(n && (cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8), "crab_decode_chain_max_clusters: cluster must be 1, 2, 4 or 8");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (first_on_device(attr_once)) {
     CRAB_CHECK_CUDA(cudaFuncSetAttribute(decode_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_MAX));
-    attr_set = true;
   }
   *n = dc_max_clusters(cluster, dc_smem(dc_pick_stages(cluster), cluster));
   CRAB_REQUIRE(*n > 0, "crab_decode_chain_max_clusters: occupancy query failed for cluster size %d", cluster);

@@ -340,11 +340,10 @@ int flash_attn_tcgen05_try(const crab_attn_args* a, cudaStream_t st) {
   if (rc != 0) return rc;
   rc = encode_tmap_bf16_2d(&tv, a->v, (uint64_t)v_rows, (uint64_t)a->v_rs, (uint64_t)a->v_rs, FT_BN, 64);
   if (rc != 0) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (first_on_device(attr_once)) {
     cudaError_t e = cudaFuncSetAttribute(flash_attn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
     if (e != cudaSuccess) return set_error(CRAB_ERR_CUDA, "flash_attn_tcgen05: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   dim3 grid((a->Sq + FT_BM - 1) / FT_BM, a->H, a->B);
   flash_attn_tcgen05_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(tq, tk, tv, p);

@@ -496,10 +496,9 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
   int splits = a->splits > 0 ? a->splits : choose_splits(a->N, kb * SK_BK);
   if (splits > SK_MAX_SPLIT) splits = SK_MAX_SPLIT;
   if (splits > kb_main) splits = kb_main;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (first_on_device(attr_once)) {
     CRAB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
-    attr_set = true;
   }
   CUtensorMap tw, tx, tz;
   int rc = 0;

@@ -543,11 +543,10 @@ static int get_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
 template <int BN>
 static int launch_gemm(const crab_gemm_args* a, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (first_on_device(attr_once)) {
     CRAB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   CUtensorMap ta, tb;
   int rc = get_tmap(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM);
@@ -566,10 +565,9 @@ static int launch_gemm(const crab_gemm_args* a, const GemmParams& p, cudaStream_
 // CTA-pair launch: one cluster of two CTAs per 256 x 256 tile, persistent over sm_count / 2 pairs.
 static int launch_gemm2(const crab_gemm_args* a, const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (first_on_device(attr_once)) {
     CRAB_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   CUtensorMap ta, tb;
   int rc = get_tmap(&ta, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, BM);
@@ -598,7 +596,7 @@ static int launch_gemm2(const crab_gemm_args* a, const GemmParams& p, cudaStream
 // tile is in use and the problem has at least two 256 x 256 tiles (tests).  Auto = the decoder-prefill regime where the
 // A/B in profiles/r02_gemm_2cta.txt shows a win: long K (>= 2048: the mainloop, not the epilogue, paces the tile) and
 // enough rows for >= 4 waves of pairs.
-static int g_gemm2_mode = -1;
+static thread_local int g_gemm2_mode = -1;   // per calling thread, like the PDL mask
 static int gemm2_mode() {
   if (g_gemm2_mode < 0) { const char* e = getenv("CRAB_GEMM_2CTA"); g_gemm2_mode = e ? atoi(e) : GEMM2_DEFAULT; }
   return g_gemm2_mode;

@@ -30,7 +30,7 @@ int sm_count() {
   return cached;
 }
 
-static int g_pdl = -1;
+static thread_local int g_pdl = -1;   // launch policy of the calling thread: two engines on two threads do not see each other
 int pdl_mask() {
   if (g_pdl < 0) {
     const char* e = getenv("CRAB_PDL");

@@ -35,6 +35,17 @@ int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint6
 
 int sm_count();
 
+// cudaFuncSetAttribute is per device: `once_per_device(flags)` is true the first time it is called for the current device with
+// this flag array (callers keep one `static DeviceOnce` per kernel), so a process that drives several GPUs sets the attribute on each.
+struct DeviceOnce { bool done[64] = {false}; };
+inline bool first_on_device(DeviceOnce& f) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (f.done[dev]) return false;
+  f.done[dev] = true;
+  return true;
+}
+
 // Programmatic dependent launch (env CRAB_PDL or crab_set_pdl): a bit mask over kernel classes.  A kernel whose class
 // bit is set is launched with cudaLaunchAttributeProgrammaticStreamSerialization, i.e. its CTAs may become resident as
 // soon as every CTA of the PREVIOUS kernel in the stream has executed griddepcontrol.launch_dependents (all decode-chain

@@ -35,7 +35,7 @@ int crab_version(void);
  * initial value, default 0): 1 = weight-streaming GEMM, 2 = row norm/LoRA pre-pass, 4 = RoPE + KV append,
  * 8 = decode attention, 16 = the other light kernels (norm, gather, arg-max, counters); modifier 32 = the decode
  * attention releases its dependents after its streaming loop instead of at its top.  Read at launch time. */
-int crab_set_pdl(int mask);   /* process-wide launch policy, like crab_set_gemm_2cta: set it from the thread that launches */
+int crab_set_pdl(int mask);   /* launch policy of the CALLING THREAD (thread-local, like crab_set_gemm_2cta) */
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Dense linear:  C[M,N] = epilogue( A[M,K] . B[N,K]^T )       (tcgen05 + TMEM + TMA, persistent, warp-specialised)
@@ -336,9 +336,6 @@ int crab_row_mean_f32(const float* x, int ldx, int rows, int cols, float* out, v
 int crab_im2col3x3(const void* in, int ldi, void* out, int h, int w, int C, void* stream);
 int crab_bilinear_f32(const float* in, int ldi, int hin, int win, float* out, int ldo, int hout, int wout, int C, float alpha,
                       float beta, int nchw_out, void* stream);
-
-/* Diagnostic (not on the product path): pure HBM->smem ring streaming, used by tools/ to size the decode pipelines. */
-int crab_debug_stream(const void* src, int64_t bytes, int chunk_bytes, int stages, int ctas, void* sink, void* stream);
 
 #ifdef __cplusplus
 }

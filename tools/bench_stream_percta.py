@@ -2,7 +2,9 @@ import ctypes as C, sys, torch
 sys.path.insert(0, ".")
 from crab_b200 import ops, lib
 ops.init(0)
-L = lib.load()
+from crab_b200 import build as _b
+L = C.CDLL(str(_b.build_diag()))
+L.crab_last_error.restype = C.c_char_p
 dev = torch.device("cuda:0")
 nbuf, size = 6, 192 << 20
 bufs = [torch.randint(0, 255, (size,), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
@@ -10,7 +12,7 @@ sink = torch.zeros(2, dtype=torch.int64, device=dev)
 def run(chunk, stages, ctas):
     def fn():
         for b in bufs:
-            lib.check(L.crab_debug_stream(C.c_void_p(b.data_ptr()), C.c_int64(size), C.c_int(chunk), C.c_int(stages), C.c_int(ctas),
+            assert 0 == (L.crab_debug_stream(C.c_void_p(b.data_ptr()), C.c_int64(size), C.c_int(chunk), C.c_int(stages), C.c_int(ctas),
                                           C.c_void_p(sink.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     fn(); torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
