@@ -54,6 +54,10 @@ struct SkinnyParams {
   int* flags;                    // [0] z / rstd published, [32] CTAs that have left (self-cleaning)
   int n_tiles, kb_main, ldz, has_stats, norm, stats_linears, ext_from_z;
   float eps, lora_scale;
+  // L2 prefetch of the NEXT launch's weight stream: each CTA touches its share once its own loads are all issued, so HBM keeps
+  // working through this launch's reduce / epilogue / exit and the next launch's ramp instead of idling between two kernels
+  const uint8_t* pf_ptr;
+  unsigned long long pf_bytes;
 };
 static constexpr int SK_SROWS = 40;                       // router/A rows per statistics k-block (33 used)
 static constexpr int SK_S_BYTES = SK_SROWS * SK_BK * 2;   // 5 KB
@@ -177,6 +181,14 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
         load_w((int)stage, kb);
         load_x((int)stage, kb);
         if (++stage == SK_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (p.pf_bytes) {
+        const unsigned long long per = ((p.pf_bytes / gridDim.x) + 16383ull) & ~16383ull;
+        const unsigned long long b0 = (unsigned long long)blockIdx.x * per;
+        for (unsigned long long o = b0; o < b0 + per && o < p.pf_bytes; o += 16384ull) {
+          const unsigned long long n = (p.pf_bytes - o < 16384ull) ? (p.pf_bytes - o) & ~15ull : 16384ull;
+          if (n) bulk_prefetch_l2(p.pf_ptr + o, (uint32_t)n);
+        }
       }
     }
   } else if (warp == 1) {
@@ -525,6 +537,8 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
   p.n_tiles = tiles; p.kb_main = kb_main; p.ldz = a->ldz;
   p.has_stats = has_stats ? 1 : 0; p.norm = a->norm != 0; p.stats_linears = a->stats_linears; p.ext_from_z = ext_z ? 1 : 0;
   p.eps = a->eps; p.lora_scale = a->lora_scale;
+  p.pf_ptr = reinterpret_cast<const uint8_t*>(a->prefetch);
+  p.pf_bytes = (a->prefetch && a->prefetch_bytes > 0) ? (unsigned long long)a->prefetch_bytes : 0ull;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((tiles + p.has_stats) * splits));
   cfg.blockDim = dim3(SK_THREADS);

@@ -195,6 +195,8 @@ class CrabEngine:
         for kv in filter(None, os.environ.get("CRAB_SKINNY_SPLITS", "").split(",")):
             k_, v_ = kv.split(":")
             self.skinny_splits[k_] = int(v_)
+        # L2 prefetch of the next linear's weights from the tail of each decode linear (MB per launch, 0 = off)
+        self.prefetch_mb = int(os.environ.get("CRAB_PREFETCH_MB", "0"))
         # K-split (= thread-block-cluster size) of the persistent decode GEMM chain
         self.chain_cluster = int(os.environ.get("CRAB_CHAIN_CLUSTER", "4"))
         # decode step: RoPE + KV append + o_proj LoRA pre-pass inside the attention kernel (8 launches per layer, not 10)
@@ -874,7 +876,12 @@ class CrabEngine:
         ops.set_pdl(self.pdl_chain)
         try:
             ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)  # embed_tokens of the previous arg-max
+            pfb = self.prefetch_mb << 20
+
+            def pf(w):
+                return dict(prefetch=w.data, prefetch_bytes=pfb) if pfb else {}
             for li, L in enumerate(self.layers):
+                nxt_qkv = self.layers[li + 1]["wqkv_c"] if li + 1 < len(self.layers) else self.lm_head_c
                 ops.gemm_skinny(x, L["wqkv_c"], bias=L["bqkv"], out=qkv, z=z["qkv"] if lo else None, kext=self.EXT_QKV if lo else 0,
                                 stats=L.get("st_qkv"), stats_linears=3 if lo else 0, norm=True, eps=c.eps, lora_scale=sc, rstd=rs["qkv"],
                                 flags=self._flags("qkv"), splits=self.skinny_splits["qkv"])
@@ -884,19 +891,19 @@ class CrabEngine:
                 if self.pdl_after_attn != self.pdl_chain:
                     ops.set_pdl(self.pdl_after_attn)
                 if o_fused_lora:
-                    ops.gemm_skinny(at, L["wo_c"], residual=x, out=x, z=at[:, nq:], kext=self.EXT_O, splits=self.skinny_splits["o"])
+                    ops.gemm_skinny(at, L["wo_c"], residual=x, out=x, z=at[:, nq:], kext=self.EXT_O, splits=self.skinny_splits["o"], **pf(L["wgu_c"]))
                 else:
                     ops.gemm_skinny(at, L["wo_c"], residual=x, out=x, z=z["o"] if lo else None, kext=self.EXT_O if lo else 0,
                                     stats=L.get("st_o"), stats_linears=1 if lo else 0, lora_scale=sc, flags=self._flags("o") if lo else None,
-                                    splits=self.skinny_splits["o"])
+                                    splits=self.skinny_splits["o"], **pf(L["wgu_c"]))
                 if self.pdl_after_attn != self.pdl_chain:
                     ops.set_pdl(self.pdl_chain)
                 ops.gemm_skinny(x, L["wgu_c"], act=ops.ACT_SWIGLU, out=hh, z=z["gu"] if lo else None, kext=self.EXT_GU if lo else 0,
                                 stats=L.get("st_gu"), stats_linears=2 if lo else 0, norm=True, eps=c.eps, lora_scale=sc, rstd=rs["gu"],
-                                flags=self._flags("gu"), splits=self.skinny_splits["gu"])
+                                flags=self._flags("gu"), splits=self.skinny_splits["gu"], **pf(L["wd_c"]))
                 ops.gemm_skinny(hh, L["wd_c"], residual=x, out=x, z=z["d"] if lo else None, kext=self.EXT_D if lo else 0,
                                 stats=L.get("st_d"), stats_linears=1 if lo else 0, lora_scale=sc, flags=self._flags("d") if lo else None,
-                                splits=self.skinny_splits["d"])
+                                splits=self.skinny_splits["d"], **pf(nxt_qkv))
             self._head(x, self.logits, self.next_ids)
             ops.add_scalar_i32(self.past_dev, 1)
             ops.add_scalar_i32(self.len_dev, 1)

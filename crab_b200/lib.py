@@ -84,6 +84,7 @@ class SkinnyArgs(C.Structure):
         ("stats_packed", C.c_void_p), ("stats_linears", C.c_int32), ("norm", C.c_int32),
         ("eps", C.c_float), ("lora_scale", C.c_float),
         ("rstd", C.c_void_p), ("flags", C.c_void_p),
+        ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
     ]
 
 

@@ -518,7 +518,8 @@ def gemm_skinny(x: torch.Tensor, w, *, bias: Optional[torch.Tensor] = None,
                 out_dtype: torch.dtype = torch.bfloat16, k: Optional[int] = None, n: Optional[int] = None,
                 splits: int = 0, z: Optional[torch.Tensor] = None, kext: int = 0, stats: Optional[torch.Tensor] = None,
                 stats_linears: int = 0, norm: bool = False, eps: float = 0.0, lora_scale: float = 1.0,
-                rstd: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None, tag: str = "gemm_skinny_tcgen05") -> torch.Tensor:
+                rstd: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None, tag: str = "gemm_skinny_tcgen05",
+                prefetch: Optional[torch.Tensor] = None, prefetch_bytes: int = 0) -> torch.Tensor:
     """out[M, N'] = epilogue(x[M<=32, K] @ w[N, K]^T): the decode-step weight-streaming GEMM (swap-AB, split-K).
     With z / kext the K-extension columns come from a separate buffer; norm / stats_linears fold the RMSNorm (as an epilogue scale
     over a gamma-folded weight) and the hyper-LoRA router / A pre-pass into the same launch (see include/crab_b200.h)."""
@@ -547,7 +548,9 @@ def gemm_skinny(x: torch.Tensor, w, *, bias: Optional[torch.Tensor] = None,
                          out_dtype=(BF16 if out.dtype == torch.bfloat16 else F32), splits=splits,
                          Z=_ptr(z), ldz=(z.stride(0) if z is not None else 0), Kext=kext, stats_packed=_ptr(stats),
                          stats_linears=stats_linears, norm=1 if norm else 0, eps=eps, lora_scale=lora_scale, rstd=_ptr(rstd),
-                         flags=_ptr(flags))
+                         flags=_ptr(flags), prefetch=_ptr(prefetch),
+                         prefetch_bytes=(min(prefetch_bytes or prefetch.numel() * prefetch.element_size(), prefetch.numel() * prefetch.element_size())
+                                         if prefetch is not None else 0))
     wb = 2.0 * N * (K + kext) + (stats.numel() * 2.0 if stats is not None else 0.0)
     with _timed(tag, 2.0 * M * N * (K + kext), 2.0 * M * K + wb + out.element_size() * M * n_out):
         _l.check(_l.load().crab_gemm_skinny_bf16(C.byref(args), _stream()), "crab_gemm_skinny_bf16")

@@ -235,6 +235,9 @@ typedef struct crab_skinny_args {
   const void* stats_packed; int32_t stats_linears; int32_t norm;
   float eps; float lora_scale;
   float* rstd; int* flags;
+  /* prefetch / prefetch_bytes: optional — a global span (the NEXT launch's packed weights) that the CTAs pull into L2 once their own
+   * loads are issued, so HBM does not idle between two dependent launches; no effect on results. */
+  const void* prefetch; int64_t prefetch_bytes;
 } crab_skinny_args;
 int crab_gemm_skinny_plan(int N, int K, int* splits, int64_t* workspace_bytes, int* n_counters);
 int crab_skinny_packed_bytes(int N, int K, int64_t* bytes);
