@@ -322,6 +322,7 @@ struct DecodeParams {
   float lora_scale;
   float* lora_ws;                             // [B, KVH, 11] per-head-group partial dots
   int* lora_cnt;                              // [B] arrival counters, zero on entry and left zero
+  unsigned long long* trace;                  // diagnostics: [ctas][16] stamps or nullptr
 };
 
 // FUSE = the decode step's RoPE + KV-cache append (+ the o_proj hyper-LoRA pre-pass) folded into the attention kernel:
@@ -344,8 +345,10 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
   // With an early trigger the next kernels of a PDL chain (ultimately the streaming GEMM, 100 KB smem / 32 K registers per
   // CTA) become resident while this grid still streams the cache and squat on its SM slots; a late trigger releases them
   // only when every CTA is past its loop, which still hides their launch latency behind the combine/tail.
+  if (threadIdx.x == 0) trace_stamp(p.trace, 0);
   if (!p.late_trigger) pdl_trigger();
   pdl_wait();
+  if (threadIdx.x == 0) trace_stamp(p.trace, 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / LPK, li = lane % LPK;
   const int b = blockIdx.x / p.KVH, kvh = blockIdx.x % p.KVH;
@@ -502,6 +505,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
       }
     }
   }
+  if (threadIdx.x == 0) trace_stamp(p.trace, 4);
   if (p.late_trigger) pdl_trigger();
   // combine the NSUB partial states
   const int sidx = warp * KPW + sub;
@@ -582,6 +586,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
       if (threadIdx.x == 0) p.lora_cnt[b] = 0;  // ready for the next launch (next layer / next step)
     }
   }
+  if (threadIdx.x == 0) trace_stamp(p.trace, 7);
 }
 
 template <int HD>
@@ -681,6 +686,7 @@ extern "C" int crab_attn_decode(const void* q, int ldq, const void* k_cache, con
   p.late_trigger = (pdl_mask() & PDL_ATTN_LATE) ? 1 : 0;
   p.cos_sin = nullptr; p.past_dev = nullptr; p.kc_w = nullptr; p.vc_w = nullptr; p.ra = nullptr; p.ldra = 0; p.z = nullptr;
   p.ldz = 0; p.lora_scale = 0.f; p.lora_ws = nullptr; p.lora_cnt = nullptr;
+  p.trace = nullptr;
   dim3 grid(B * KVH, nsplit);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
@@ -720,6 +726,7 @@ extern "C" int crab_attn_decode_fused(const crab_decode_fused_args* a, void* str
   p.cos_sin = a->cos_sin; p.past_dev = a->past_dev; p.kc_w = (__nv_bfloat16*)a->k_cache; p.vc_w = (__nv_bfloat16*)a->v_cache;
   p.ra = (const __nv_bfloat16*)a->lora_ra; p.ldra = a->ld_ra; p.z = (__nv_bfloat16*)a->lora_z; p.ldz = a->ld_z;
   p.lora_scale = a->lora_scale; p.lora_ws = a->lora_ws; p.lora_cnt = a->lora_counters;
+  p.trace = next_trace_slot(a->B * a->KVH * a->nsplit);
   dim3 grid(a->B * a->KVH, a->nsplit);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;

@@ -58,6 +58,8 @@ struct SkinnyParams {
   // working through this launch's reduce / epilogue / exit and the next launch's ramp instead of idling between two kernels
   const uint8_t* pf_ptr;
   unsigned long long pf_bytes;
+  unsigned long long* trace;   // diagnostics: [ctas][16] stamps or nullptr
+  int debug;                   // diagnostics (env CRAB_SKINNY_DEBUG): 1 = no final stores, 2 = no partial loads
 };
 static constexpr int SK_SROWS = 40;                       // router/A rows per statistics k-block (33 used)
 static constexpr int SK_S_BYTES = SK_SROWS * SK_BK * 2;   // 5 KB
@@ -97,6 +99,70 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Final step of the reduce-scatter for S_ in {1, 2, 4, 8} (R = 128 / S_ tile rows per rank).  The partials in `part` already carry
+// the RMSNorm scale, the bias and the residual (added by the thread that produced the rank's own partial), so this is a pure
+// fixed-order sum + convert + store.  Deliberately ROLLED loops with a small body: the code runs once per launch with one warp
+// per scheduler, i.e. at instruction-fetch speed — the in-kernel timeline (profiles/r04_skinny_timeline.txt) showed ~0.25 us per
+// 128-byte line of cold straight-line code and ~30 ns per line for loop bodies that do not fit the L0 instruction cache.
+template <int S_>
+__device__ __forceinline__ void sk_finish_split(const SkinnyParams& p, const float* __restrict__ part, int tt, int tile, int rank) {
+  constexpr int R = 128 / S_;
+  const int row0 = rank * R;
+  if (p.act == CRAB_ACT_SWIGLU) {
+    constexpr int PAIRS = R / 2, IT = R / 8, BSTEP = 128 / PAIRS;
+    const int pr = tt & (PAIRS - 1), b0 = tt / PAIRS;
+    const int n = tile * 64 + ((row0 + 2 * pr) >> 1);
+    const float* pp = part + (2 * pr) * SK_PSTRIDE + b0;
+    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)b0 * p.ldc + n;
+    const int mlim = (n < (p.N >> 1)) ? p.M : 0;
+    const size_t cstep = (size_t)BSTEP * p.ldc;
+#pragma unroll 1
+    for (int b = b0; b < 32; b += BSTEP) {
+      float g = 0.f, u = 0.f;
+#pragma unroll
+      for (int s = 0; s < S_; ++s) {  // fixed rank order: deterministic
+        g += pp[s * R * SK_PSTRIDE];
+        u += pp[s * R * SK_PSTRIDE + SK_PSTRIDE];
+      }
+      if (b < mlim) *cp = __float2bfloat16_rn(g / (1.0f + __expf(-g)) * u);
+      pp += BSTEP;
+      cp += cstep;
+    }
+    (void)IT;
+  } else {
+    constexpr int BSTEP = 128 / R;
+    const int rl = tt & (R - 1), b0 = tt / R;
+    const int n = tile * SK_BM + row0 + rl;
+    const float* pp = part + rl * SK_PSTRIDE + b0;
+    const int mlim = (n < p.N) ? p.M : 0;
+    if (p.out_dtype == CRAB_BF16) {
+      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)b0 * p.ldc + n;
+      const size_t cstep = (size_t)BSTEP * p.ldc;
+#pragma unroll 1
+      for (int b = b0; b < 32; b += BSTEP) {
+        float a = 0.f;
+#pragma unroll
+        for (int s = 0; s < S_; ++s) a += pp[s * R * SK_PSTRIDE];
+        if (b < mlim) *cp = __float2bfloat16_rn(a);
+        pp += BSTEP;
+        cp += cstep;
+      }
+    } else {
+      float* cp = reinterpret_cast<float*>(p.C) + (size_t)b0 * p.ldc + n;
+      const size_t cstep = (size_t)BSTEP * p.ldc;
+#pragma unroll 1
+      for (int b = b0; b < 32; b += BSTEP) {
+        float a = 0.f;
+#pragma unroll
+        for (int s = 0; s < S_; ++s) a += pp[s * R * SK_PSTRIDE];
+        if (b < mlim) *cp = a;
+        pp += BSTEP;
+        cp += cstep;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(SK_THREADS, 2)
 gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                            const __grid_constant__ CUtensorMap tmap_z, const SkinnyParams p) {
@@ -109,6 +175,7 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   const uint32_t tmem_slot = bar_base + 8u * (2 * SK_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_stamp(p.trace, 0);
   const int S = p.splits;
   const int tile = (int)blockIdx.x / S - p.has_stats;   // weight tile of this cluster (-1: the statistics cluster)
   const int rank = (S > 1) ? (int)cluster_ctarank() : 0;
@@ -172,7 +239,9 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
         }
       };
       for (int i = 0; i < npre; ++i) load_w(i, kb0 + i);
+      trace_stamp(p.trace, 1);
       pdl_wait();
+      trace_stamp(p.trace, 2);
       for (int i = 0; i < npre; ++i) load_x(i, kb0 + i);
       uint32_t stage = 0, phase = 1;  // ring position after the prefill (npre == SK_STAGES wraps to stage 0)
       if (npre < SK_STAGES) { stage = (uint32_t)npre; phase = 0; }
@@ -198,6 +267,7 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
       uint32_t stage = 0, phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar(stage), phase);
+        if (kb == kb0) trace_stamp(p.trace, 3);
         tc_fence_after();
         const uint32_t sw = smem_base + stage * SK_STAGE_BYTES;
         const uint64_t da = make_sdesc_sw128(sw);
@@ -221,10 +291,28 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   const int quarter = warp & 3;
   const int row = quarter * 32 + lane;  // weight row of this thread within the tile (epilogue warps)
   const bool swiglu = p.act == CRAB_ACT_SWIGLU;
+  const int R = p.rows_per_rank;  // even; rank j owns tile rows [j*R, min(128, (j+1)*R))
+  // a thread whose tile row stays in this CTA after the reduce-scatter adds the bias and the residual to its partial: the
+  // values are fetched NOW, behind the weight stream (packed two bf16 per register), not between the last MMA and the store
+  const bool own = epi && !is_stats && (S == 1 || row / R == rank) && (tile * SK_BM + row) < p.N && !swiglu;
+  const bool add_res = own && p.residual != nullptr;
   uint32_t r[32];
+  uint32_t resp[16];
+  float bias_v = 0.f;
   if (epi) {
     pdl_wait();
+    if (own && p.bias) bias_v = p.bias[tile * SK_BM + row];
+    if (add_res) {
+      const unsigned short* rp = reinterpret_cast<const unsigned short*>(p.residual) + (tile * SK_BM + row);
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        const uint32_t lo = (2 * b < p.M) ? rp[(size_t)(2 * b) * p.ldr] : 0u;
+        const uint32_t hi = (2 * b + 1 < p.M) ? rp[(size_t)(2 * b + 1) * p.ldr] : 0u;
+        resp[b] = lo | (hi << 16);
+      }
+    }
     mbar_wait(tfull_bar, 0);
+    if (threadIdx.x == 64) trace_stamp(p.trace, 4);
     tc_fence_after();
     tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16), r);
     tmem_ld_wait();
@@ -290,7 +378,10 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
         __threadfence();
         asm volatile("fence.proxy.async;" ::: "memory");
         asm volatile("bar.sync 2, %0;" ::"r"(32 * nw) : "memory");
-        if (tt == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags), "r"(1) : "memory");
+        if (tt == 0) {
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags), "r"(1) : "memory");
+          trace_stamp(p.trace, 5);
+        }
       }
     }
   } else if (p.norm && epi) {
@@ -301,98 +392,101 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
       float v;
       asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p.rstd + lane) : "memory");
       rstd_s[lane] = lane < p.M ? v : 0.f;
+      if (lane == 0) trace_stamp(p.trace, 5);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
 
-  if (is_stats) {
-  } else if (S == 1) {
+  if (!is_stats) {
+    // ---- reduce-scatter of the K-split partials through (distributed) shared memory; S == 1 takes the same route through
+    //      its own shared memory, so that there is ONE compact finishing loop ----
     if (epi) {
-      // ---- no split: finish straight from registers (thread = weight row, 32 batch values) ----
-      if (swiglu) {
-        // decode SwiGLU weights interleave rows (2i = gate_i, 2i+1 = up_i): the partner is the neighbouring lane
-        const int n = tile * 64 + (row >> 1);
+      if (p.norm) {
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
-          const float mine = __uint_as_float(r[b]) * (p.norm ? rstd_s[b] : 1.0f);
-          const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-          if (!(row & 1) && b < p.M && n < (p.N >> 1))
-            reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(mine / (1.0f + __expf(-mine)) * other);
+        for (int b = 0; b < 32; ++b) r[b] = __float_as_uint(__uint_as_float(r[b]) * rstd_s[b]);
+      }
+      if (add_res) {
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+          r[2 * b] = __float_as_uint(__uint_as_float(r[2 * b]) + __uint_as_float(resp[b] << 16));
+          r[2 * b + 1] = __float_as_uint(__uint_as_float(r[2 * b + 1]) + __uint_as_float(resp[b] & 0xffff0000u));
         }
+      }
+      if (own && p.bias) {
+#pragma unroll
+        for (int b = 0; b < 32; ++b) r[b] = __float_as_uint(__uint_as_float(r[b]) + bias_v);
+      }
+    }
+    // Barrier 1: every CTA of the cluster has finished its MMAs (its epilogue warps passed tfull), so its TMA ring is
+    // idle and can be overwritten with partials.  Layout in the owner's smem: [src rank][row in group][SK_PSTRIDE].
+    if (S > 1) cluster_sync_all();
+    if (threadIdx.x == 64) trace_stamp(p.trace, 8);
+    if (epi) {
+      const int dst_rank = (S > 1) ? row / R : 0;
+      const int row_in = row - dst_rank * R;
+      const uint32_t local = smem_base + (uint32_t)((rank * R + row_in) * SK_PSTRIDE * 4);
+      if (S > 1) {
+        const uint32_t remote = map_to_rank(local, (uint32_t)dst_rank);
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          st_cluster_f4(remote + g * 16, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                        __uint_as_float(r[4 * g + 3]));
       } else {
-        const int n = tile * SK_BM + row;
-        if (n < p.N) {
-          const float bias = p.bias ? p.bias[n] : 0.f;
-          float resv[32];
 #pragma unroll
-          for (int b = 0; b < 32; ++b)  // all residual loads first: C may alias the residual (in-place x += ...)
-            resv[b] = (p.residual != nullptr && b < p.M) ? __bfloat162float(p.residual[(size_t)b * p.ldr + n]) : 0.f;
-#pragma unroll
-          for (int b = 0; b < 32; ++b) {
-            if (b < p.M) {
-              const float v = __uint_as_float(r[b]) * (p.norm ? rstd_s[b] : 1.0f) + bias + resv[b];
-              if (p.out_dtype == CRAB_BF16) reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(v);
-              else reinterpret_cast<float*>(p.C)[(size_t)b * p.ldc + n] = v;
+        for (int g = 0; g < 8; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(local + g * 16), "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]),
+                       "r"(r[4 * g + 3]) : "memory");
+      }
+    }
+    if (threadIdx.x == 64) trace_stamp(p.trace, 9);
+    if (S > 1) cluster_sync_all();  // Barrier 2: all partials have landed (release/acquire at cluster scope)
+    else if (epi) asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) trace_stamp(p.trace, 6);
+    if (epi) {
+      const int tt = (warp - 2) * 32 + lane;
+      const float* part = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+      if (S == 1) sk_finish_split<1>(p, part, tt, tile, rank);
+      else if (S == 2) sk_finish_split<2>(p, part, tt, tile, rank);
+      else if (S == 4) sk_finish_split<4>(p, part, tt, tile, rank);
+      else if (S == 8) sk_finish_split<8>(p, part, tt, tile, rank);
+      else {
+        // other cluster sizes (3, 5, 6, 7: only on request, they schedule poorly): generic index arithmetic
+        const int row0 = rank * R;
+        const int rows_g = max(0, min(R, SK_BM - row0));
+        if (swiglu) {
+          const int pairs = rows_g >> 1;
+          for (int idx = tt; idx < pairs * 32; idx += 128) {
+            const int b = idx / pairs, pr = idx - b * pairs;
+            float g = 0.f, u = 0.f;
+            for (int s2 = 0; s2 < S; ++s2) {  // fixed rank order: deterministic
+              g += part[(s2 * R + 2 * pr) * SK_PSTRIDE + b];
+              u += part[(s2 * R + 2 * pr + 1) * SK_PSTRIDE + b];
+            }
+            const int n = tile * 64 + ((row0 + 2 * pr) >> 1);
+            if (b < p.M && n < (p.N >> 1))
+              reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(g / (1.0f + __expf(-g)) * u);
+          }
+        } else {
+          for (int idx = tt; idx < rows_g * 32; idx += 128) {
+            const int b = idx / rows_g, rl = idx - b * rows_g;
+            const int n = tile * SK_BM + row0 + rl;
+            float a = 0.f;
+            for (int s2 = 0; s2 < S; ++s2) a += part[(s2 * R + rl) * SK_PSTRIDE + b];
+            if (b < p.M && n < p.N) {
+              if (p.out_dtype == CRAB_BF16) reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(a);
+              else reinterpret_cast<float*>(p.C)[(size_t)b * p.ldc + n] = a;
             }
           }
         }
       }
     }
-  } else {
-    // ---- split-K over the cluster: reduce-scatter through distributed shared memory ----
-    // Barrier 1: every CTA of the cluster has finished its MMAs (its epilogue warps passed tfull), so its TMA ring is
-    // idle and can be overwritten with partials.  Layout in the owner's smem: [src rank][row in group][SK_PSTRIDE].
-    cluster_sync_all();
-    const int R = p.rows_per_rank;  // even; rank j owns tile rows [j*R, min(128, (j+1)*R))
-    if (epi) {
-      const int dst_rank = row / R;
-      const int row_in = row - dst_rank * R;
-      const uint32_t local = smem_base + (uint32_t)((rank * R + row_in) * SK_PSTRIDE * 4);
-      const uint32_t remote = map_to_rank(local, (uint32_t)dst_rank);
-#pragma unroll
-      for (int g = 0; g < 8; ++g)
-        st_cluster_f4(remote + g * 16, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
-                      __uint_as_float(r[4 * g + 3]));
-    }
-    cluster_sync_all();  // Barrier 2: all partials have landed (release/acquire at cluster scope)
-    if (epi) {
-      const int tt = (warp - 2) * 32 + lane;
-      const int row0 = rank * R;
-      const int rows_g = max(0, min(R, SK_BM - row0));
-      const float* part = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
-      if (swiglu) {
-        const int pairs = rows_g >> 1;
-        for (int idx = tt; idx < pairs * 32; idx += 128) {
-          const int b = idx / pairs, pr = idx - b * pairs;
-          float g = 0.f, u = 0.f;
-          for (int s = 0; s < S; ++s) {  // fixed rank order: deterministic
-            g += part[(s * R + 2 * pr) * SK_PSTRIDE + b];
-            u += part[(s * R + 2 * pr + 1) * SK_PSTRIDE + b];
-          }
-          if (p.norm) { g *= rstd_s[b]; u *= rstd_s[b]; }
-          const int n = tile * 64 + ((row0 + 2 * pr) >> 1);
-          if (b < p.M && n < (p.N >> 1))
-            reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(g / (1.0f + __expf(-g)) * u);
-        }
-      } else {
-        for (int idx = tt; idx < rows_g * 32; idx += 128) {
-          const int b = idx / rows_g, rl = idx - b * rows_g;
-          const int n = tile * SK_BM + row0 + rl;
-          float a = 0.f;
-          for (int s = 0; s < S; ++s) a += part[(s * R + rl) * SK_PSTRIDE + b];
-          if (p.norm) a *= rstd_s[b];
-          if (b < p.M && n < p.N) {
-            a += p.bias ? p.bias[n] : 0.f;
-            if (p.residual) a += __bfloat162float(p.residual[(size_t)b * p.ldr + n]);
-            if (p.out_dtype == CRAB_BF16) reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)b * p.ldc + n] = __float2bfloat16_rn(a);
-            else reinterpret_cast<float*>(p.C)[(size_t)b * p.ldc + n] = a;
-          }
-        }
-      }
-    }
   }
+  if (threadIdx.x == 64) trace_stamp(p.trace, 10);
+  if (threadIdx.x == 0) trace_stamp(p.trace, 11);
+  if (threadIdx.x == 32) trace_stamp(p.trace, 12);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_stamp(p.trace, 7);
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
   // self-cleaning flags: the last CTA to get here (every flag wait is over by then) zeroes them for the next launch
   if (p.has_stats && threadIdx.x == 0) {
@@ -539,6 +633,8 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
   p.eps = a->eps; p.lora_scale = a->lora_scale;
   p.pf_ptr = reinterpret_cast<const uint8_t*>(a->prefetch);
   p.pf_bytes = (a->prefetch && a->prefetch_bytes > 0) ? (unsigned long long)a->prefetch_bytes : 0ull;
+  p.trace = next_trace_slot((tiles + p.has_stats) * splits);
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("CRAB_SKINNY_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((tiles + p.has_stats) * splits));
   cfg.blockDim = dim3(SK_THREADS);

@@ -74,7 +74,24 @@ int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint6
   return 0;
 }
 
+static unsigned long long* g_trace_buf = nullptr;
+static int g_trace_slots = 0, g_trace_ctas = 0, g_trace_next = 0;
+unsigned long long* next_trace_slot(int ctas) {
+  if (!g_trace_buf || g_trace_next >= g_trace_slots) return nullptr;
+  const int slot = g_trace_next++;
+  if (ctas > g_trace_ctas) return nullptr;
+  return g_trace_buf + (size_t)slot * g_trace_ctas * 16;
+}
+
 }  // namespace crab
+
+extern "C" int crab_debug_trace(void* buf, int nslots, int ctas_per_slot) {
+  crab::g_trace_buf = reinterpret_cast<unsigned long long*>(buf);
+  crab::g_trace_slots = buf ? nslots : 0;
+  crab::g_trace_ctas = ctas_per_slot;
+  crab::g_trace_next = 0;
+  return CRAB_OK;
+}
 
 extern "C" const char* crab_last_error(void) { return crab::last_error_buf(); }
 

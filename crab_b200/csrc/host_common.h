@@ -69,4 +69,8 @@ inline cudaError_t launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Diagnostics (tools/trace_skinny.py): when crab_debug_trace() has armed a buffer, every traced launch gets the next slot of
+// [ctas][8] globaltimer stamps; nullptr otherwise (the kernels then skip every stamp).
+unsigned long long* next_trace_slot(int ctas);
+
 }  // namespace crab

@@ -202,6 +202,10 @@ __device__ __forceinline__ uint4 ld_dep_u4(const void* p) {
   asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+// diagnostics: stamp i of this CTA in a per-launch trace slot (nullptr = tracing off, the normal case)
+__device__ __forceinline__ void trace_stamp(unsigned long long* t, int i) {
+  if (t) t[((size_t)blockIdx.x + (size_t)gridDim.x * blockIdx.y) * 16 + i] = globaltimer_ns();
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float ld_dep_f32(const float* p) {

@@ -340,6 +340,12 @@ int crab_im2col3x3(const void* in, int ldi, void* out, int h, int w, int C, void
 int crab_bilinear_f32(const float* in, int ldi, int hin, int win, float* out, int ldo, int hout, int wout, int C, float alpha,
                       float beta, int nchw_out, void* stream);
 
+/* Diagnostics only (tools/trace_skinny.py): arm (buf != NULL) or disarm a device buffer of nslots x ctas_per_slot x 16 uint64
+ * globaltimer stamps; each following crab_gemm_skinny_bf16 / crab_attn_decode_fused launch takes the next slot and its CTAs
+ * record when they started, passed the dependency wait, saw their first operand, finished their MMAs / stream and left.
+ * Process-wide, not thread-safe, costs ~1 us per CTA while armed. */
+int crab_debug_trace(void* buf, int nslots, int ctas_per_slot);
+
 #ifdef __cplusplus
 }
 #endif
