@@ -53,6 +53,9 @@ struct SkinnyParams {
   float* rstd;                   // [32]
   int* flags;                    // [0] z / rstd published, [32] CTAs that have left (self-cleaning)
   int n_tiles, kb_main, ldz, has_stats, norm, stats_linears, ext_from_z;
+  int stats_clusters;          // C: clusters that share the statistics item (0 when the launch has none)
+  float* stats_scratch;        // [C][34][32] floats (C > 1): per-cluster partial sums, combined by the last cluster to arrive
+  int* flags_clear;            // optional: flag slot of the PREVIOUS launch, zeroed here (then this launch leaves its own slot set)
   float eps, lora_scale;
   // L2 prefetch of the NEXT launch's weight stream: each CTA touches its share once its own loads are all issued, so HBM keeps
   // working through this launch's reduce / epilogue / exit and the next launch's ramp instead of idling between two kernels
@@ -177,7 +180,8 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) trace_stamp(p.trace, 0);
   const int S = p.splits;
-  const int tile = (int)blockIdx.x / S - p.has_stats;   // weight tile of this cluster (-1: the statistics cluster)
+  const int SC = p.stats_clusters;
+  const int tile = (int)blockIdx.x / S - SC;   // weight tile of this cluster (< 0: a statistics cluster)
   const int rank = (S > 1) ? (int)cluster_ctarank() : 0;
   // One cluster of the launch is the STATISTICS cluster (when the launch has one): its A tile is
   // [x rows (32) ; gamma*[R;A] rows], so the same MMA chain yields diag(x x^T) = sum x^2 and the hyper-LoRA router / A dots;
@@ -185,9 +189,11 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   // z' (their K-extension k-blocks, the last ones of the last rank) and rstd (epilogue scale) only after that flag.
   // It is the FIRST cluster of the grid: clusters are placed in block order, so it is resident before any cluster that will
   // wait for its flag (a last-placed statistics cluster can be starved of a contiguous slot by the very CTAs that spin on it).
-  const bool is_stats = p.has_stats && blockIdx.x < (unsigned)S;
+  const bool is_stats = blockIdx.x < (unsigned)(SC * S);
   const int KB = is_stats ? p.kb_main : p.kb_per_tile;
-  const int kb0 = rank * KB / S, kb1 = (rank + 1) * KB / S;
+  // K-slice: a weight tile is split over the S ranks of its cluster, the statistics item over the SC * S CTAs of its clusters
+  const int kpart = is_stats ? (int)blockIdx.x : rank, kparts = is_stats ? SC * S : S;
+  const int kb0 = kpart * KB / kparts, kb1 = (kpart + 1) * KB / kparts;
 
   if (warp == 0 && lane == 0) {
     if (!p.w_tiled) tma_prefetch_desc(&tmap_w);
@@ -208,7 +214,8 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
     if (lane == 0) {
       // ===================== producer =====================
       // Weights never depend on an earlier kernel: the ring is filled with W tiles before the PDL wait.
-      const int npre = min(SK_STAGES, kb1 - kb0);
+      const int depth = (p.debug >> 8) > 0 ? min(SK_STAGES, p.debug >> 8) : SK_STAGES;   // diagnostics: loads in flight per CTA
+      const int npre = min(depth, kb1 - kb0);
       const size_t blk0 = (size_t)tile * p.kb_per_tile;
       auto load_w = [&](int slot_i, int kb) {
         const uint32_t sw = smem_base + slot_i * SK_STAGE_BYTES;
@@ -246,6 +253,10 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
       uint32_t stage = 0, phase = 1;  // ring position after the prefill (npre == SK_STAGES wraps to stage 0)
       if (npre < SK_STAGES) { stage = (uint32_t)npre; phase = 0; }
       for (int kb = kb0 + npre; kb < kb1; ++kb) {
+        if (depth < SK_STAGES) {   // wait until load (i - depth) has landed before issuing load i
+          const int j = kb - kb0 - depth;
+          mbar_wait(full_bar(j % SK_STAGES), (uint32_t)((j / SK_STAGES) & 1));
+        }
         mbar_wait(empty_bar(stage), phase ^ 1);
         load_w((int)stage, kb);
         load_x((int)stage, kb);
@@ -301,6 +312,10 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   float bias_v = 0.f;
   if (epi) {
     pdl_wait();
+    if (p.flags_clear && blockIdx.x == 0 && threadIdx.x == 64) {   // the launch that used that slot is complete
+      p.flags_clear[0] = 0;
+      p.flags_clear[1] = 0;
+    }
     if (own && p.bias) bias_v = p.bias[tile * SK_BM + row];
     if (add_res) {
       const unsigned short* rp = reinterpret_cast<const unsigned short*>(p.residual) + (tile * SK_BM + row);
@@ -322,6 +337,7 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   if (is_stats) {
     // ---- statistics cluster: partial x x^T rows / router-A dots of every rank -> rank 0 -> rstd, z', flag ----
     cluster_sync_all();   // every CTA of the cluster has finished its MMAs: the TMA ring is free to hold partials
+    if (threadIdx.x == 64) trace_stamp(p.trace, 8);
     if (epi && row < SK_SROWS) {
       // dots row `row` -> slot 32 + row of rank 0's buffer
       const uint32_t local = smem_base + (uint32_t)((rank * SK_SSROWS + 32 + row) * SK_PSTRIDE * 4);
@@ -339,7 +355,9 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
       const uint32_t dl = smem_base + (uint32_t)(((rank * SK_SSROWS + b) * SK_PSTRIDE + b) * 4);
       asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(map_to_rank(dl, 0u)), "f"(d) : "memory");
     }
+    if (threadIdx.x == 64) trace_stamp(p.trace, 9);
     cluster_sync_all();
+    if (threadIdx.x == 64) trace_stamp(p.trace, 6);
     if (rank == 0 && epi) {
       const int tt = (warp - 2) * 32 + lane;
       const int b = tt & 31, l = tt >> 5;
@@ -347,40 +365,82 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
       const int nw = L > 1 ? L : 1;
       const float* part = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
       if (l < nw) {
-        float ss = 0.f;
+        // this cluster's sums (fixed rank order): thread (b, l) owns sum x^2 of batch row b and the 11 dots of linear l
+        float ss = 0.f, t[11];
         for (int s = 0; s < S; ++s) ss += part[(s * SK_SSROWS + b) * SK_PSTRIDE + b];   // diagonal of x x^T
-        const float rs = p.norm ? rsqrtf(ss / (float)(p.kb_main * SK_BK) + p.eps) : 1.0f;
-        if (l == 0 && p.norm && b < p.M) p.rstd[b] = rs;
-        if (l < L && b < p.M) {
-          float t[11];
 #pragma unroll
-          for (int j = 0; j < 11; ++j) {
-            float a = 0.f;
-            for (int s = 0; s < S; ++s) a += part[(s * SK_SSROWS + 32 + l * 11 + j) * SK_PSTRIDE + b];
-            t[j] = a;
-          }
-          const float l0 = t[0] * rs, l1 = t[1] * rs, l2 = t[2] * rs;
-          const float mx = fmaxf(l0, fmaxf(l1, l2));
-          const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx), e2 = __expf(l2 - mx);
-          const float inv = p.lora_scale / (e0 + e1 + e2);
-          const float rw[3] = {e0 * inv, e1 * inv, e2 * inv};
-          __nv_bfloat16* zrow = p.zbuf + (size_t)b * p.ldz + l * 24;
+        for (int j = 0; j < 11; ++j) t[j] = 0.f;
+        if (l < L) {
+#pragma unroll 1
+          for (int s = 0; s < S; ++s) {
+            const float* pr = part + (s * SK_SSROWS + 32 + l * 11) * SK_PSTRIDE + b;
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {   // z' is NOT normalised: the consumers' epilogue multiplies the whole accumulator by rstd
-            uint4 v;
-            v.x = pack_bf16x2(rw[i] * t[3], rw[i] * t[4]);
-            v.y = pack_bf16x2(rw[i] * t[5], rw[i] * t[6]);
-            v.z = pack_bf16x2(rw[i] * t[7], rw[i] * t[8]);
-            v.w = pack_bf16x2(rw[i] * t[9], rw[i] * t[10]);
-            *reinterpret_cast<uint4*>(zrow + i * 8) = v;
+            for (int j = 0; j < 11; ++j) t[j] += pr[j * SK_PSTRIDE];
           }
         }
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        asm volatile("bar.sync 2, %0;" ::"r"(32 * nw) : "memory");
-        if (tt == 0) {
-          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags), "r"(1) : "memory");
-          trace_stamp(p.trace, 5);
+        bool fin = true;
+        if (SC > 1) {
+          // several statistics clusters: partials meet in global memory, the last cluster to arrive adds them in cluster order
+          float* sc = p.stats_scratch + (size_t)(blockIdx.x / S) * (34 * 32);
+          if (l == 0) sc[b] = ss;
+          if (l < L) {
+#pragma unroll
+            for (int j = 0; j < 11; ++j) sc[(1 + l * 11 + j) * 32 + b] = t[j];
+          }
+          __threadfence();
+          asm volatile("bar.sync 2, %0;" ::"r"(32 * nw) : "memory");
+          __shared__ int ticket_s;
+          if (tt == 0) ticket_s = atomicAdd(p.flags + 1, 1);
+          asm volatile("bar.sync 2, %0;" ::"r"(32 * nw) : "memory");
+          fin = ticket_s == SC - 1;
+          if (fin) {
+            __threadfence();
+            ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 11; ++j) t[j] = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < SC; ++c) {
+              const float* scc = p.stats_scratch + (size_t)c * (34 * 32);
+              float v;
+              asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(scc + b) : "memory");
+              ss += v;
+              if (l < L) {
+#pragma unroll
+                for (int j = 0; j < 11; ++j) {
+                  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(scc + (1 + l * 11 + j) * 32 + b) : "memory");
+                  t[j] += v;
+                }
+              }
+            }
+          }
+        }
+        if (fin) {
+          const float rs = p.norm ? rsqrtf(ss / (float)(p.kb_main * SK_BK) + p.eps) : 1.0f;
+          if (l == 0 && p.norm && b < p.M) p.rstd[b] = rs;
+          if (l < L && b < p.M) {
+            const float l0 = t[0] * rs, l1 = t[1] * rs, l2 = t[2] * rs;
+            const float mx = fmaxf(l0, fmaxf(l1, l2));
+            const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx), e2 = __expf(l2 - mx);
+            const float inv = p.lora_scale / (e0 + e1 + e2);
+            const float rw[3] = {e0 * inv, e1 * inv, e2 * inv};
+            __nv_bfloat16* zrow = p.zbuf + (size_t)b * p.ldz + l * 24;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {   // z' is NOT normalised: the consumers' epilogue multiplies the whole accumulator by rstd
+              uint4 v;
+              v.x = pack_bf16x2(rw[i] * t[3], rw[i] * t[4]);
+              v.y = pack_bf16x2(rw[i] * t[5], rw[i] * t[6]);
+              v.z = pack_bf16x2(rw[i] * t[7], rw[i] * t[8]);
+              v.w = pack_bf16x2(rw[i] * t[9], rw[i] * t[10]);
+              *reinterpret_cast<uint4*>(zrow + i * 8) = v;
+            }
+          }
+          __threadfence();
+          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("bar.sync 2, %0;" ::"r"(32 * nw) : "memory");
+          if (tt == 0) {
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags), "r"(1) : "memory");
+            trace_stamp(p.trace, 5);
+          }
         }
       }
     }
@@ -489,11 +549,12 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   if (threadIdx.x == 0) trace_stamp(p.trace, 7);
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
   // self-cleaning flags: the last CTA to get here (every flag wait is over by then) zeroes them for the next launch
-  if (p.has_stats && threadIdx.x == 0) {
+  if (p.has_stats && !p.flags_clear && threadIdx.x == 0) {
     __threadfence();
     const int prev = atomicAdd(p.flags + 32, 1);
     if (prev == (int)gridDim.x - 1) {
       p.flags[0] = 0;
+      p.flags[1] = 0;
       p.flags[32] = 0;
       __threadfence();
     }
@@ -633,10 +694,22 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
   p.eps = a->eps; p.lora_scale = a->lora_scale;
   p.pf_ptr = reinterpret_cast<const uint8_t*>(a->prefetch);
   p.pf_bytes = (a->prefetch && a->prefetch_bytes > 0) ? (unsigned long long)a->prefetch_bytes : 0ull;
-  p.trace = next_trace_slot((tiles + p.has_stats) * splits);
+  // clusters that share the statistics item: ~8 k-blocks per CTA (its stream is latency-bound: x from L2 + 5 KB of router/A rows per
+  // k-block behind the weight streams of 300 other CTAs), at most 8; more than one needs the scratch buffer
+  int sc = 0;
+  if (has_stats) {
+    sc = a->stats_clusters > 0 ? a->stats_clusters : (a->stats_scratch ? (kb_main + splits * 8 - 1) / (splits * 8) : 1);
+    if (sc > 8) sc = 8;
+    if (sc * splits > kb_main) sc = kb_main / splits > 0 ? kb_main / splits : 1;
+    CRAB_REQUIRE(sc == 1 || a->stats_scratch, "crab_gemm_skinny_bf16: stats_clusters > 1 needs stats_scratch (8 x 34 x 32 floats)");
+  }
+  p.stats_clusters = sc;
+  p.stats_scratch = a->stats_scratch;
+  p.flags_clear = has_stats ? a->flags_clear : nullptr;
+  p.trace = next_trace_slot((tiles + sc) * splits);
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("CRAB_SKINNY_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)((tiles + p.has_stats) * splits));
+  cfg.gridDim = dim3((unsigned)((tiles + sc) * splits));
   cfg.blockDim = dim3(SK_THREADS);
   cfg.dynamicSmemBytes = SK_SMEM;
   cfg.stream = stream;

@@ -191,10 +191,13 @@ class CrabEngine:
         # K-split (cluster size) per decode linear, 0 = the library's choice; env CRAB_SKINNY_SPLITS="qkv:2,o:8,gu:1,d:8" overrides
         # o_proj: 4 rather than the library's 8 — measured inside the step (tools/sweep_splits.sh): 14-15 us instead of 20.6 us per
         # launch; its input arrives from the attention kernel all at once, so a shorter DSMEM reduce beats the extra CTAs
-        self.skinny_splits = {"qkv": 0, "o": 4, "gu": 0, "d": 0}
+        self.skinny_splits = {"qkv": 0, "o": 4, "gu": 0, "d": 4}
         for kv in filter(None, os.environ.get("CRAB_SKINNY_SPLITS", "").split(",")):
             k_, v_ = kv.split(":")
             self.skinny_splits[k_] = int(v_)
+        # flag slots in a ring (each launch zeroes its predecessor's) and several statistics clusters per launch (0 = library's choice)
+        self.flag_ring = os.environ.get("CRAB_FLAG_RING", "1") != "0"
+        self.stats_clusters = int(os.environ.get("CRAB_STATS_CLUSTERS", "0"))
         # L2 prefetch of the next linear's weights from the tail of each decode linear (MB per launch, 0 = off)
         self.prefetch_mb = int(os.environ.get("CRAB_PREFETCH_MB", "0"))
         # K-split (= thread-block-cluster size) of the persistent decode GEMM chain
@@ -731,7 +734,7 @@ class CrabEngine:
         return ops.ChainPhase(x_rows, self.lm_head_c, logits, k=c.hidden, norm=True, eps=c.eps,
                               rstd=self._buf("dec_rstd_head", (32,), torch.float32), n=self.vocab)
 
-    def _head(self, x_last: torch.Tensor, logits: torch.Tensor, next_ids: torch.Tensor):
+    def _head(self, x_last: torch.Tensor, logits: torch.Tensor, next_ids: torch.Tensor, flag_kw: Optional[dict] = None):
         """final RMSNorm -> lm_head (fp32 logits) -> greedy arg-max."""
         c = self.cfg.decoder
         if x_last.shape[0] <= 32 and self.lm_head_p is not None:
@@ -740,7 +743,8 @@ class CrabEngine:
         elif x_last.shape[0] <= 32 and self.lm_head_c is not None:
             # one launch: the statistics cluster computes rstd, the lm_head tiles apply it in their epilogue (gamma is in lm_head_c)
             ops.gemm_skinny(x_last, self.lm_head_c, out=logits, n=self.vocab, norm=True, eps=c.eps,
-                            rstd=self._buf("dec_rstd_head", (32,), torch.float32), flags=self._flags("head"), tag="lm_head_skinny")
+                            rstd=self._buf("dec_rstd_head", (32,), torch.float32), tag="lm_head_skinny",
+                            **(flag_kw if flag_kw is not None else dict(flags=self._flags("head"))))
         else:
             hn = ops.rmsnorm(x_last, self.final_norm, c.eps, out=self._buf("head_hn", tuple(x_last.shape)))
             ops.gemm(hn, self.lm_head, out=logits)
@@ -753,6 +757,22 @@ class CrabEngine:
         """Per-GEMM flag words of the fused skinny launches (zero on entry, left zero).  One buffer per linear: with programmatic
         dependent launch the next kernel's CTAs may poll before the previous launch has reset ITS flags."""
         return self._buf("dec_flags_" + name, (64,), torch.int32, zero=True)
+
+    def _flag_ring(self, n: int):
+        """Flag slots for the n statistics-carrying launches of one decode step: launch k raises slot k and zeroes slot k - 1 (the
+        first one zeroes the last slot of the previous step), so no launch spends its tail resetting its own flags; plus the
+        scratch through which several statistics clusters of one launch combine.  Returns a function handing out the kwargs."""
+        if not self.flag_ring:
+            names = iter(range(n))
+            return lambda: dict(flags=self._flags("l%d" % (next(names) % 4)))
+        ring = self._buf("dec_flag_ring_%d" % n, (n, 32), torch.int32, zero=True)
+        scratch = self._buf("dec_stats_scratch", (8 * 34 * 32,), torch.float32)
+        it = iter(range(n))
+
+        def slot():
+            k = next(it)
+            return dict(flags=ring[k], flags_clear=ring[(k - 1) % n], stats_scratch=scratch, stats_clusters=self.stats_clusters)
+        return slot
 
     def prefill(self, inputs_embeds: torch.Tensor):
         """inputs_embeds bf16 [B,S,D] (consumed in place) -> (last-position logits fp32 [B, vocab], next ids [B])."""
@@ -873,6 +893,9 @@ class CrabEngine:
         gqa_tc = G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
         fused = self.fuse_decode_attn and not gqa_tc
         o_fused_lora = lo and fused and nsplit == 1     # the attention kernel writes o_proj's z columns into at[:, nq:]
+        o_stats = lo and not o_fused_lora
+        head_fused = B <= 32 and self.lm_head_p is None and self.lm_head_c is not None
+        fslot = self._flag_ring(len(self.layers) * (2 + int(o_stats) + int(lo)) + int(head_fused))
         ops.set_pdl(self.pdl_chain)
         try:
             ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)  # embed_tokens of the previous arg-max
@@ -884,7 +907,7 @@ class CrabEngine:
                 nxt_qkv = self.layers[li + 1]["wqkv_c"] if li + 1 < len(self.layers) else self.lm_head_c
                 ops.gemm_skinny(x, L["wqkv_c"], bias=L["bqkv"], out=qkv, z=z["qkv"] if lo else None, kext=self.EXT_QKV if lo else 0,
                                 stats=L.get("st_qkv"), stats_linears=3 if lo else 0, norm=True, eps=c.eps, lora_scale=sc, rstd=rs["qkv"],
-                                flags=self._flags("qkv"), splits=self.skinny_splits["qkv"])
+                                splits=self.skinny_splits["qkv"], **fslot())
                 self._decode_attention(li, B, nsplit, ws, qkv, at, fused, gqa_tc, o_fused_lora)
                 # the kernel right after the decode attention is launched under its own PDL mask: early-resident streaming-GEMM
                 # CTAs must not squat on the SMs while the 1024-CTA attention kernel still runs
@@ -894,17 +917,17 @@ class CrabEngine:
                     ops.gemm_skinny(at, L["wo_c"], residual=x, out=x, z=at[:, nq:], kext=self.EXT_O, splits=self.skinny_splits["o"], **pf(L["wgu_c"]))
                 else:
                     ops.gemm_skinny(at, L["wo_c"], residual=x, out=x, z=z["o"] if lo else None, kext=self.EXT_O if lo else 0,
-                                    stats=L.get("st_o"), stats_linears=1 if lo else 0, lora_scale=sc, flags=self._flags("o") if lo else None,
-                                    splits=self.skinny_splits["o"], **pf(L["wgu_c"]))
+                                    stats=L.get("st_o"), stats_linears=1 if lo else 0, lora_scale=sc,
+                                    splits=self.skinny_splits["o"], **(fslot() if lo else {}), **pf(L["wgu_c"]))
                 if self.pdl_after_attn != self.pdl_chain:
                     ops.set_pdl(self.pdl_chain)
                 ops.gemm_skinny(x, L["wgu_c"], act=ops.ACT_SWIGLU, out=hh, z=z["gu"] if lo else None, kext=self.EXT_GU if lo else 0,
                                 stats=L.get("st_gu"), stats_linears=2 if lo else 0, norm=True, eps=c.eps, lora_scale=sc, rstd=rs["gu"],
-                                flags=self._flags("gu"), splits=self.skinny_splits["gu"], **pf(L["wd_c"]))
+                                splits=self.skinny_splits["gu"], **fslot(), **pf(L["wd_c"]))
                 ops.gemm_skinny(hh, L["wd_c"], residual=x, out=x, z=z["d"] if lo else None, kext=self.EXT_D if lo else 0,
-                                stats=L.get("st_d"), stats_linears=1 if lo else 0, lora_scale=sc, flags=self._flags("d") if lo else None,
-                                splits=self.skinny_splits["d"], **pf(nxt_qkv))
-            self._head(x, self.logits, self.next_ids)
+                                stats=L.get("st_d"), stats_linears=1 if lo else 0, lora_scale=sc,
+                                splits=self.skinny_splits["d"], **(fslot() if lo else {}), **pf(nxt_qkv))
+            self._head(x, self.logits, self.next_ids, flag_kw=fslot() if head_fused else None)
             ops.add_scalar_i32(self.past_dev, 1)
             ops.add_scalar_i32(self.len_dev, 1)
         finally:

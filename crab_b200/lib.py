@@ -85,6 +85,7 @@ class SkinnyArgs(C.Structure):
         ("eps", C.c_float), ("lora_scale", C.c_float),
         ("rstd", C.c_void_p), ("flags", C.c_void_p),
         ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
+        ("stats_scratch", C.c_void_p), ("flags_clear", C.c_void_p), ("stats_clusters", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -519,12 +519,14 @@ def gemm_skinny(x: torch.Tensor, w, *, bias: Optional[torch.Tensor] = None,
                 splits: int = 0, z: Optional[torch.Tensor] = None, kext: int = 0, stats: Optional[torch.Tensor] = None,
                 stats_linears: int = 0, norm: bool = False, eps: float = 0.0, lora_scale: float = 1.0,
                 rstd: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None, tag: str = "gemm_skinny_tcgen05",
-                prefetch: Optional[torch.Tensor] = None, prefetch_bytes: int = 0) -> torch.Tensor:
+                prefetch: Optional[torch.Tensor] = None, prefetch_bytes: int = 0, stats_scratch: Optional[torch.Tensor] = None,
+                flags_clear: Optional[torch.Tensor] = None, stats_clusters: int = 0) -> torch.Tensor:
     """out[M, N'] = epilogue(x[M<=32, K] @ w[N, K]^T): the decode-step weight-streaming GEMM (swap-AB, split-K).
     With z / kext the K-extension columns come from a separate buffer; norm / stats_linears fold the RMSNorm (as an epilogue scale
     over a gamma-folded weight) and the hyper-LoRA router / A pre-pass into the same launch (see include/crab_b200.h)."""
     packed = isinstance(w, PackedWeight)
-    _req_cuda(x, w.data if packed else w, bias, residual, out, z, stats, rstd, flags)
+    _req_cuda(x, w.data if packed else w, bias, residual, out, z, stats, rstd, flags, stats_scratch, flags_clear)
+    assert stats_scratch is None or (stats_scratch.dtype == torch.float32 and stats_scratch.numel() >= 8 * 34 * 32)
     assert x.dim() == 2 and x.dtype == torch.bfloat16
     M = x.shape[0]
     if packed:
@@ -548,7 +550,8 @@ def gemm_skinny(x: torch.Tensor, w, *, bias: Optional[torch.Tensor] = None,
                          out_dtype=(BF16 if out.dtype == torch.bfloat16 else F32), splits=splits,
                          Z=_ptr(z), ldz=(z.stride(0) if z is not None else 0), Kext=kext, stats_packed=_ptr(stats),
                          stats_linears=stats_linears, norm=1 if norm else 0, eps=eps, lora_scale=lora_scale, rstd=_ptr(rstd),
-                         flags=_ptr(flags), prefetch=_ptr(prefetch),
+                         flags=_ptr(flags), stats_scratch=_ptr(stats_scratch), flags_clear=_ptr(flags_clear),
+                         stats_clusters=stats_clusters, reserved0=0, prefetch=_ptr(prefetch),
                          prefetch_bytes=(min(prefetch_bytes or prefetch.numel() * prefetch.element_size(), prefetch.numel() * prefetch.element_size())
                                          if prefetch is not None else 0))
     wb = 2.0 * N * (K + kext) + (stats.numel() * 2.0 if stats is not None else 0.0)

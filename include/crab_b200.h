@@ -230,7 +230,14 @@ typedef struct crab_skinny_args {
    *      rstd[b] = rsqrt(mean(X[b]^2) + eps) and, per wrapped linear, t = X . [R;A]^T, z' = lora_scale * softmax(rstd * t[0:3])_i *
    *      t[3+j] -> Z[b, 24*linear + 8*i + j]; the K-extension k-blocks and the epilogues of the other clusters wait for it.
    *      replaces the separate crab_row_norm_loraz launch (peft_hyper/tuners/lora.py:344-350, models/modeling_llama.py:103-117).
-   * rstd: 32 floats of scratch; flags: 64 ints, 128-byte aligned, zero on entry (left zero). */
+   * rstd: 32 floats of scratch; flags: 64 ints, 128-byte aligned, zero on entry (left zero).
+   * stats_clusters / stats_scratch: the statistics item is latency-bound (x tiles from L2 behind everybody's weight stream), so
+   *      its K range may be shared by up to 8 clusters whose partial sums meet in stats_scratch (8 x 34 x 32 floats; any launch
+   *      may reuse the same buffer) and are added in cluster order by the last one to arrive (deterministic).  0 = the library's
+   *      choice (several when stats_scratch is given, else one).
+   * flags_clear: optional.  NULL: the launch zeroes its own `flags` before it exits (one atomic per CTA, ~1 us at the tail).
+   *      Otherwise: the `flags` slot (first 2 ints) of the launch that ran BEFORE this one on the stream — it is zeroed here and
+   *      this launch leaves its own slot set for the next launch to zero: give consecutive launches distinct slots in a ring. */
   const void* Z; int32_t ldz; int32_t Kext;
   const void* stats_packed; int32_t stats_linears; int32_t norm;
   float eps; float lora_scale;
@@ -238,6 +245,7 @@ typedef struct crab_skinny_args {
   /* prefetch / prefetch_bytes: optional — a global span (the NEXT launch's packed weights) that the CTAs pull into L2 once their own
    * loads are issued, so HBM does not idle between two dependent launches; no effect on results. */
   const void* prefetch; int64_t prefetch_bytes;
+  float* stats_scratch; int* flags_clear; int32_t stats_clusters; int32_t reserved0;
 } crab_skinny_args;
 int crab_gemm_skinny_plan(int N, int K, int* splits, int64_t* workspace_bytes, int* n_counters);
 int crab_skinny_packed_bytes(int N, int K, int64_t* bytes);

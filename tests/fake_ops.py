@@ -323,7 +323,7 @@ def _fused_linear(x, w, k, z, kext, stats, L, norm, eps, scale, bias, residual, 
 
 def gemm_skinny(x, w, *, bias=None, residual=None, act=ACT_NONE, out=None, out_dtype=torch.bfloat16, k=None, n=None, splits=0,
                 z=None, kext=0, stats=None, stats_linears=0, norm=False, eps=0.0, lora_scale=1.0, rstd=None, flags=None, tag="",
-                prefetch=None, prefetch_bytes=0):
+                prefetch=None, prefetch_bytes=0, stats_scratch=None, flags_clear=None, stats_clusters=0):
     packed = isinstance(w, PackedWeight)
     if packed and (kext or norm or stats_linears):
         assert (not norm and not stats_linears) or flags is not None

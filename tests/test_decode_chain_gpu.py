@@ -257,6 +257,37 @@ def test_fused_skinny_qkv_like(cuda_dev, M):
         assert e < 6e-3, e
 
 
+@pytest.mark.parametrize("clusters", [1, 3, 8])
+def test_fused_skinny_stats_clusters_and_flag_ring(cuda_dev, clusters):
+    """The statistics item shared by several clusters (partials combined through the scratch buffer by the last cluster to arrive)
+    gives the one-cluster result up to summation order, and is bit-reproducible; flag slots handed round a ring — every launch
+    zeroes its predecessor's slot and leaves its own set."""
+    from crab_b200 import ops
+
+    M = 32
+    lin = Lin(cuda_dev, 51, 4096, [4096, 4096, 4096], lora=True, gamma=True, bias=True, kext=96)
+    x = mk((M, 4096), cuda_dev, 52, 3.0).to(torch.bfloat16)
+    z = torch.zeros((32, 128), device=cuda_dev, dtype=torch.bfloat16)
+    rstd = torch.zeros(32, device=cuda_dev, dtype=torch.float32)
+    ring = torch.zeros((3, 32), device=cuda_dev, dtype=torch.int32)
+    scratch = torch.full((8 * 34 * 32,), float("nan"), device=cuda_dev, dtype=torch.float32)
+    outs = []
+    for it in range(6):
+        out = torch.empty((M, lin.N), device=cuda_dev, dtype=torch.bfloat16)
+        k = it % 3
+        ops.gemm_skinny(x, lin.packed, bias=lin.bias, out=out, z=z, kext=96, stats=lin.stats, stats_linears=3, norm=True, eps=1e-6,
+                        lora_scale=lin.scale, rstd=rstd, flags=ring[k], flags_clear=ring[(k - 1) % 3], stats_scratch=scratch,
+                        stats_clusters=clusters)
+        torch.cuda.synchronize()
+        assert int(ring[k, 0]) == 1 and int(ring[(k - 1) % 3, :2].abs().sum()) == 0, ring[:, :2]
+        assert int(ring[k, 1]) == (clusters if clusters > 1 else 0)
+        assert torch.allclose(rstd[:M], torch.rsqrt(x.float().pow(2).mean(-1) + 1e-6), rtol=1e-5, atol=0)
+        e = rel(out, lin.ref(x))
+        assert e < 6e-3, e
+        outs.append(out)
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+
 def test_fused_skinny_gate_up_down_head(cuda_dev):
     """gate/up (SwiGLU, norm, 2 LoRA linears, no K split) -> down (K = 11008, 8-way split, 1 LoRA linear, in-place residual) ->
     final norm + lm_head (ragged N, fp32 out), each one launch, chained through bf16 buffers like the decode step."""

@@ -70,6 +70,15 @@ for j in range(6):
         if v.size:
             r = (v - origin) / 1e3
             out.append(f"      {lab[k]:22s} {r.min():8.2f} {np.median(r):8.2f} {r.max():8.2f}   ({v.size})")
+    tiles = {"qkv": -(-(b["heads"] + 2 * b["kv_heads"]) * b["head_dim"] // 128), "gate_up": -(-2 * b["inter"] // 128), "down": -(-b["hidden"] // 128)}.get(names[j % 5])
+    if tiles and n % (tiles + 1) == 0:
+        S = n // (tiles + 1)
+        out.append(f"      statistics cluster (first {S} CTAs):")
+        for k in (0, 2, 3, 4, 8, 9, 6, 5, 7):
+            v = m[:S, k][m[:S, k] > 0]
+            if v.size:
+                r = (v - origin) / 1e3
+                out.append(f"        {lab[k]:22s} {r.min():8.2f} {np.median(r):8.2f} {r.max():8.2f}   ({v.size})")
     ex = (m[:, 7][m[:, 7] > 0] - origin) / 1e3
     if prev_exit is not None:
         out.append(f"      -> last exit of previous launch to last exit of this one: {ex.max() - prev_exit:.2f} us")
