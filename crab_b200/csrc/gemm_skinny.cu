@@ -54,7 +54,7 @@ struct SkinnyParams {
   int* flags;                    // [0] z / rstd published, [32] CTAs that have left (self-cleaning)
   int n_tiles, kb_main, ldz, has_stats, norm, stats_linears, ext_from_z;
   int stats_clusters;          // C: clusters that share the statistics item (0 when the launch has none)
-  float* stats_scratch;        // [C][34][32] floats (C > 1): per-cluster partial sums, combined by the last cluster to arrive
+  float* stats_scratch;        // [C][3][32][12] floats (C > 1): per-cluster partial sums, combined by the last cluster to arrive
   int* flags_clear;            // optional: flag slot of the PREVIOUS launch, zeroed here (then this launch leaves its own slot set)
   float eps, lora_scale;
   // L2 prefetch of the NEXT launch's weight stream: each CTA touches its share once its own loads are all issued, so HBM keeps
@@ -97,6 +97,19 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t ran
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
+}
+// Remote shared-memory store that reports its bytes to an mbarrier of the destination CTA: the receiver waits for the expected
+// byte count, no fence on either side.  (barrier.cluster.arrive.release and mbarrier.arrive.release.cluster both compile to
+// MEMBAR.ALL.GPU, which inside a saturated weight stream costs 1-3 us per use: profiles/r04_skinny_timeline.txt.)
+__device__ __forceinline__ void st_async_f4(uint32_t remote_addr, uint32_t remote_bar, float a, float b, float c, float d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr),
+               "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void st_async_f1(uint32_t remote_addr, uint32_t remote_bar, float a) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(remote_addr), "f"(a), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
 }
 __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -176,6 +189,8 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   auto empty_bar = [&](int s) { return bar_base + 8u * (SK_STAGES + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * SK_STAGES);
   const uint32_t tmem_slot = bar_base + 8u * (2 * SK_STAGES + 1);
+  const uint32_t rfree_bar = bar_base + 8u * (2 * SK_STAGES + 2);   // one arrival per rank of the cluster: "my MMAs are done, my ring may be overwritten"
+  const uint32_t pfull_bar = bar_base + 8u * (2 * SK_STAGES + 3);   // bytes of the partials this CTA receives
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) trace_stamp(p.trace, 0);
@@ -200,7 +215,15 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
     tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < SK_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tfull_bar, 1);
+    mbar_init(rfree_bar, (uint32_t)S);
+    mbar_init(pfull_bar, 1);
     fence_barrier_init();
+    // partials this CTA will receive: a weight tile's rank gets its rows from all S ranks (128 B each), rank 0 of a statistics
+    // cluster gets the router/A dot rows and the 32 diagonal elements of x x^T from all S ranks
+    const int rpr = p.rows_per_rank;
+    const int rows_mine = max(0, min(rpr, SK_BM - rank * rpr));
+    const uint32_t expect = S == 1 ? 0u : is_stats ? (rank == 0 ? (uint32_t)S * (SK_SROWS * 128u + 32u * 4u) : 0u) : (uint32_t)(S * rows_mine) * 128u;
+    if (expect) mbar_arrive_expect_tx(pfull_bar, expect);
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 32); tmem_relinquish(); }
   tc_fence_before();
@@ -208,6 +231,8 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // the peers' barriers exist once every thread of the cluster has arrived here; the epilogue waits for that before its first remote op
+  if (S > 1) asm volatile("barrier.cluster.arrive.release;" ::: "memory");
 
   pdl_trigger();
   if (warp == 0) {
@@ -336,28 +361,45 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   __shared__ float rstd_s[32];
   if (is_stats) {
     // ---- statistics cluster: partial x x^T rows / router-A dots of every rank -> rank 0 -> rstd, z', flag ----
-    cluster_sync_all();   // every CTA of the cluster has finished its MMAs: the TMA ring is free to hold partials
-    if (threadIdx.x == 64) trace_stamp(p.trace, 8);
-    if (epi && row < SK_SROWS) {
-      // dots row `row` -> slot 32 + row of rank 0's buffer
-      const uint32_t local = smem_base + (uint32_t)((rank * SK_SSROWS + 32 + row) * SK_PSTRIDE * 4);
-      const uint32_t remote = map_to_rank(local, 0u);
+    if (epi) {
+      if (S > 1) {
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+        // every rank tells every rank that its MMAs are done (tfull was observed above), i.e. that its TMA ring may hold partials
+        if (warp == 2 && lane < S) mbar_arrive_remote_relaxed(map_to_rank(rfree_bar, (uint32_t)lane));
+        mbar_wait(rfree_bar, 0);
+      }
+      if (threadIdx.x == 64) trace_stamp(p.trace, 8);
+      const uint32_t pf0 = (S > 1) ? map_to_rank(pfull_bar, 0u) : 0u;
+      if (row < SK_SROWS) {
+        // dots row `row` -> slot 32 + row of rank 0's buffer
+        const uint32_t local = smem_base + (uint32_t)((rank * SK_SSROWS + 32 + row) * SK_PSTRIDE * 4);
+        if (S > 1) {
+          const uint32_t remote = map_to_rank(local, 0u);
 #pragma unroll
-      for (int g = 0; g < 8; ++g)
-        st_cluster_f4(remote + g * 16, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
-                      __uint_as_float(r[4 * g + 3]));
-    } else if (epi && row >= 96) {
-      // x x^T row of batch row b = row - 96: only its diagonal element is needed -> slot b, column b
-      const int b = row - 96;
-      float d = 0.f;
+          for (int g = 0; g < 8; ++g)
+            st_async_f4(remote + g * 16, pf0, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                        __uint_as_float(r[4 * g + 3]));
+        } else {   // a launch without cluster dimensions has no shared::cluster window (st.async / remote arrive are illegal there)
 #pragma unroll
-      for (int c = 0; c < 32; ++c) d = (c == b) ? __uint_as_float(r[c]) : d;
-      const uint32_t dl = smem_base + (uint32_t)(((rank * SK_SSROWS + b) * SK_PSTRIDE + b) * 4);
-      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(map_to_rank(dl, 0u)), "f"(d) : "memory");
+          for (int g = 0; g < 8; ++g)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(local + g * 16), "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]),
+                         "r"(r[4 * g + 3]) : "memory");
+        }
+      } else if (row >= 96) {
+        // x x^T row of batch row b = row - 96: only its diagonal element is needed -> slot b, column b
+        const int b = row - 96;
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) d = (c == b) ? __uint_as_float(r[c]) : d;
+        const uint32_t dl = smem_base + (uint32_t)(((rank * SK_SSROWS + b) * SK_PSTRIDE + b) * 4);
+        if (S > 1) st_async_f1(map_to_rank(dl, 0u), pf0, d);
+        else asm volatile("st.shared.f32 [%0], %1;" ::"r"(dl), "f"(d) : "memory");
+      }
+      if (threadIdx.x == 64) trace_stamp(p.trace, 9);
+      if (S == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else if (rank == 0) mbar_wait(pfull_bar, 0);
+      if (threadIdx.x == 64) trace_stamp(p.trace, 6);
     }
-    if (threadIdx.x == 64) trace_stamp(p.trace, 9);
-    cluster_sync_all();
-    if (threadIdx.x == 64) trace_stamp(p.trace, 6);
     if (rank == 0 && epi) {
       const int tt = (warp - 2) * 32 + lane;
       const int b = tt & 31, l = tt >> 5;
@@ -380,38 +422,34 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
         }
         bool fin = true;
         if (SC > 1) {
-          // several statistics clusters: partials meet in global memory, the last cluster to arrive adds them in cluster order
-          float* sc = p.stats_scratch + (size_t)(blockIdx.x / S) * (34 * 32);
-          if (l == 0) sc[b] = ss;
-          if (l < L) {
-#pragma unroll
-            for (int j = 0; j < 11; ++j) sc[(1 + l * 11 + j) * 32 + b] = t[j];
-          }
+          // several statistics clusters: partials meet in global memory, the last cluster to arrive adds them in cluster order.
+          // scratch[c][l][b][12] = {ss, t[0..10]} of thread (b, l): three 16-byte stores / loads per thread and cluster
+          float4* sc = reinterpret_cast<float4*>(p.stats_scratch) + ((size_t)(blockIdx.x / S) * (3 * 32) + l * 32 + b) * 3;
+          sc[0] = make_float4(ss, t[0], t[1], t[2]);
+          sc[1] = make_float4(t[3], t[4], t[5], t[6]);
+          sc[2] = make_float4(t[7], t[8], t[9], t[10]);
           __threadfence();
           asm volatile("bar.sync 2, %0;" ::"r"(32 * nw) : "memory");
           __shared__ int ticket_s;
           if (tt == 0) ticket_s = atomicAdd(p.flags + 1, 1);
           asm volatile("bar.sync 2, %0;" ::"r"(32 * nw) : "memory");
           fin = ticket_s == SC - 1;
+          if (threadIdx.x == 64) trace_stamp(p.trace, 14);
           if (fin) {
             __threadfence();
             ss = 0.f;
 #pragma unroll
             for (int j = 0; j < 11; ++j) t[j] = 0.f;
-#pragma unroll 1
+            const float4* rd = reinterpret_cast<const float4*>(p.stats_scratch) + ((size_t)l * 32 + b) * 3;
+#pragma unroll 4
             for (int c = 0; c < SC; ++c) {
-              const float* scc = p.stats_scratch + (size_t)c * (34 * 32);
-              float v;
-              asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(scc + b) : "memory");
-              ss += v;
-              if (l < L) {
-#pragma unroll
-                for (int j = 0; j < 11; ++j) {
-                  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(scc + (1 + l * 11 + j) * 32 + b) : "memory");
-                  t[j] += v;
-                }
-              }
+              const float4 v0 = __ldcg(rd + (size_t)c * (3 * 32 * 3)), v1 = __ldcg(rd + (size_t)c * (3 * 32 * 3) + 1),
+                           v2 = __ldcg(rd + (size_t)c * (3 * 32 * 3) + 2);
+              ss += v0.x; t[0] += v0.y; t[1] += v0.z; t[2] += v0.w;
+              t[3] += v1.x; t[4] += v1.y; t[5] += v1.z; t[6] += v1.w;
+              t[7] += v2.x; t[8] += v2.y; t[9] += v2.z; t[10] += v2.w;
             }
+            if (threadIdx.x == 64) trace_stamp(p.trace, 15);
           }
         }
         if (fin) {
@@ -477,31 +515,37 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
         for (int b = 0; b < 32; ++b) r[b] = __float_as_uint(__uint_as_float(r[b]) + bias_v);
       }
     }
-    // Barrier 1: every CTA of the cluster has finished its MMAs (its epilogue warps passed tfull), so its TMA ring is
-    // idle and can be overwritten with partials.  Layout in the owner's smem: [src rank][row in group][SK_PSTRIDE].
-    if (S > 1) cluster_sync_all();
-    if (threadIdx.x == 64) trace_stamp(p.trace, 8);
+    // Ring free: every rank tells every rank that its MMAs are done (its epilogue passed tfull), so its TMA ring is idle and can
+    // hold partials.  Layout in the owner's smem: [src rank][row in group][SK_PSTRIDE].  The partials travel as st.async stores
+    // that report their bytes to the owner's pfull barrier: no cluster barrier, no fence.
     if (epi) {
+      if (S > 1) {
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+        if (warp == 2 && lane < S) mbar_arrive_remote_relaxed(map_to_rank(rfree_bar, (uint32_t)lane));
+        mbar_wait(rfree_bar, 0);
+      }
+      if (threadIdx.x == 64) trace_stamp(p.trace, 8);
       const int dst_rank = (S > 1) ? row / R : 0;
       const int row_in = row - dst_rank * R;
       const uint32_t local = smem_base + (uint32_t)((rank * R + row_in) * SK_PSTRIDE * 4);
       if (S > 1) {
         const uint32_t remote = map_to_rank(local, (uint32_t)dst_rank);
+        const uint32_t rbar = map_to_rank(pfull_bar, (uint32_t)dst_rank);
 #pragma unroll
         for (int g = 0; g < 8; ++g)
-          st_cluster_f4(remote + g * 16, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
-                        __uint_as_float(r[4 * g + 3]));
+          st_async_f4(remote + g * 16, rbar, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                      __uint_as_float(r[4 * g + 3]));
       } else {
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(local + g * 16), "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]),
                        "r"(r[4 * g + 3]) : "memory");
       }
+      if (threadIdx.x == 64) trace_stamp(p.trace, 9);
+      if (S > 1) mbar_wait(pfull_bar, 0);   // all partials of this rank's rows have landed
+      else asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) trace_stamp(p.trace, 6);
     }
-    if (threadIdx.x == 64) trace_stamp(p.trace, 9);
-    if (S > 1) cluster_sync_all();  // Barrier 2: all partials have landed (release/acquire at cluster scope)
-    else if (epi) asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (threadIdx.x == 64) trace_stamp(p.trace, 6);
     if (epi) {
       const int tt = (warp - 2) * 32 + lane;
       const float* part = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
@@ -701,7 +745,7 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
     sc = a->stats_clusters > 0 ? a->stats_clusters : (a->stats_scratch ? (kb_main + splits * 8 - 1) / (splits * 8) : 1);
     if (sc > 8) sc = 8;
     if (sc * splits > kb_main) sc = kb_main / splits > 0 ? kb_main / splits : 1;
-    CRAB_REQUIRE(sc == 1 || a->stats_scratch, "crab_gemm_skinny_bf16: stats_clusters > 1 needs stats_scratch (8 x 34 x 32 floats)");
+    CRAB_REQUIRE(sc == 1 || a->stats_scratch, "crab_gemm_skinny_bf16: stats_clusters > 1 needs stats_scratch (8 x 36 x 32 floats)");
   }
   p.stats_clusters = sc;
   p.stats_scratch = a->stats_scratch;

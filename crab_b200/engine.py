@@ -766,7 +766,7 @@ class CrabEngine:
             names = iter(range(n))
             return lambda: dict(flags=self._flags("l%d" % (next(names) % 4)))
         ring = self._buf("dec_flag_ring_%d" % n, (n, 32), torch.int32, zero=True)
-        scratch = self._buf("dec_stats_scratch", (8 * 34 * 32,), torch.float32)
+        scratch = self._buf("dec_stats_scratch", (8 * 36 * 32,), torch.float32)
         it = iter(range(n))
 
         def slot():

@@ -526,7 +526,7 @@ def gemm_skinny(x: torch.Tensor, w, *, bias: Optional[torch.Tensor] = None,
     over a gamma-folded weight) and the hyper-LoRA router / A pre-pass into the same launch (see include/crab_b200.h)."""
     packed = isinstance(w, PackedWeight)
     _req_cuda(x, w.data if packed else w, bias, residual, out, z, stats, rstd, flags, stats_scratch, flags_clear)
-    assert stats_scratch is None or (stats_scratch.dtype == torch.float32 and stats_scratch.numel() >= 8 * 34 * 32)
+    assert stats_scratch is None or (stats_scratch.dtype == torch.float32 and stats_scratch.numel() >= 8 * 36 * 32)
     assert x.dim() == 2 and x.dtype == torch.bfloat16
     M = x.shape[0]
     if packed:

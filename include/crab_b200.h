@@ -232,7 +232,7 @@ typedef struct crab_skinny_args {
    *      replaces the separate crab_row_norm_loraz launch (peft_hyper/tuners/lora.py:344-350, models/modeling_llama.py:103-117).
    * rstd: 32 floats of scratch; flags: 64 ints, 128-byte aligned, zero on entry (left zero).
    * stats_clusters / stats_scratch: the statistics item is latency-bound (x tiles from L2 behind everybody's weight stream), so
-   *      its K range may be shared by up to 8 clusters whose partial sums meet in stats_scratch (8 x 34 x 32 floats; any launch
+   *      its K range may be shared by up to 8 clusters whose partial sums meet in stats_scratch (8 x 36 x 32 floats; any launch
    *      may reuse the same buffer) and are added in cluster order by the last one to arrive (deterministic).  0 = the library's
    *      choice (several when stats_scratch is given, else one).
    * flags_clear: optional.  NULL: the launch zeroes its own `flags` before it exits (one atomic per CTA, ~1 us at the tail).

@@ -270,7 +270,7 @@ def test_fused_skinny_stats_clusters_and_flag_ring(cuda_dev, clusters):
     z = torch.zeros((32, 128), device=cuda_dev, dtype=torch.bfloat16)
     rstd = torch.zeros(32, device=cuda_dev, dtype=torch.float32)
     ring = torch.zeros((3, 32), device=cuda_dev, dtype=torch.int32)
-    scratch = torch.full((8 * 34 * 32,), float("nan"), device=cuda_dev, dtype=torch.float32)
+    scratch = torch.full((8 * 36 * 32,), float("nan"), device=cuda_dev, dtype=torch.float32)
     outs = []
     for it in range(6):
         out = torch.empty((M, lin.N), device=cuda_dev, dtype=torch.bfloat16)

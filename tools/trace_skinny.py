@@ -54,7 +54,7 @@ out = [f"in-kernel timeline: backbone {a.backbone} bs {a.bs} layers {a.layers} c
        f"{len(used)} traced launches in the replay, traced step {e0.elapsed_time(e1) * 1e3:.1f} us"]
 assert len(used) == 5 * a.layers + 1, (len(used), 5 * a.layers + 1)
 names = ["qkv", "attn", "o", "gate_up", "down"]
-lab = {0: "entry", 1: "w-ring armed", 2: "dep wait over", 3: "first operand", 4: "last MMA / loop end", 5: "flag seen/raised", 6: "split-K landed", 7: "exit", 8: "cluster barrier 1", 9: "partials sent", 10: "epilogue loop done", 11: "producer thread done", 12: "MMA thread done", 13: "finish: start", 14: "finish: residual/bias in", 15: "finish: sums done"}
+lab = {0: "entry", 1: "w-ring armed", 2: "dep wait over", 3: "first operand", 4: "last MMA / loop end", 5: "flag seen/raised", 6: "split-K landed", 7: "exit", 8: "cluster barrier 1", 9: "partials sent", 10: "epilogue loop done", 11: "producer thread done", 12: "MMA thread done", 13: "finish: start", 14: "stats: ticket taken", 15: "stats: partials re-read"}
 base = used[5 * a.layer]
 origin = t[base, :, 0][t[base, :, 0] > 0].min()
 out.append(f"layer {a.layer}: us relative to the first CTA of its qkv launch entering; per stamp: min / median / max over CTAs (count)")
@@ -65,17 +65,23 @@ for j in range(6):
     m = t[s]
     n = int((m[:, 0] > 0).sum())
     out.append(f"  {nm}: {n} CTAs")
-    for k in (0, 1, 2, 3, 12, 11, 4, 5, 8, 9, 6, 13, 14, 15, 10, 7):
+    for k in (0, 1, 2, 3, 12, 11, 4, 5, 8, 9, 6, 10, 7):
         v = m[:, k][m[:, k] > 0]
         if v.size:
             r = (v - origin) / 1e3
             out.append(f"      {lab[k]:22s} {r.min():8.2f} {np.median(r):8.2f} {r.max():8.2f}   ({v.size})")
     tiles = {"qkv": -(-(b["heads"] + 2 * b["kv_heads"]) * b["head_dim"] // 128), "gate_up": -(-2 * b["inter"] // 128), "down": -(-b["hidden"] // 128)}.get(names[j % 5])
-    if tiles and n % (tiles + 1) == 0:
-        S = n // (tiles + 1)
-        out.append(f"      statistics cluster (first {S} CTAs):")
-        for k in (0, 2, 3, 4, 8, 9, 6, 5, 7):
-            v = m[:S, k][m[:S, k] > 0]
+    ns = 0
+    if tiles:
+        for S_ in (8, 4, 2, 1):
+            rest = n - tiles * S_
+            if rest > 0 and rest % S_ == 0 and rest // S_ <= 8:
+                ns = rest
+                break
+    if ns:
+        out.append(f"      statistics clusters (first {ns} CTAs, cluster size {S_}):")
+        for k in (0, 2, 3, 4, 8, 9, 6, 14, 15, 5, 7):
+            v = m[:ns, k][m[:ns, k] > 0]
             if v.size:
                 r = (v - origin) / 1e3
                 out.append(f"        {lab[k]:22s} {r.min():8.2f} {np.median(r):8.2f} {r.max():8.2f}   ({v.size})")
