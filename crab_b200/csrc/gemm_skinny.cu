@@ -634,11 +634,13 @@ __global__ void pack_skinny_weight_kernel(const __nv_bfloat16* __restrict__ w, i
   *reinterpret_cast<uint4*>(out + i * 8) = v;
 }
 
-// K-split (= cluster size) for (N, K): fill the 2 x SMs CTA slots in one wave, at least 4 k-blocks per CTA
+// K-split (= cluster size) for (N, K): about one CTA per SM (at most 1.3 x SMs), at least 4 k-blocks per CTA.  Measured inside the
+// decode step (tools/sweep_splits_timeline.sh, profiles/r04_split_sweep_timeline.txt): a second CTA per SM adds cluster-exchange
+// and scheduling cost but no bandwidth — LLaMA qkv (96 tiles) 2 > 4 > 1, o / down (32 tiles) 4 > 8 > 2, Qwen2 qkv (36 tiles) 4 > 8.
 int choose_splits(int N, int K) {
   const int tiles = (N + SK_BM - 1) / SK_BM;
   const int kb = (K + SK_BK - 1) / SK_BK;
-  const int slots = 2 * sm_count();
+  const int slots = sm_count() * 13 / 10;
   int s = 1;
   // powers of two only: odd cluster sizes schedule poorly (measured: qkv S=3 33.6 us vs S=2 26.2 us)
   while (s * 2 <= SK_MAX_SPLIT && tiles * s * 2 <= slots && kb / (s * 2) >= 4) s *= 2;
@@ -704,13 +706,14 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
   const int tiles = (a->N + SK_BM - 1) / SK_BM;
   const int kb_main = (a->K + SK_BK - 1) / SK_BK;
   const int kb = kb_main + (ext_z ? (a->Kext + SK_BK - 1) / SK_BK : 0);
-  int splits = a->splits > 0 ? a->splits : choose_splits(a->N, kb * SK_BK);
-  if (splits > SK_MAX_SPLIT) splits = SK_MAX_SPLIT;
-  if (splits > kb_main) splits = kb_main;
   static DeviceOnce attr_once;
   if (first_on_device(attr_once)) {
     CRAB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
+    CRAB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_tcgen05_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
+  int splits = a->splits > 0 ? a->splits : choose_splits(a->N, kb * SK_BK);
+  if (splits > SK_MAX_SPLIT) splits = SK_MAX_SPLIT;
+  if (splits > kb_main) splits = kb_main;
   CUtensorMap tw, tx, tz;
   int rc = 0;
   if (a->W_packed) memset(&tw, 0, sizeof(tw));

@@ -191,6 +191,8 @@ class CrabEngine:
         # K-split (cluster size) per decode linear, 0 = the library's choice; env CRAB_SKINNY_SPLITS="qkv:2,o:8,gu:1,d:8" overrides
         # o_proj: 4 rather than the library's 8 — measured inside the step (tools/sweep_splits.sh): 14-15 us instead of 20.6 us per
         # launch; its input arrives from the attention kernel all at once, so a shorter DSMEM reduce beats the extra CTAs
+        # down_proj: 4 (library: 8) — with the statistics clusters and the st.async exchange the timeline shows 20.5 us against
+        # 25.4 us (tools/sweep_splits_timeline.sh, profiles/r04_split_sweep_timeline.txt)
         self.skinny_splits = {"qkv": 0, "o": 4, "gu": 0, "d": 4}
         for kv in filter(None, os.environ.get("CRAB_SKINNY_SPLITS", "").split(",")):
             k_, v_ = kv.split(":")

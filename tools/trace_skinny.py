@@ -52,16 +52,19 @@ used = [i for i in range(NS) if (t[i, :, 0] > 0).any()]
 out = [f"in-kernel timeline: backbone {a.backbone} bs {a.bs} layers {a.layers} ctx {a.ctx} mode {os.environ['CRAB_DECODE_MODE']} "
        f"splits {os.environ.get('CRAB_SKINNY_SPLITS', 'default')} pdl {os.environ.get('CRAB_PDL', 'default')}: "
        f"{len(used)} traced launches in the replay, traced step {e0.elapsed_time(e1) * 1e3:.1f} us"]
-assert len(used) == 5 * a.layers + 1, (len(used), 5 * a.layers + 1)
-names = ["qkv", "attn", "o", "gate_up", "down"]
+PL = len(used) // a.layers          # traced launches per layer: 5, or 4 when the attention runs in the (untraced) flash kernel
+assert PL in (4, 5) and len(used) - PL * a.layers in (0, 1), (len(used), a.layers)   # + lm_head unless its grid exceeds a trace slot
+names = ["qkv", "attn", "o", "gate_up", "down"] if PL == 5 else ["qkv", "o", "gate_up", "down"]
 lab = {0: "entry", 1: "w-ring armed", 2: "dep wait over", 3: "first operand", 4: "last MMA / loop end", 5: "flag seen/raised", 6: "split-K landed", 7: "exit", 8: "cluster barrier 1", 9: "partials sent", 10: "epilogue loop done", 11: "producer thread done", 12: "MMA thread done", 13: "finish: start", 14: "stats: ticket taken", 15: "stats: partials re-read"}
-base = used[5 * a.layer]
+base = used[PL * a.layer]
 origin = t[base, :, 0][t[base, :, 0] > 0].min()
 out.append(f"layer {a.layer}: us relative to the first CTA of its qkv launch entering; per stamp: min / median / max over CTAs (count)")
 prev_exit = None
-for j in range(6):
-    s = used[5 * a.layer + j]
-    nm = names[j % 5] + (" (next layer)" if j == 5 else "")
+for j in range(PL + 1):
+    if PL * a.layer + j >= len(used):
+        break
+    s = used[PL * a.layer + j]
+    nm = names[j % PL] + (" (next layer)" if j == PL else "")
     m = t[s]
     n = int((m[:, 0] > 0).sum())
     out.append(f"  {nm}: {n} CTAs")
@@ -70,7 +73,7 @@ for j in range(6):
         if v.size:
             r = (v - origin) / 1e3
             out.append(f"      {lab[k]:22s} {r.min():8.2f} {np.median(r):8.2f} {r.max():8.2f}   ({v.size})")
-    tiles = {"qkv": -(-(b["heads"] + 2 * b["kv_heads"]) * b["head_dim"] // 128), "gate_up": -(-2 * b["inter"] // 128), "down": -(-b["hidden"] // 128)}.get(names[j % 5])
+    tiles = {"qkv": -(-(b["heads"] + 2 * b["kv_heads"]) * b["head_dim"] // 128), "gate_up": -(-2 * b["inter"] // 128), "down": -(-b["hidden"] // 128)}.get(names[j % PL])
     ns = 0
     if tiles:
         for S_ in (8, 4, 2, 1):
@@ -91,18 +94,18 @@ for j in range(6):
     prev_exit = ex.max()
 per_layer = []
 for l in range(1, a.layers - 1):
-    s0, s1 = used[5 * l], used[5 * (l + 1)]
+    s0, s1 = used[PL * l], used[PL * (l + 1)]
     per_layer.append((t[s1, :, 0][t[s1, :, 0] > 0].min() - t[s0, :, 0][t[s0, :, 0] > 0].min()) / 1e3)
 out.append(f"layer period (qkv entry to next qkv entry), layers 1..{a.layers - 2}: " + " ".join(f"{x:.1f}" for x in per_layer))
 # critical path: last exit of each launch, averaged over the middle layers
 acc = {n: [] for n in names}
 for l in range(1, a.layers - 1):
     prev = None
-    for j in range(6):
-        s = used[5 * l + j]
+    for j in range(PL + 1):
+        s = used[PL * l + j]
         ex = t[s, :, 7][t[s, :, 7] > 0].max() / 1e3
         if prev is not None:
-            acc[names[j % 5]].append(ex - prev)
+            acc[names[j % PL]].append(ex - prev)
         prev = ex
 out.append("last-exit to last-exit per launch, mean over the middle layers (us): " + ", ".join(f"{k} {np.mean(v):.1f}" for k, v in acc.items() if v))
 txt = "\n".join(out)
