@@ -325,6 +325,50 @@ struct DecodeParams {
   unsigned long long* trace;                  // diagnostics: [ctas][16] stamps or nullptr
 };
 
+// o_proj hyper-LoRA pre-pass, block tail shared by the fused decode attention (one block per (b, kv head)) and the split-KV
+// combine kernel (one block per (b, head)): t11 = this thread's share of the 11 router / A dots of its block's output elements.
+// Block partial -> workspace slot `slot` of batch row b; the last of the row's `nblocks` blocks (arrival counter) sums the slots
+// in fixed order, applies the fp32 router softmax and writes the 24 z columns (peft_hyper/tuners/lora.py:344-350).
+__device__ __forceinline__ void lora_prepass_tail(float (&t11)[11], int b, int slot, int nblocks, float* __restrict__ lora_ws,
+                                                  int* __restrict__ lora_cnt, __nv_bfloat16* __restrict__ z, int ldz, float lora_scale,
+                                                  float (*sh_red)[11], float* sh_tot, int* sh_ticket) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 11; ++j) {
+    const float v = warp_sum(t11[j]);
+    if (lane == 0) sh_red[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 11) {
+    float v = 0.f;
+    for (int w = 0; w < nwarps; ++w) v += sh_red[w][threadIdx.x];
+    lora_ws[((size_t)b * nblocks + slot) * 11 + threadIdx.x] = v;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *sh_ticket = atomicAdd(lora_cnt + b, 1);
+  __syncthreads();
+  if (*sh_ticket == nblocks - 1) {
+    __threadfence();
+    if (threadIdx.x < 11) {
+      const volatile float* wsp = lora_ws + (size_t)b * nblocks * 11 + threadIdx.x;
+      float t = 0.f;
+      for (int h2 = 0; h2 < nblocks; ++h2) t += wsp[(size_t)h2 * 11];
+      sh_tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 24) {
+      const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+      const float l0 = sh_tot[0], l1 = sh_tot[1], l2 = sh_tot[2];
+      const float mx = fmaxf(l0, fmaxf(l1, l2));
+      const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx), e2 = __expf(l2 - mx);
+      const float ri = (i == 0 ? e0 : (i == 1 ? e1 : e2)) / (e0 + e1 + e2);
+      z[(size_t)b * ldz + threadIdx.x] = __float2bfloat16_rn(lora_scale * ri * sh_tot[3 + j]);
+    }
+    if (threadIdx.x == 0) lora_cnt[b] = 0;  // ready for the next launch (next layer / next step)
+  }
+}
+
 // FUSE = the decode step's RoPE + KV-cache append (+ the o_proj hyper-LoRA pre-pass) folded into the attention kernel:
 // the block rotates its own q heads and the new k row in registers (models/modeling_llama.py:204-236), appends k / v to
 // the cache, treats the new key as one more key of the stream, and — when `ra` is given — finishes with the 11 router /
@@ -516,7 +560,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
     for (int j = 0; j < 8; ++j) sh_acc[sidx][g][li * 8 + j] = acc[g][j];
   }
   __syncthreads();
-  const bool lora = FUSE && p.ra != nullptr;
+  const bool lora = FUSE && p.ra != nullptr && p.nsplit == 1;   // split KV: the combine kernel does the pre-pass
   float t11[11];
 #pragma unroll
   for (int j = 0; j < 11; ++j) t11[j] = 0.f;
@@ -550,48 +594,17 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
       if (d == 0) { w[HD] = mm; w[HD + 1] = ll; }
     }
   }
-  if (lora) {
-    // block partial of the 11 dots -> workspace; the last block of this batch row reduces over the kv heads in order
-#pragma unroll
-    for (int j = 0; j < 11; ++j) {
-      const float v = warp_sum(t11[j]);
-      if (lane == 0) sh_red[warp][j] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 11) {
-      const float v = sh_red[0][threadIdx.x] + sh_red[1][threadIdx.x] + sh_red[2][threadIdx.x] + sh_red[3][threadIdx.x];
-      p.lora_ws[((size_t)b * p.KVH + kvh) * 11 + threadIdx.x] = v;
-      __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) sh_ticket = atomicAdd(p.lora_cnt + b, 1);
-    __syncthreads();
-    if (sh_ticket == p.KVH - 1) {
-      __threadfence();
-      if (threadIdx.x < 11) {
-        const volatile float* wsp = p.lora_ws + (size_t)b * p.KVH * 11 + threadIdx.x;
-        float t = 0.f;
-        for (int h2 = 0; h2 < p.KVH; ++h2) t += wsp[(size_t)h2 * 11];
-        sh_tot[threadIdx.x] = t;
-      }
-      __syncthreads();
-      if (threadIdx.x < 24) {
-        const int i = threadIdx.x / 8, j = threadIdx.x % 8;
-        const float l0 = sh_tot[0], l1 = sh_tot[1], l2 = sh_tot[2];
-        const float mx = fmaxf(l0, fmaxf(l1, l2));
-        const float e0 = __expf(l0 - mx), e1 = __expf(l1 - mx), e2 = __expf(l2 - mx);
-        const float ri = (i == 0 ? e0 : (i == 1 ? e1 : e2)) / (e0 + e1 + e2);
-        p.z[(size_t)b * p.ldz + threadIdx.x] = __float2bfloat16_rn(p.lora_scale * ri * sh_tot[3 + j]);
-      }
-      if (threadIdx.x == 0) p.lora_cnt[b] = 0;  // ready for the next launch (next layer / next step)
-    }
-  }
+  if (lora) lora_prepass_tail(t11, b, kvh, p.KVH, p.lora_ws, p.lora_cnt, p.z, p.ldz, p.lora_scale, sh_red, sh_tot, &sh_ticket);
   if (threadIdx.x == 0) trace_stamp(p.trace, 7);
 }
 
 template <int HD>
-__global__ void attn_decode_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ o, int ldo, int H,
-                                           int nsplit) {
+__global__ void attn_decode_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ o, int ldo, int H, int nsplit,
+                                           const __nv_bfloat16* __restrict__ ra, int ldra, __nv_bfloat16* __restrict__ z, int ldz,
+                                           float lora_scale, float* __restrict__ lora_ws, int* __restrict__ lora_cnt) {
+  __shared__ float sh_red[4][11];
+  __shared__ float sh_tot[11];
+  __shared__ int sh_ticket;
   pdl_trigger();
   pdl_wait();
   const int bh = blockIdx.x;
@@ -599,6 +612,9 @@ __global__ void attn_decode_combine_kernel(const float* __restrict__ ws, __nv_bf
   const float* w = ws + (size_t)bh * nsplit * (HD + 2);
   float mm = -INFINITY;
   for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, w[s * (HD + 2) + HD]);
+  float t11[11];
+#pragma unroll
+  for (int j = 0; j < 11; ++j) t11[j] = 0.f;
   for (int d = threadIdx.x; d < HD; d += blockDim.x) {
     float ll = 0.f, aa = 0.f;
     for (int s = 0; s < nsplit; ++s) {
@@ -607,8 +623,16 @@ __global__ void attn_decode_combine_kernel(const float* __restrict__ ws, __nv_bf
       ll += w[s * (HD + 2) + HD + 1] * c;
       aa += w[s * (HD + 2) + d] * c;
     }
-    o[(size_t)b * ldo + (size_t)h * HD + d] = __float2bfloat16_rn(ll > 0.f ? aa / ll : 0.f);
+    const __nv_bfloat16 ob = __float2bfloat16_rn(ll > 0.f ? aa / ll : 0.f);
+    o[(size_t)b * ldo + (size_t)h * HD + d] = ob;
+    if (ra) {   // o_proj hyper-LoRA pre-pass on the rounded output, as the unsplit fused kernel does
+      const float of = __bfloat162float(ob);
+      const __nv_bfloat16* rp = ra + (size_t)h * HD + d;
+#pragma unroll
+      for (int j = 0; j < 11; ++j) t11[j] += of * __bfloat162float(rp[(size_t)j * ldra]);
+    }
   }
+  if (ra) lora_prepass_tail(t11, b, h, H, lora_ws, lora_cnt, z, ldz, lora_scale, sh_red, sh_tot, &sh_ticket);
 }
 
 }  // namespace crab
@@ -698,8 +722,10 @@ extern "C" int crab_attn_decode(const void* q, int ldq, const void* k_cache, con
 #undef CRAB_DECODE_CASE
   CRAB_CHECK_CUDA(e);
   if (nsplit > 1) {
-    if (head_dim == 128) e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<128>, dim3(B * H), dim3(128), 0, st, (const float*)workspace, p.o, ldo, H, nsplit);
-    else e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<64>, dim3(B * H), dim3(64), 0, st, (const float*)workspace, p.o, ldo, H, nsplit);
+    if (head_dim == 128) e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<128>, dim3(B * H), dim3(128), 0, st, (const float*)workspace, p.o, ldo, H, nsplit,
+                                        (const __nv_bfloat16*)nullptr, 0, (__nv_bfloat16*)nullptr, 0, 0.f, (float*)nullptr, (int*)nullptr);
+    else e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<64>, dim3(B * H), dim3(64), 0, st, (const float*)workspace, p.o, ldo, H, nsplit,
+                        (const __nv_bfloat16*)nullptr, 0, (__nv_bfloat16*)nullptr, 0, 0.f, (float*)nullptr, (int*)nullptr);
     CRAB_CHECK_CUDA(e);
   }
   return CRAB_OK;
@@ -713,9 +739,8 @@ extern "C" int crab_attn_decode_fused(const crab_decode_fused_args* a, void* str
   CRAB_REQUIRE(a->ldq % 8 == 0 && ((uintptr_t)a->qkv % 16 == 0) && ((uintptr_t)a->cos_sin % 16 == 0), "crab_attn_decode_fused: alignment");
   CRAB_REQUIRE(a->ldq >= (a->H + 2 * a->KVH) * a->head_dim, "crab_attn_decode_fused: ldq smaller than the [q|k|v] row");
   if (a->lora_ra) {
-    CRAB_REQUIRE(a->nsplit == 1, "crab_attn_decode_fused: the LoRA pre-pass needs nsplit == 1");
     CRAB_REQUIRE(a->lora_z && a->lora_ws && a->lora_counters && a->ld_ra >= a->H * a->head_dim && a->ld_z >= 24,
-                 "crab_attn_decode_fused: LoRA pre-pass needs z, workspace [B*KVH*11] floats and counters [B] ints");
+                 "crab_attn_decode_fused: LoRA pre-pass needs z, workspace [B*KVH*11] floats ([B*H*11] when nsplit > 1) and counters [B] ints");
   }
   const int G = a->H / a->KVH;
   DecodeParams p;
@@ -738,8 +763,11 @@ extern "C" int crab_attn_decode_fused(const crab_decode_fused_args* a, void* str
 #undef CRAB_DECODE_CASE
   CRAB_CHECK_CUDA(e);
   if (a->nsplit > 1) {
-    if (a->head_dim == 128) e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<128>, dim3(a->B * a->H), dim3(128), 0, st, (const float*)a->workspace, p.o, a->ldo, a->H, a->nsplit);
-    else e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<64>, dim3(a->B * a->H), dim3(64), 0, st, (const float*)a->workspace, p.o, a->ldo, a->H, a->nsplit);
+    // split KV: the o_proj pre-pass moves to the combine kernel (one block per (b, head): lora_ws holds B * H * 11 floats)
+    if (a->head_dim == 128) e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<128>, dim3(a->B * a->H), dim3(128), 0, st, (const float*)a->workspace, p.o, a->ldo, a->H, a->nsplit,
+                                           p.ra, p.ldra, p.z, p.ldz, p.lora_scale, p.lora_ws, p.lora_cnt);
+    else e = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<64>, dim3(a->B * a->H), dim3(64), 0, st, (const float*)a->workspace, p.o, a->ldo, a->H, a->nsplit,
+                        p.ra, p.ldra, p.z, p.ldz, p.lora_scale, p.lora_ws, p.lora_cnt);
     CRAB_CHECK_CUDA(e);
   }
   return CRAB_OK;

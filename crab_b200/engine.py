@@ -821,7 +821,7 @@ class CrabEngine:
         G = H // KV
         gqa_tc = G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
         fused = self.fuse_decode_attn and not gqa_tc
-        o_fused_lora = lo and fused and nsplit == 1     # the attention kernel writes o_proj's z columns into at[:, nq:]
+        o_fused_lora = lo and fused     # the attention (or its split-KV combine) kernel writes o_proj's z columns into at[:, nq:]
         self._dec_mode = (fused, gqa_tc, o_fused_lora)
 
         def qkv_phase(L):
@@ -870,7 +870,7 @@ class CrabEngine:
             ops.attn_decode_fused(qkv, self.rope, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV,
                                   head_dim=hd, scale=1 / math.sqrt(hd), past_dev=self.past_dev, nsplit=nsplit, workspace=ws,
                                   ra=L["ra_o"] if o_fused_lora else None, z=at[:, nq:] if o_fused_lora else None, lora_scale=self.scaling,
-                                  lora_ws=self._buf("dec_lora_ws", (B * KV * 11,), torch.float32) if o_fused_lora else None,
+                                  lora_ws=self._buf("dec_lora_ws", (B * H * 11,), torch.float32) if o_fused_lora else None,
                                   lora_counters=self._buf("dec_lora_cnt", (B,), torch.int32, zero=True) if o_fused_lora else None)
         else:
             ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, 1, H, KV, hd, past=0, past_dev=self.past_dev)
@@ -894,7 +894,7 @@ class CrabEngine:
         G = H // KV
         gqa_tc = G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
         fused = self.fuse_decode_attn and not gqa_tc
-        o_fused_lora = lo and fused and nsplit == 1     # the attention kernel writes o_proj's z columns into at[:, nq:]
+        o_fused_lora = lo and fused     # the attention (or its split-KV combine) kernel writes o_proj's z columns into at[:, nq:]
         o_stats = lo and not o_fused_lora
         head_fused = B <= 32 and self.lm_head_p is None and self.lm_head_c is not None
         fslot = self._flag_ring(len(self.layers) * (2 + int(o_stats) + int(lo)) + int(head_fused))
@@ -950,7 +950,7 @@ class CrabEngine:
         G = H // KV
         gqa_tc = G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
         fused = self.fuse_decode_attn and not gqa_tc
-        o_fused_lora = lo and fused and nsplit == 1
+        o_fused_lora = lo and fused
         ops.set_pdl(self.pdl_chain)
         try:
             ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)

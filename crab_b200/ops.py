@@ -272,7 +272,7 @@ def attn_decode_fused(qkv: torch.Tensor, rope: torch.Tensor, k_cache: torch.Tens
         workspace = torch.empty(B * H * nsplit * (head_dim + 2), device=qkv.device, dtype=torch.float32)
     if ra is not None:
         assert z is not None and lora_ws is not None and lora_counters is not None
-        assert lora_ws.dtype == torch.float32 and lora_ws.numel() >= B * KVH * 11
+        assert lora_ws.dtype == torch.float32 and lora_ws.numel() >= B * (KVH if nsplit == 1 else H) * 11
         assert lora_counters.dtype == torch.int32 and lora_counters.numel() >= B and ra.stride(1) == 1 and z.stride(1) == 1
     a = _l.DecodeFusedArgs(
         qkv=qkv.data_ptr(), ldq=qkv.stride(0), cos_sin=rope.data_ptr(), k_cache=k_cache.data_ptr(), v_cache=v_cache.data_ptr(),

@@ -140,8 +140,8 @@ int crab_attn_decode(const void* q, int ldq, const void* k_cache, const void* v_
  *           given — the o_proj hyper-LoRA router / A projections with the fp32 router softmax
  *           (peft_hyper/tuners/lora.py:344-350), whose 24 z values land in lora_z (the o_proj GEMM's K-extension).
  *           qkv: RAW [B, ldq] rows [q | k | v] from the qkv projection; cos_sin from crab_rope_table; *past_dev = position
- *           of the new token (valid keys = past + 1).  lora_ws: B*KVH*11 floats; lora_counters: B ints, zero on entry
- *           (left zero).  The LoRA pre-pass needs nsplit == 1. */
+ *           of the new token (valid keys = past + 1).  lora_ws: B*KVH*11 floats (B*H*11 when nsplit > 1: the pre-pass then runs in
+ *           the split-KV combine launch, one block per head); lora_counters: B ints, zero on entry (left zero). */
 typedef struct crab_decode_fused_args {
   const void* qkv; int32_t ldq;
   const float* cos_sin;

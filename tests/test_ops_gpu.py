@@ -157,7 +157,8 @@ def test_attn_decode(cuda_dev, B, H, KVH, hd, length, nsplit):
 @pytest.mark.parametrize("B,H,KVH,hd,past,nsplit,lora", [(4, 8, 8, 128, 300, 1, True), (32, 32, 32, 128, 1100, 1, True),
                                                           (3, 28, 4, 128, 517, 1, True), (2, 8, 8, 128, 1213, 4, False),
                                                           (2, 4, 4, 128, 0, 1, True), (2, 4, 4, 64, 77, 1, False),
-                                                          (1, 28, 4, 128, 1000, 8, False)])
+                                                          (1, 28, 4, 128, 1000, 8, False), (1, 32, 32, 128, 150, 10, True),
+                                                          (3, 8, 8, 128, 1213, 4, True), (2, 28, 4, 128, 517, 3, True)])
 def test_attn_decode_fused_equals_the_three_kernel_sequence(cuda_dev, B, H, KVH, hd, past, nsplit, lora):
     """RoPE + KV append + decode attention (+ o_proj LoRA pre-pass) in one launch vs rope_kv_append -> attn_decode ->
     row_norm_loraz: caches bit-identical, attention output and z within fp32 summation-order noise; repeated launches
@@ -184,7 +185,7 @@ def test_attn_decode_fused_equals_the_three_kernel_sequence(cuda_dev, B, H, KVH,
     # fused
     k2, v2 = kc.clone(), vc.clone()
     o2 = torch.zeros(B, nq + 32, dtype=torch.bfloat16, device=cuda_dev)
-    ws = torch.empty(B * KVH * 11, dtype=torch.float32, device=cuda_dev)
+    ws = torch.empty(B * (KVH if nsplit == 1 else H) * 11, dtype=torch.float32, device=cuda_dev)
     cnt = torch.zeros(B, dtype=torch.int32, device=cuda_dev)
     for rep in range(2):
         if rep == 1:
