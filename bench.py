@@ -782,6 +782,13 @@ def main():
             tkey = top
         roof["peak_source"] = peaks_src
         roof["share_of_step"] = cands[top] / ms_step
+        if lin_us and "per_linear" not in roof:
+            # the class VERDICT r01 named stays visible whichever kernel holds the largest share of the step this round
+            ach_l = lin_bytes / (lin_us * 1e-6) / 1e9
+            roof["decode_linears"] = {"kernel": "decode:gemm_skinny_tcgen05 (qkv + o + gate/up + down + lm_head launches)", "bound": "hbm",
+                                      "achieved": ach_l, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_l / peaks["hbm_gbs"],
+                                      "share_of_step": cands["decode:weight_streaming_linears"] / ms_step,
+                                      "per_linear": {k: dec_roof[k] for k in lin_names}}
         if tkey in traffic:
             roof["traffic"] = traffic[tkey]["traffic_bytes_per_launch"]
             roof["traffic_note"] = f"ncu dram bytes of one launch, {traffic[tkey]['shape']} ({traffic.get('_source', '')})"

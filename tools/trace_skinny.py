@@ -55,7 +55,7 @@ out = [f"in-kernel timeline: backbone {a.backbone} bs {a.bs} layers {a.layers} c
 PL = len(used) // a.layers          # traced launches per layer: 5, or 4 when the attention runs in the (untraced) flash kernel
 assert PL in (4, 5) and len(used) - PL * a.layers in (0, 1), (len(used), a.layers)   # + lm_head unless its grid exceeds a trace slot
 names = ["qkv", "attn", "o", "gate_up", "down"] if PL == 5 else ["qkv", "o", "gate_up", "down"]
-lab = {0: "entry", 1: "w-ring armed", 2: "dep wait over", 3: "first operand", 4: "last MMA / loop end", 5: "flag seen/raised", 6: "split-K landed", 7: "exit", 8: "cluster barrier 1", 9: "partials sent", 10: "epilogue loop done", 11: "producer thread done", 12: "MMA thread done", 13: "finish: start", 14: "stats: ticket taken", 15: "stats: partials re-read"}
+lab = {0: "entry", 1: "w-ring armed", 2: "dep wait over", 3: "first operand", 4: "last MMA / loop end", 5: "flag seen/raised", 6: "split-K landed", 7: "exit", 8: "ring free (all ranks)", 9: "partials sent", 10: "epilogue loop done", 11: "producer thread done", 12: "MMA thread done", 13: "finish: start", 14: "stats: ticket taken", 15: "stats: partials re-read"}
 base = used[PL * a.layer]
 origin = t[base, :, 0][t[base, :, 0] > 0].min()
 out.append(f"layer {a.layer}: us relative to the first CTA of its qkv launch entering; per stamp: min / median / max over CTAs (count)")
