@@ -30,11 +30,12 @@ namespace crab {
 static constexpr int SK_BM = 128;   // weight rows per tile
 static constexpr int SK_MB = 32;    // batch columns (UMMA N)
 static constexpr int SK_BK = 64;
-static constexpr int SK_STAGES = 5;  // 100 KB ring: two CTAs per SM
+static constexpr int SK_STAGES = 4;  // 80 KB ring + 18 KB receive area: two CTAs per SM
 static constexpr int SK_W_BYTES = SK_BM * SK_BK * 2;
 static constexpr int SK_X_BYTES = SK_MB * SK_BK * 2;
 static constexpr int SK_STAGE_BYTES = SK_W_BYTES + SK_X_BYTES;
-static constexpr int SK_SMEM = SK_STAGES * SK_STAGE_BYTES + 1024 + 256;
+static constexpr int SK_PART_BYTES = 20 * 1024;   // receive area of the split-K reduce-scatter: [src rank][rows per rank][36 floats]; S * R <= 140 rows (S = 7)
+static constexpr int SK_SMEM = SK_STAGES * SK_STAGE_BYTES + SK_PART_BYTES + 1024 + 256;
 static constexpr int SK_THREADS = 192;
 static constexpr int SK_MAX_SPLIT = 8;  // portable cluster size
 static constexpr int SK_PSTRIDE = 36;   // floats per partial row in smem (32 + pad, keeps 16-byte alignment)
@@ -104,6 +105,11 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t ran
 __device__ __forceinline__ void st_async_f4(uint32_t remote_addr, uint32_t remote_bar, float a, float b, float c, float d) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr),
                "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar) : "memory");
+}
+// smem -> smem of another CTA of the cluster, bytes reported to an mbarrier of the destination CTA (one transaction per call)
+__device__ __forceinline__ void bulk_copy_to_rank(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(remote_dst),
+               "r"(local_src), "r"(bytes), "r"(remote_bar) : "memory");
 }
 __device__ __forceinline__ void st_async_f1(uint32_t remote_addr, uint32_t remote_bar, float a) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(remote_addr), "f"(a), "r"(remote_bar) : "memory");
@@ -184,13 +190,15 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
                            const __grid_constant__ CUtensorMap tmap_z, const SkinnyParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + SK_STAGES * SK_STAGE_BYTES;
+  const uint32_t part_base = smem_base + SK_STAGES * SK_STAGE_BYTES;   // dedicated receive area: peers may write it while the ring still streams
+  const uint32_t bar_base = part_base + SK_PART_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (SK_STAGES + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * SK_STAGES);
   const uint32_t tmem_slot = bar_base + 8u * (2 * SK_STAGES + 1);
   const uint32_t rfree_bar = bar_base + 8u * (2 * SK_STAGES + 2);   // one arrival per rank of the cluster: "my MMAs are done, my ring may be overwritten"
   const uint32_t pfull_bar = bar_base + 8u * (2 * SK_STAGES + 3);   // bytes of the partials this CTA receives
+  const uint32_t sent_bar = bar_base + 8u * (2 * SK_STAGES + 4);    // one arrival per rank: "your partials have arrived here" (source smem may go)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) trace_stamp(p.trace, 0);
@@ -217,12 +225,13 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
     mbar_init(tfull_bar, 1);
     mbar_init(rfree_bar, (uint32_t)S);
     mbar_init(pfull_bar, 1);
+    mbar_init(sent_bar, (uint32_t)S);
     fence_barrier_init();
     // partials this CTA will receive: a weight tile's rank gets its rows from all S ranks (128 B each), rank 0 of a statistics
     // cluster gets the router/A dot rows and the 32 diagonal elements of x x^T from all S ranks
     const int rpr = p.rows_per_rank;
     const int rows_mine = max(0, min(rpr, SK_BM - rank * rpr));
-    const uint32_t expect = S == 1 ? 0u : is_stats ? (rank == 0 ? (uint32_t)S * (SK_SROWS * 128u + 32u * 4u) : 0u) : (uint32_t)(S * rows_mine) * 128u;
+    const uint32_t expect = S == 1 ? 0u : is_stats ? (rank == 0 ? (uint32_t)S * (SK_SROWS * 128u + 32u * 4u) : 0u) : (uint32_t)(S * rows_mine) * (SK_PSTRIDE * 4u);
     if (expect) mbar_arrive_expect_tx(pfull_bar, expect);
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 32); tmem_relinquish(); }
@@ -515,40 +524,43 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
         for (int b = 0; b < 32; ++b) r[b] = __float_as_uint(__uint_as_float(r[b]) + bias_v);
       }
     }
-    // Ring free: every rank tells every rank that its MMAs are done (its epilogue passed tfull), so its TMA ring is idle and can
-    // hold partials.  Layout in the owner's smem: [src rank][row in group][SK_PSTRIDE].  The partials travel as st.async stores
-    // that report their bytes to the owner's pfull barrier: no cluster barrier, no fence.
+    // Reduce-scatter: every thread parks its tile row (32 floats) in this CTA's own ring — idle, its MMAs are done — and one lane
+    // per warp sends the rows as bulk shared-to-shared copies into the owners' dedicated receive areas ([src rank][row in group]
+    // [SK_PSTRIDE]); the copies report their bytes to the owner's pfull barrier.  No cluster barrier, no fence, no handshake before
+    // the send (nobody streams into a receive area), one mbarrier update per copy instead of one per 16 bytes.
     if (epi) {
-      if (S > 1) {
-        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-        if (warp == 2 && lane < S) mbar_arrive_remote_relaxed(map_to_rank(rfree_bar, (uint32_t)lane));
-        mbar_wait(rfree_bar, 0);
-      }
+      const uint32_t stage_row = smem_base + (uint32_t)(row * SK_PSTRIDE * 4);
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + g * 16), "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]),
+                     "r"(r[4 * g + 3]) : "memory");
       if (threadIdx.x == 64) trace_stamp(p.trace, 8);
-      const int dst_rank = (S > 1) ? row / R : 0;
-      const int row_in = row - dst_rank * R;
-      const uint32_t local = smem_base + (uint32_t)((rank * R + row_in) * SK_PSTRIDE * 4);
       if (S > 1) {
-        const uint32_t remote = map_to_rank(local, (uint32_t)dst_rank);
-        const uint32_t rbar = map_to_rank(pfull_bar, (uint32_t)dst_rank);
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          st_async_f4(remote + g * 16, rbar, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
-                      __uint_as_float(r[4 * g + 3]));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores above -> async-proxy reads of the copies
+        __syncwarp();
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");     // the peers' barriers are initialised (arrive: prologue)
+        if (lane == 0) {
+          const int r0 = quarter * 32;
+          for (int d = r0 / R; d * R < r0 + 32 && d < S; ++d) {   // destination ranks of this warp's 32 rows
+            const int ra = max(r0, d * R), rb = min(r0 + 32, (d + 1) * R);
+            bulk_copy_to_rank(map_to_rank(part_base + (uint32_t)((rank * R + (ra - d * R)) * SK_PSTRIDE * 4), (uint32_t)d),
+                              smem_base + (uint32_t)(ra * SK_PSTRIDE * 4), (uint32_t)((rb - ra) * SK_PSTRIDE * 4),
+                              map_to_rank(pfull_bar, (uint32_t)d));
+          }
+        }
+        if (threadIdx.x == 64) trace_stamp(p.trace, 9);
+        mbar_wait(pfull_bar, 0);   // all partials of this rank's rows have landed
+        // tell every sender that its rows are here: a CTA may exit (and its ring be reused) only after its copies were read
+        if (warp == 2 && lane < S) mbar_arrive_remote_relaxed(map_to_rank(sent_bar, (uint32_t)lane));
       } else {
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(local + g * 16), "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]),
-                       "r"(r[4 * g + 3]) : "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      if (threadIdx.x == 64) trace_stamp(p.trace, 9);
-      if (S > 1) mbar_wait(pfull_bar, 0);   // all partials of this rank's rows have landed
-      else asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) trace_stamp(p.trace, 6);
     }
     if (epi) {
       const int tt = (warp - 2) * 32 + lane;
-      const float* part = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+      // S == 1: the parked rows are the result; S > 1: the receive area
+      const float* part = reinterpret_cast<const float*>(smem_raw + ((S > 1 ? part_base : smem_base) - smem_u32(smem_raw)));
       if (S == 1) sk_finish_split<1>(p, part, tt, tile, rank);
       else if (S == 2) sk_finish_split<2>(p, part, tt, tile, rank);
       else if (S == 4) sk_finish_split<4>(p, part, tt, tile, rank);
@@ -585,6 +597,7 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
       }
     }
   }
+  if (S > 1 && !is_stats && threadIdx.x == 64) mbar_wait(sent_bar, 0);   // every owner has received this CTA's rows
   if (threadIdx.x == 64) trace_stamp(p.trace, 10);
   if (threadIdx.x == 0) trace_stamp(p.trace, 11);
   if (threadIdx.x == 32) trace_stamp(p.trace, 12);
