@@ -51,6 +51,9 @@ struct FlashParams {
   const float* gate;   // [B, H, Sq] or null
   const float* table;  // [H, Sq, Sk] or null   (bias = gate * table)
   const int* sk_dev;   // null, or the number of keys in device memory (overrides Sk)
+  int sk_add;          // added to *sk_dev (decode: *past_dev + 1 keys)
+  int nsplit;          // > 1: split-KV (Sq <= 64 only): blockIdx.x = split, partial states -> ws, attn_decode_combine_kernel finishes
+  float* ws;           // [(b * H * Sq + h * Sq + row) * nsplit + split][HD + 2]: un-normalised acc, running max (log2 domain), sum
 };
 
 template <int HD, int MT>
@@ -86,13 +89,14 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
   const uint32_t sK0 = sQ + MT * Cfg::TILE_BYTES;
   const uint32_t sV0 = sK0 + 2 * Cfg::TILE_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int split = p.nsplit > 1 ? (int)blockIdx.x : 0;
+  const int m_blk = p.nsplit > 1 ? 0 : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int kvh = h / (p.H / p.KVH);
   const int q0 = m_blk * Cfg::BM;
   const __nv_bfloat16* qg = p.q + b * p.q_bs + h * p.q_hs;
   const __nv_bfloat16* kg = p.k + b * p.k_bs + kvh * p.k_hs;
   const __nv_bfloat16* vg = p.v + b * p.v_bs + kvh * p.v_hs;
-  const int Sk = p.sk_dev ? *p.sk_dev : p.Sk;
+  const int Sk = p.sk_dev ? *p.sk_dev + p.sk_add : p.Sk;
   const int off = Sk - p.Sq;  // causal: key j visible to query i iff j <= i + off
   int n_tiles = (Sk + Cfg::BN - 1) / Cfg::BN;
   if (p.causal) {
@@ -100,10 +104,17 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
     n_tiles = min(n_tiles, last_key / Cfg::BN + 1);
   }
 
+  // split-KV: this block walks key tiles [t_begin, t_end)
+  int t_begin = 0, t_end = n_tiles;
+  if (p.nsplit > 1) {
+    const int per = (n_tiles + p.nsplit - 1) / p.nsplit;
+    t_begin = min(n_tiles, split * per);
+    t_end = min(n_tiles, t_begin + per);
+  }
 #pragma unroll
   for (int t = 0; t < MT; ++t) load_tile<HD>(sQ + t * Cfg::TILE_BYTES, qg, p.q_rs, q0 + t * 64, p.Sq);
-  load_tile<HD>(sK0, kg, p.k_rs, 0, Sk);
-  load_tile<HD>(sV0, vg, p.v_rs, 0, Sk);
+  load_tile<HD>(sK0, kg, p.k_rs, t_begin * Cfg::BN, Sk);
+  load_tile<HD>(sV0, vg, p.v_rs, t_begin * Cfg::BN, Sk);
   cp_async_commit();
 
   constexpr int DT = HD / 8;  // output n8-tiles per row
@@ -125,10 +136,12 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
     }
   }
   const float sl2 = p.scale * 1.4426950408889634f;
+  const bool warp_active = q0 + warp * MT * 16 < p.Sq;
 
-  for (int t = 0; t < n_tiles; ++t) {
-    const int buf = t & 1;
-    if (t + 1 < n_tiles) {
+  if (t_begin >= t_end) cp_async_wait<0>();   // empty split: nothing to consume
+  for (int t = t_begin; t < t_end; ++t) {
+    const int buf = (t - t_begin) & 1;
+    if (t + 1 < t_end) {
       load_tile<HD>(sK0 + (buf ^ 1) * Cfg::TILE_BYTES, kg, p.k_rs, (t + 1) * Cfg::BN, Sk);
       load_tile<HD>(sV0 + (buf ^ 1) * Cfg::TILE_BYTES, vg, p.v_rs, (t + 1) * Cfg::BN, Sk);
       cp_async_commit();
@@ -139,6 +152,9 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
     __syncthreads();
     const uint32_t sK = sK0 + buf * Cfg::TILE_BYTES, sV = sV0 + buf * Cfg::TILE_BYTES;
 
+    // a warp whose query rows all lie past Sq (decode over a kv group: Sq = G <= 16 rows, three of the four warps) only helps
+    // with the loads: its MMAs / softmax would be work on padding that competes with the one useful warp for the tensor pipe
+    if (warp_active) {
     // ---- S = Q K^T  (MT x 16 x 64 per warp) ----
     float s[MT][8][4];
 #pragma unroll
@@ -276,10 +292,36 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
         }
       }
     }
+    }   // warp_active
     __syncthreads();
   }
 
   // ---- finalise ----
+  if (p.nsplit > 1) {
+    // partial state of this key range -> workspace (one row per query row, i.e. per q head of the kv group in GQA decode)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        l_run[mt][hi] += __shfl_xor_sync(0xffffffffu, l_run[mt][hi], 1);
+        l_run[mt][hi] += __shfl_xor_sync(0xffffffffu, l_run[mt][hi], 2);
+      }
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        const int row = r_lo[mt] + 8 * hi;
+        if (row < p.Sq) {
+          float* w = p.ws + ((((size_t)b * p.H + h) * p.Sq + row) * p.nsplit + split) * (HD + 2);
+#pragma unroll
+          for (int i = 0; i < DT; ++i) {
+            const int col = i * 8 + (lane & 3) * 2;
+            *reinterpret_cast<float2*>(w + col) = make_float2(o_acc[mt][i][2 * hi], o_acc[mt][i][2 * hi + 1]);
+          }
+          if ((lane & 3) == 0) { w[HD] = m_run[mt][hi]; w[HD + 1] = l_run[mt][hi]; }
+        }
+      }
+    }
+    return;
+  }
   __nv_bfloat16* og = p.o + b * p.o_bs + h * p.o_hs;
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
@@ -658,6 +700,7 @@ extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
   p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
   p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.Sq = a->Sq; p.Sk = a->Sk;
   p.scale = a->scale; p.causal = a->causal; p.gate = a->gate; p.table = a->bias_table; p.sk_dev = a->sk_dev;
+  p.sk_add = 0; p.nsplit = 1; p.ws = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   {  // head_dim 128 without a bias table and with TMA-describable strides: the tcgen05 / TMEM kernel (flash_tcgen05.cu)
     const int rc = a->sk_dev ? -1 : flash_attn_tcgen05_try(a, st);
@@ -669,11 +712,10 @@ extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
   const bool big = a->Sq >= 512;  // N=257 (CLIP) wastes less with 64-row blocks (5 x 64 vs 3 x 128 row slots)
 #define CRAB_FLASH_LAUNCH(HD_, MT_)                                                                                        \
   {                                                                                                                        \
-    static bool set = false;                                                                                               \
-    if (!set) {                                                                                                            \
+    static DeviceOnce set;                                                                                                 \
+    if (first_on_device(set)) {                                                                                            \
       CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                            FlashCfg<HD_, MT_>::SMEM));                                                     \
-      set = true;                                                                                                          \
     }                                                                                                                      \
     dim3 grid((a->Sq + FlashCfg<HD_, MT_>::BM - 1) / FlashCfg<HD_, MT_>::BM, a->H, a->B);                                  \
     flash_attn_kernel<HD_, MT_><<<grid, 128, FlashCfg<HD_, MT_>::SMEM, st>>>(p);                                           \
@@ -743,6 +785,39 @@ extern "C" int crab_attn_decode_fused(const crab_decode_fused_args* a, void* str
                  "crab_attn_decode_fused: LoRA pre-pass needs z, workspace [B*KVH*11] floats ([B*H*11] when nsplit > 1) and counters [B] ints");
   }
   const int G = a->H / a->KVH;
+  if (a->gqa_tensor_cores) {
+    // Grouped-query decode on tensor cores: the G query heads of a kv group are the Sq = G rows of one flash-attention problem
+    // (q row stride = head_dim), the key count is *past_dev + 1; RoPE + cache append run as their own launch.  With nsplit > 1
+    // every (b, kv head) is split over nsplit blocks (128 problems alone cannot keep HBM busy: 32 KB in flight each) and the
+    // combine launch finishes — and does the o_proj pre-pass.
+    CRAB_REQUIRE(a->head_dim == 128 && G >= 1 && G <= 64, "crab_attn_decode_fused: gqa_tensor_cores needs head_dim 128 and a group of <= 64 heads");
+    CRAB_REQUIRE(!a->lora_ra || a->nsplit > 1, "crab_attn_decode_fused: with gqa_tensor_cores the LoRA pre-pass runs in the combine launch (nsplit > 1)");
+    int rc = crab_rope_kv_append(const_cast<void*>(a->qkv), a->ldq, a->cos_sin, a->k_cache, a->v_cache, a->B, 1, a->H, a->KVH, a->head_dim,
+                                 a->ctx_max, a->past_dev, 0, stream);
+    if (rc != CRAB_OK) return rc;
+    FlashParams fp;
+    fp.q = (const __nv_bfloat16*)a->qkv; fp.k = (const __nv_bfloat16*)a->k_cache; fp.v = (const __nv_bfloat16*)a->v_cache; fp.o = (__nv_bfloat16*)a->o;
+    fp.q_bs = a->ldq; fp.q_rs = a->head_dim; fp.q_hs = (long long)G * a->head_dim;
+    fp.k_bs = (long long)a->KVH * a->ctx_max * a->head_dim; fp.k_rs = a->head_dim; fp.k_hs = (long long)a->ctx_max * a->head_dim;
+    fp.v_bs = fp.k_bs; fp.v_rs = fp.k_rs; fp.v_hs = fp.k_hs;
+    fp.o_bs = a->ldo; fp.o_rs = a->head_dim; fp.o_hs = (long long)G * a->head_dim;
+    fp.B = a->B; fp.H = a->KVH; fp.KVH = a->KVH; fp.Sq = G; fp.Sk = a->ctx_max;
+    fp.scale = a->scale; fp.causal = 0; fp.gate = nullptr; fp.table = nullptr; fp.sk_dev = a->past_dev; fp.sk_add = 1;
+    fp.nsplit = a->nsplit; fp.ws = a->workspace;
+    static DeviceOnce fset;
+    if (first_on_device(fset))
+      CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlashCfg<128, 1>::SMEM));
+    cudaStream_t st2 = (cudaStream_t)stream;
+    flash_attn_kernel<128, 1><<<dim3((unsigned)a->nsplit, (unsigned)a->KVH, (unsigned)a->B), 128, FlashCfg<128, 1>::SMEM, st2>>>(fp);
+    CRAB_CHECK_CUDA(cudaGetLastError());
+    if (a->nsplit > 1) {
+      cudaError_t e2 = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<128>, dim3(a->B * a->H), dim3(128), 0, st2, (const float*)a->workspace,
+                                  (__nv_bfloat16*)a->o, a->ldo, a->H, a->nsplit, (const __nv_bfloat16*)a->lora_ra, a->ld_ra,
+                                  (__nv_bfloat16*)a->lora_z, a->ld_z, a->lora_scale, a->lora_ws, a->lora_counters);
+      CRAB_CHECK_CUDA(e2);
+    }
+    return CRAB_OK;
+  }
   DecodeParams p;
   p.q = (const __nv_bfloat16*)a->qkv; p.ldq = a->ldq; p.kc = (const __nv_bfloat16*)a->k_cache; p.vc = (const __nv_bfloat16*)a->v_cache;
   p.o = (__nv_bfloat16*)a->o; p.ldo = a->ldo; p.ws = a->workspace; p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.ctx_max = a->ctx_max;

@@ -138,7 +138,7 @@ __device__ __forceinline__ void sk_finish_split(const SkinnyParams& p, const flo
     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)b0 * p.ldc + n;
     const int mlim = (n < (p.N >> 1)) ? p.M : 0;
     const size_t cstep = (size_t)BSTEP * p.ldc;
-#pragma unroll 1
+#pragma unroll 2
     for (int b = b0; b < 32; b += BSTEP) {
       float g = 0.f, u = 0.f;
 #pragma unroll
@@ -160,7 +160,7 @@ __device__ __forceinline__ void sk_finish_split(const SkinnyParams& p, const flo
     if (p.out_dtype == CRAB_BF16) {
       __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)b0 * p.ldc + n;
       const size_t cstep = (size_t)BSTEP * p.ldc;
-#pragma unroll 1
+#pragma unroll 2
       for (int b = b0; b < 32; b += BSTEP) {
         float a = 0.f;
 #pragma unroll
@@ -172,7 +172,7 @@ __device__ __forceinline__ void sk_finish_split(const SkinnyParams& p, const flo
     } else {
       float* cp = reinterpret_cast<float*>(p.C) + (size_t)b0 * p.ldc + n;
       const size_t cstep = (size_t)BSTEP * p.ldc;
-#pragma unroll 1
+#pragma unroll 2
       for (int b = b0; b < 32; b += BSTEP) {
         float a = 0.f;
 #pragma unroll

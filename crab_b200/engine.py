@@ -821,7 +821,7 @@ class CrabEngine:
         G = H // KV
         gqa_tc = G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
         fused = self.fuse_decode_attn and not gqa_tc
-        o_fused_lora = lo and fused     # the attention (or its split-KV combine) kernel writes o_proj's z columns into at[:, nq:]
+        o_fused_lora = lo and (fused or (gqa_tc and nsplit > 1))     # the attention (or its split-KV combine) kernel writes o_proj's z columns into at[:, nq:]
         self._dec_mode = (fused, gqa_tc, o_fused_lora)
 
         def qkv_phase(L):
@@ -856,14 +856,14 @@ class CrabEngine:
         ctx = self.cfg.max_ctx
         L = self.layers[li]
         if gqa_tc:
-            # grouped-query decode with enough (batch x kv-head) problems to fill the SMs: the G query heads of a kv
-            # group are the Sq = G "rows" of one flash-attention problem, so QK^T / PV run on tensor cores
-            G = H // KV
-            ops.rope_kv_append(qkv, self.rope, self.k_cache[li], self.v_cache[li], B, 1, H, KV, hd, past=0, past_dev=self.past_dev)
-            ops.flash_attn(qkv, self.k_cache[li], self.v_cache[li], at, B=B, H=KV, KVH=KV, Sq=G, Sk=ctx, head_dim=hd,
-                           q_strides=(nq + 2 * nk, hd, G * hd), k_strides=(KV * ctx * hd, hd, ctx * hd),
-                           v_strides=(KV * ctx * hd, hd, ctx * hd), o_strides=(nq + self.EXT_O, hd, G * hd),
-                           scale=1 / math.sqrt(hd), sk_dev=self.len_dev)
+            # grouped-query decode: the G query heads of a kv group are the Sq = G "rows" of one flash-attention problem, so QK^T / PV run
+            # on tensor cores; B x KVH problems alone keep only 32 KB each in flight, so the keys are split over nsplit blocks and the
+            # combine launch finishes (and does the o_proj LoRA pre-pass when o_fused_lora)
+            ops.attn_decode_fused(qkv, self.rope, self.k_cache[li], self.v_cache[li], at[:, :nq], B=B, H=H, KVH=KV, head_dim=hd,
+                                  scale=1 / math.sqrt(hd), past_dev=self.past_dev, nsplit=nsplit, workspace=ws, gqa_tc=True,
+                                  ra=L["ra_o"] if o_fused_lora else None, z=at[:, nq:] if o_fused_lora else None, lora_scale=self.scaling,
+                                  lora_ws=self._buf("dec_lora_ws", (B * H * 11,), torch.float32) if o_fused_lora else None,
+                                  lora_counters=self._buf("dec_lora_cnt", (B,), torch.int32, zero=True) if o_fused_lora else None)
         elif fused:
             # one launch: RoPE on q / new k, cache append, attention over past + 1 keys, and (nsplit == 1) the o_proj
             # LoRA pre-pass whose z columns land in at[:, nq:]
@@ -894,7 +894,7 @@ class CrabEngine:
         G = H // KV
         gqa_tc = G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
         fused = self.fuse_decode_attn and not gqa_tc
-        o_fused_lora = lo and fused     # the attention (or its split-KV combine) kernel writes o_proj's z columns into at[:, nq:]
+        o_fused_lora = lo and (fused or (gqa_tc and nsplit > 1))     # the attention (or its split-KV combine) kernel writes o_proj's z columns into at[:, nq:]
         o_stats = lo and not o_fused_lora
         head_fused = B <= 32 and self.lm_head_p is None and self.lm_head_c is not None
         fslot = self._flag_ring(len(self.layers) * (2 + int(o_stats) + int(lo)) + int(head_fused))
@@ -950,7 +950,7 @@ class CrabEngine:
         G = H // KV
         gqa_tc = G > 1 and hd == 128 and B * KV >= 64 and self.gqa_decode_tc
         fused = self.fuse_decode_attn and not gqa_tc
-        o_fused_lora = lo and fused
+        o_fused_lora = lo and (fused or (gqa_tc and nsplit > 1))
         ops.set_pdl(self.pdl_chain)
         try:
             ops.gather_rows(self.embed, x, B, D, src_rows=self.next_ids)
@@ -1019,7 +1019,7 @@ class CrabEngine:
         finally:
             ops.set_pdl(0)  # prefill / encoder launches are never PDL launches
 
-    def begin_decode(self, B: int, use_graph: bool = True):
+    def begin_decode(self, B: int, use_graph: bool = True, max_len: Optional[int] = None):
         """Prepare the decode loop after a prefill.  With `use_graph`, one decode step (all layers + head + arg-max +
         position bump) is captured in a CUDA graph ONCE per (batch, buffers) and replayed every step of every later
         request: the context length lives in device memory (`past_dev`, `len_dev`), so nothing in the graph changes."""
@@ -1031,10 +1031,19 @@ class CrabEngine:
         self.len_dev.fill_(self.cur_len + 1)
         blocks = B * c.kv_heads
         nsplit = 1 if blocks >= 2 * 148 else max(1, min(16, (2 * 148 + blocks - 1) // blocks))
+        G = c.heads // c.kv_heads
+        if G > 1 and c.head_dim == 128 and blocks >= 64 and self.gqa_decode_tc:
+            # tensor-core GQA decode: two 80 KB blocks per SM — keep all splits in one wave (3 x 128 blocks = a second wave: 30 us vs 18)
+            nsplit = max(1, min(8, (2 * 148) // blocks))
+            nsplit = int(os.environ.get("CRAB_GQA_NSPLIT", nsplit))
+        if max_len is not None:
+            # a split needs keys to be worth its combine launch (~8 us per layer at bs 1): at least 256 keys per split over the longest
+            # context this request can reach.  bs 1 with a 64-token prompt + 128 new tokens: one launch per layer instead of two
+            nsplit = min(nsplit, max(1, -(-int(max_len) // 256)))
         ws = self._buf("dec_ws", (B * c.heads * nsplit * (c.head_dim + 2),), torch.float32) if nsplit > 1 else None
         self._dec_args = (B, nsplit, ws)
         self._use_graph = use_graph
-        if use_graph and (self._graph is None or self._graph_bs != B):
+        if use_graph and (self._graph is None or self._graph_bs != (B, nsplit)):
             s = torch.cuda.Stream(device=self.dev)
             s.wait_stream(torch.cuda.current_stream())
             saved = (self.next_ids.clone(), self.past_dev.clone(), self.len_dev.clone())
@@ -1050,7 +1059,7 @@ class CrabEngine:
             self._graph_kernels = ops.launch_count() - n0
             ops.count_launches(-self._graph_kernels)  # capture launches nothing
             self.next_ids.copy_(saved[0]); self.past_dev.copy_(saved[1]); self.len_dev.copy_(saved[2])
-            self._graph, self._graph_bs = g, B
+            self._graph, self._graph_bs = g, (B, nsplit)
 
     begin_decode_cached = begin_decode
 
@@ -1099,7 +1108,7 @@ class CrabEngine:
         all_logits = [logits.clone()] if return_logits else None
         steps_h = []
         if max_new_tokens > 1:
-            self.begin_decode(B, use_graph and self.dev.type == "cuda")
+            self.begin_decode(B, use_graph and self.dev.type == "cuda", max_len=S + max_new_tokens)
         steps = max_new_tokens
         for step in range(max_new_tokens):
             if eos is None:

@@ -119,4 +119,5 @@ class DecodeFusedArgs(C.Structure):
         ("nsplit", C.c_int32), ("past_dev", C.c_void_p), ("scale", C.c_float),
         ("lora_ra", C.c_void_p), ("ld_ra", C.c_int32), ("lora_z", C.c_void_p), ("ld_z", C.c_int32),
         ("lora_scale", C.c_float), ("lora_ws", C.c_void_p), ("lora_counters", C.c_void_p),
+        ("gqa_tensor_cores", C.c_int32), ("reserved0", C.c_int32),
     ]

@@ -262,7 +262,7 @@ def attn_decode_fused(qkv: torch.Tensor, rope: torch.Tensor, k_cache: torch.Tens
                       B: int, H: int, KVH: int, head_dim: int, scale: float, past_dev: torch.Tensor, nsplit: int = 1,
                       workspace: Optional[torch.Tensor] = None, ra: Optional[torch.Tensor] = None,
                       z: Optional[torch.Tensor] = None, lora_scale: float = 0.0, lora_ws: Optional[torch.Tensor] = None,
-                      lora_counters: Optional[torch.Tensor] = None):
+                      lora_counters: Optional[torch.Tensor] = None, gqa_tc: bool = False):
     """Decode-step attention with RoPE + KV append (+ the o_proj hyper-LoRA pre-pass) fused in: `qkv` is the RAW output
     of the qkv projection; the caches are appended at *past_dev; z (24 columns) is written when `ra` is given."""
     _req_cuda(qkv, rope, k_cache, v_cache, out, past_dev, workspace, ra, z, lora_ws, lora_counters)
@@ -279,10 +279,10 @@ def attn_decode_fused(qkv: torch.Tensor, rope: torch.Tensor, k_cache: torch.Tens
         o=out.data_ptr(), ldo=out.stride(0), workspace=_ptr(workspace), B=B, H=H, KVH=KVH, head_dim=head_dim,
         ctx_max=k_cache.shape[2], nsplit=nsplit, past_dev=past_dev.data_ptr(), scale=scale,
         lora_ra=_ptr(ra), ld_ra=ra.stride(0) if ra is not None else 0, lora_z=_ptr(z), ld_z=z.stride(0) if z is not None else 0,
-        lora_scale=lora_scale, lora_ws=_ptr(lora_ws), lora_counters=_ptr(lora_counters))
+        lora_scale=lora_scale, lora_ws=_ptr(lora_ws), lora_counters=_ptr(lora_counters), gqa_tensor_cores=1 if gqa_tc else 0, reserved0=0)
     with _timed("crab_attn_decode_fused"):
         _l.check(_l.load().crab_attn_decode_fused(C.byref(a), _stream()), "crab_attn_decode_fused")
-    count_launches(2 if nsplit > 1 else 1)
+    count_launches((2 if nsplit > 1 else 1) + (1 if gqa_tc else 0))
     return out
 
 

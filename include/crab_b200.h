@@ -155,6 +155,10 @@ typedef struct crab_decode_fused_args {
   void* lora_z; int32_t ld_z;             /* bf16 [B, ld_z] */
   float lora_scale;
   float* lora_ws; int* lora_counters;
+  /* != 0 (head_dim 128, grouped-query models): RoPE + append as one launch, then the G query heads of a kv group as the G rows of a
+   * tensor-core flash-attention problem, split over nsplit key ranges, then the combine launch (which also does the o_proj pre-pass:
+   * lora_ra needs nsplit > 1 here).  workspace: B * H * nsplit * (head_dim + 2) floats. */
+  int32_t gqa_tensor_cores; int32_t reserved0;
 } crab_decode_fused_args;
 int crab_attn_decode_fused(const crab_decode_fused_args* args, void* stream);
 

@@ -267,7 +267,7 @@ def row_norm_loraz(x, *, gamma=None, eps=0.0, y=None, ra=None, groups=0, z=None,
 
 
 def attn_decode_fused(qkv, rope, k_cache, v_cache, out, *, B, H, KVH, head_dim, scale, past_dev, nsplit=1, workspace=None,
-                      ra=None, z=None, lora_scale=0.0, lora_ws=None, lora_counters=None):
+                      ra=None, z=None, lora_scale=0.0, lora_ws=None, lora_counters=None, gqa_tc=False):
     hd, past = head_dim, int(past_dev[0])
     G = H // KVH
     for b in range(B):

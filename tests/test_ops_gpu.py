@@ -205,6 +205,44 @@ def test_attn_decode_fused_equals_the_three_kernel_sequence(cuda_dev, B, H, KVH,
             assert o2[:, nq + 24:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("B,H,KVH,past,nsplit,lora", [(32, 28, 4, 1150, 3, True), (16, 32, 8, 77, 2, True), (20, 28, 4, 63, 4, False),
+                                                      (16, 28, 4, 0, 3, True), (32, 28, 4, 700, 1, False)])
+def test_gqa_decode_split_kv_on_tensor_cores(cuda_dev, B, H, KVH, past, nsplit, lora):
+    """crab_attn_decode_fused(gqa_tensor_cores): RoPE + append, the G heads of a kv group as the rows of a flash problem split over
+    nsplit key ranges, combine (+ o_proj LoRA pre-pass) — against rope_kv_append -> scalar attn_decode -> row_norm_loraz."""
+    from crab_b200 import ops
+
+    hd, ctx = 128, 1280
+    g = _g(B * 11 + H + past + nsplit)
+    nq = H * hd
+    qkv = torch.randn(B, (H + 2 * KVH) * hd, generator=g).to(torch.bfloat16).to(cuda_dev)
+    kc = torch.randn(B, KVH, ctx, hd, generator=g).to(torch.bfloat16).to(cuda_dev)
+    vc = torch.randn(B, KVH, ctx, hd, generator=g).to(torch.bfloat16).to(cuda_dev)
+    ra = (torch.randn(11, nq, generator=g) / math.sqrt(nq)).to(torch.bfloat16).to(cuda_dev)
+    rope = ops.rope_table(ctx, hd, 1e6, cuda_dev)
+    pd = torch.tensor([past], dtype=torch.int32, device=cuda_dev)
+    ld = torch.tensor([past + 1], dtype=torch.int32, device=cuda_dev)
+    q1, k1, v1 = qkv.clone(), kc.clone(), vc.clone()
+    o1 = torch.zeros(B, nq + 32, dtype=torch.bfloat16, device=cuda_dev)
+    ops.rope_kv_append(q1, rope, k1, v1, B, 1, H, KVH, hd, past=0, past_dev=pd)
+    ops.attn_decode(q1, k1, v1, o1[:, :nq], B=B, H=H, KVH=KVH, head_dim=hd, scale=hd ** -0.5, len_dev=ld)
+    if lora:
+        ops.row_norm_loraz(o1[:, :nq], ra=ra, groups=1, z=o1[:, nq:], scale=2.0)
+    q2, k2, v2 = qkv.clone(), kc.clone(), vc.clone()
+    o2 = torch.zeros(B, nq + 32, dtype=torch.bfloat16, device=cuda_dev)
+    ws = torch.empty(B * H * 11, dtype=torch.float32, device=cuda_dev)
+    cnt = torch.zeros(B, dtype=torch.int32, device=cuda_dev)
+    ops.attn_decode_fused(q2, rope, k2, v2, o2[:, :nq], B=B, H=H, KVH=KVH, head_dim=hd, scale=hd ** -0.5, past_dev=pd, nsplit=nsplit,
+                          gqa_tc=True, ra=ra if lora else None, z=o2[:, nq:] if lora else None, lora_scale=2.0,
+                          lora_ws=ws if lora else None, lora_counters=cnt if lora else None)
+    torch.cuda.synchronize()
+    assert torch.equal(k2, k1) and torch.equal(v2, v1) and torch.equal(q2, q1)     # RoPE + append in place, as the separate launch
+    _close(o2[:, :nq], o1[:, :nq], 1.5e-2)   # P is rounded to bf16 before PV on the tensor-core path
+    assert int(cnt.abs().sum()) == 0
+    if lora:
+        _close(o2[:, nq:nq + 24], o1[:, nq:nq + 24], 3e-2)
+
+
 @pytest.mark.parametrize("B,H,KVH,length", [(32, 28, 4, 1150), (16, 32, 8, 77), (20, 8, 4, 64), (16, 28, 4, 1)])
 def test_gqa_decode_on_tensor_cores(cuda_dev, B, H, KVH, length):
     """Grouped-query decode as a flash-attention problem (the G heads of a kv group = the query rows; key count read from
