@@ -280,8 +280,7 @@ def attn_decode_fused(qkv, rope, k_cache, v_cache, out, *, B, H, KVH, head_dim, 
         vv = v_cache[b, :, : past + 1].float().repeat_interleave(G, 0)
         a = torch.softmax((q.unsqueeze(1) @ kk.transpose(-1, -2)) * scale, -1) @ vv      # (H, 1, hd)
         out[b, : H * hd] = a.reshape(-1).to(torch.bfloat16)
-    if ra is not None:
-        assert nsplit == 1
+    if ra is not None:   # unsplit: in the attention launch; split KV: in the combine launch — same arithmetic
         z[:, :24] = _lora_rows(out[:, : H * hd], ra, 1, lora_scale).to(torch.bfloat16)
     return out
 
