@@ -288,6 +288,36 @@ def test_fused_skinny_stats_clusters_and_flag_ring(cuda_dev, clusters):
     assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 
+def test_debug_trace_stamps_are_ordered(cuda_dev):
+    """crab_debug_trace: every CTA of a traced launch stamps entry <= dependency wait <= first operand <= last MMA <= exit, the
+    result is the untraced launch's bit for bit, and a disarmed library writes nothing."""
+    import ctypes as C
+    from crab_b200 import lib, ops
+
+    lin = Lin(cuda_dev, 81, 4096, [4096], lora=False)
+    x = mk((32, 4096), cuda_dev, 82, 1.0).to(torch.bfloat16)
+    ref = ops.gemm_skinny(x, lin.packed, splits=4)
+    L = lib.load()
+    L.crab_debug_trace.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.crab_debug_trace.restype = C.c_int
+    buf = torch.zeros(2 * 256 * 16, dtype=torch.int64, device=cuda_dev)
+    assert L.crab_debug_trace(C.c_void_p(buf.data_ptr()), 2, 256) == 0
+    try:
+        out = ops.gemm_skinny(x, lin.packed, splits=4)
+    finally:
+        L.crab_debug_trace(None, 0, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    t = buf.view(2, 256, 16)[0, :128].cpu()          # 32 tiles x 4 ranks
+    assert (t[:, 0] > 0).all() and (t[128:] == 0).all() if t.shape[0] > 128 else True
+    for a_, b_ in ((0, 2), (2, 3), (3, 4), (4, 7)):
+        assert (t[:, a_] <= t[:, b_]).all(), (a_, b_)
+    snap = buf.clone()
+    ops.gemm_skinny(x, lin.packed, splits=4)
+    torch.cuda.synchronize()
+    assert torch.equal(buf, snap)
+
+
 def test_fused_skinny_gate_up_down_head(cuda_dev):
     """gate/up (SwiGLU, norm, 2 LoRA linears, no K split) -> down (K = 11008, 8-way split, 1 LoRA linear, in-place residual) ->
     final norm + lm_head (ragged N, fp32 out), each one launch, chained through bf16 buffers like the decode step."""
