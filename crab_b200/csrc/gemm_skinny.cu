@@ -8,18 +8,26 @@
 // N/128 tiles cannot fill 148 SMs for the 4096-wide projections, so K is split S ways and the S CTAs of one tile form
 // a THREAD-BLOCK CLUSTER.  The split-K reduction never touches global memory: after its K-slice each CTA holds a
 // 128x32 fp32 partial in registers (from TMEM); the cluster does a reduce-scatter over DISTRIBUTED SHARED MEMORY —
-// rank j owns a group of rows, every rank stores its partial for that group straight into rank j's smem
-// (st.shared::cluster), one cluster barrier, then every rank sums its S partials in rank order (deterministic) and
-// applies the epilogue (bias, residual, SwiGLU, cast) for its rows.  No workspace, no atomics, no tickets.
-// (Measured on B200: the workspace + ticket + last-CTA fix-up design this replaces spent ~11 us of a 30 us launch in
-// the reduction tail; profiles/r01_skinny_epilogue_trace.txt.)
+// rank j owns a group of rows; every rank parks its partial in its own (by then idle) TMA ring and sends the rows of
+// group j as bulk shared->shared copies into rank j's dedicated receive area, reporting the bytes to an mbarrier there;
+// rank j sums its S partials in rank order (deterministic) and stores.  No workspace, no atomics, no cluster barrier or
+// release fence after the last MMA (both compile to MEMBAR.ALL.GPU: 1-3 us inside a saturated stream).
+// What follows the last MMA runs once per launch with one warp per scheduler, i.e. at instruction-FETCH speed (~0.25 us
+// per 128-byte line of cold straight-line code): bias / residual are fetched behind the weight stream and pre-added by the
+// thread that owns the row, and the finishing loop is one compact rolled loop per cluster size (sk_finish_split).
+// History with measurements: profiles/r01_skinny_epilogue_trace.txt (workspace + ticket -> cluster/DSMEM) and
+// profiles/r04_skinny_timeline.txt (in-kernel timeline: 24 us per layer of finishing loops -> 3 us).
+//
+// Fused form (the decode step): the packed weight carries W.diag(gamma) so the launch reads the raw residual stream and
+// multiplies its accumulator by rstd[b]; rstd and the hyper-LoRA pre-pass z' come from STATISTICS CLUSTERS, the first
+// clusters of the same grid (see is_stats below), through a flag in global memory.
 //
 // Weights are read either through a TMA tensor map (row-major [N, ldw]) or — the decode path — from the streaming
 // layout of crab_pack_skinny_weight: every (tile, k-block) is one contiguous, pre-swizzled 16 KB block, fetched with
 // a 1-D cp.async.bulk, so a CTA's K-slice is one sequential span of HBM.
 //
 //   warp 0 : TMA producer (W 128x64 + X 32x64 per stage, SWIZZLE_128B)     warp 1 : MMA issuer + TMEM owner
-//   warps 2-5 : TMEM -> registers -> DSMEM reduce-scatter -> epilogue
+//   warps 2-5 : TMEM -> registers -> (rstd, bias, residual) -> DSMEM reduce-scatter -> finishing loop
 #include <stdlib.h>
 
 #include "host_common.h"
@@ -206,12 +214,13 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
   const int SC = p.stats_clusters;
   const int tile = (int)blockIdx.x / S - SC;   // weight tile of this cluster (< 0: a statistics cluster)
   const int rank = (S > 1) ? (int)cluster_ctarank() : 0;
-  // One cluster of the launch is the STATISTICS cluster (when the launch has one): its A tile is
-  // [x rows (32) ; gamma*[R;A] rows], so the same MMA chain yields diag(x x^T) = sum x^2 and the hyper-LoRA router / A dots;
-  // its rank 0 publishes rstd and z' = scale * softmax(rstd * logits)_i * u_j and raises flags[0].  The other clusters read
-  // z' (their K-extension k-blocks, the last ones of the last rank) and rstd (epilogue scale) only after that flag.
-  // It is the FIRST cluster of the grid: clusters are placed in block order, so it is resident before any cluster that will
-  // wait for its flag (a last-placed statistics cluster can be starved of a contiguous slot by the very CTAs that spin on it).
+  // The first SC clusters of the launch are STATISTICS clusters (when the launch has any): their A tile is
+  // [gamma*[R;A] rows ; x rows (32)], so the same MMA chain yields diag(x x^T) = sum x^2 and the hyper-LoRA router / A dots over
+  // their share of K; rank 0 of each reduces its cluster, the last cluster to arrive (ticket) adds the clusters' partials in
+  // cluster order and publishes rstd and z' = scale * softmax(rstd * logits)_i * u_j, then raises flags[0].  The other clusters
+  // read z' (their K-extension k-blocks, the last ones of the last rank) and rstd (epilogue scale) only after that flag.
+  // They come FIRST in the grid: clusters are placed in block order, so they are resident before any cluster that will wait for
+  // the flag (a last-placed statistics cluster can be starved of a slot by the very CTAs that spin on it).
   const bool is_stats = blockIdx.x < (unsigned)(SC * S);
   const int KB = is_stats ? p.kb_main : p.kb_per_tile;
   // K-slice: a weight tile is split over the S ranks of its cluster, the statistics item over the SC * S CTAs of its clusters
