@@ -82,7 +82,7 @@ __device__ __forceinline__ void load_tile(uint32_t sbase, const __nv_bfloat16* g
 
 // Each warp owns MT x 16 query rows, so every K / V fragment fetched from shared memory (ldmatrix) feeds MT MMAs.
 template <int HD, int MT>
-__global__ void __launch_bounds__(128) flash_attn_kernel(const FlashParams p) {
+__global__ void __launch_bounds__(128, (HD == 64 && MT == 1) ? 4 : 1) flash_attn_kernel(const FlashParams p) {
   using Cfg = FlashCfg<HD, MT>;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem);
