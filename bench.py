@@ -67,6 +67,12 @@ class LazySynthSD:
     def __contains__(self, k):
         return k in self.m
 
+    def __iter__(self):
+        return iter(self.m)
+
+    def keys(self):
+        return self.m.keys()
+
     def items(self):
         for k in self.m:
             yield k, self[k]
@@ -443,6 +449,36 @@ def cpu_leg_and_parity(args, b, dev, cfg, ids, X_host, eng):
     return cpu, parity
 
 
+def run_seg_leg(dev):
+    """the segmentation head of generate_avs (crab_b200/seg.py) at the reference's sizes — d_model 4096, two ViT
+    taps of one 224^2 image (16 x 16 x 1024), 300 queries, 224^2 masks — one object per call as in quick_start; device-timed."""
+    from crab_b200 import ops
+    from crab_b200.models.unified_arch import seg_manifest
+    from crab_b200.seg import SegHead
+
+    sd = {k: v.cpu() for k, v in LazySynthSD({"model.seg_module." + k: v for k, v in seg_manifest(4096).items()}, 77, dev).items()}
+    head = SegHead(sd, dev, prefix="model.seg_module", grid=16)   # the head folds constants on the host at load time
+    g = torch.Generator(device=dev).manual_seed(5)
+    pred = torch.randn(1, 6, 4096, generator=g, device=dev).to(torch.bfloat16)
+    feats = [torch.randn(1, 256, 1024, generator=g, device=dev).to(torch.bfloat16) for _ in range(2)]
+    out = {}
+    for task in ("s4", "avss"):
+        n0 = ops.launch_count()
+        head.forward(pred, feats, [task])
+        launches = ops.launch_count() - n0
+        torch.cuda.synchronize()
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            m = head.forward(pred, feats, [task])
+        e1.record()
+        torch.cuda.synchronize()
+        out[task] = {"ms_per_object": e0.elapsed_time(e1) / reps, "kernels": int(launches), "mask_shape": list(m[0].shape)}
+    out["timing"] = "CUDA events over 10 calls, inputs resident, eager launches (the head is ~190 small kernels: launch-bound)"
+    return out
+
+
 def run_leg(leg, args, dev, eng, peaks):
     """Extra single-GPU configurations of BASELINE.json reported as keys of the same line (device-timed, inputs resident):
     bs1 = configs[1] (one sample, 64-token prompt, S = 638, 128 new tokens, same LLaMA-7B-dim engine);
@@ -478,7 +514,7 @@ def run_leg(leg, args, dev, eng, peaks):
         _, nxt = e.prefill(emb)
         if ev:
             ev[1].record()
-        e.begin_decode(a2.bs)
+        e.begin_decode(a2.bs, max_len=S2 + n_new)
         for _ in range(1, n_new):
             e.decode_step()
         if ev:
@@ -524,7 +560,7 @@ def main():
     ap.add_argument("--cpu-layers", type=int, default=4, help="decoder layers of the in-bench CPU leg / parity check (full-depth encoders)")
     ap.add_argument("--cpu-steps", type=int, default=3, help="decode steps of the CPU sample")
     ap.add_argument("--ref-layers", type=int, default=2, help="layers per stack of one --impl reference step (kept short: the driver runs 25 of them)")
-    ap.add_argument("--legs", default="bs1,qwen", help="extra single-GPU legs reported as keys of the same line ('' = none)")
+    ap.add_argument("--legs", default="bs1,qwen,seg", help="extra single-GPU legs reported as keys of the same line ('' = none)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --bs is the WHOLE-job batch, split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-pass", action="store_true",
@@ -839,7 +875,7 @@ def main():
         if world == 1 and args.legs and not args.layers:
             for leg in [x for x in args.legs.split(",") if x]:
                 try:
-                    legs[leg] = run_leg(leg, args, dev, eng, peaks)
+                    legs[leg] = run_seg_leg(dev) if leg == "seg" else run_leg(leg, args, dev, eng, peaks)
                 except Exception as e:
                     import traceback
                     traceback.print_exc()
@@ -853,6 +889,7 @@ def main():
                     "api": "crab_b200.models.unified_llama.UnifiedForCausalLM.generate", "ids_equal_resident_run": e2e_same},
             "gpu_launches": int(launches), "roofline": roof, "rooflines": rooflines, "cpu_baseline": cpu, "parity_check": parity,
             "phases": phases, "frontend": frontend, "bs1_config1": legs.get("bs1"), "qwen7b_config4": legs.get("qwen"),
+            "seg_head_f1": legs.get("seg"),
             "deterministic_across_steps": deterministic, "weights": "random-init (seeded), generated on device",
             "load_s": round(t_load, 1),
         }

@@ -1036,10 +1036,10 @@ class CrabEngine:
             # tensor-core GQA decode: two 80 KB blocks per SM — keep all splits in one wave (3 x 128 blocks = a second wave: 30 us vs 18)
             nsplit = max(1, min(8, (2 * 148) // blocks))
             nsplit = int(os.environ.get("CRAB_GQA_NSPLIT", nsplit))
-        if max_len is not None:
-            # a split needs keys to be worth its combine launch (~8 us per layer at bs 1): at least 256 keys per split over the longest
-            # context this request can reach.  bs 1 with a 64-token prompt + 128 new tokens: one launch per layer instead of two
-            nsplit = min(nsplit, max(1, -(-int(max_len) // 256)))
+        if max_len is not None and max_len <= 256:
+            # a short context is not worth the combine launch (~8 us per layer): one block per (b, kv head).  Longer ones keep the
+            # split that fills the SMs — measured at bs 1, S = 638: 3 splits 3.38 ms / step, 10 splits 3.22 ms
+            nsplit = 1
         ws = self._buf("dec_ws", (B * c.heads * nsplit * (c.head_dim + 2),), torch.float32) if nsplit > 1 else None
         self._dec_args = (B, nsplit, ws)
         self._use_graph = use_graph
