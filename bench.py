@@ -463,6 +463,7 @@ def run_seg_leg(dev):
     feats = [torch.randn(1, 256, 1024, generator=g, device=dev).to(torch.bfloat16) for _ in range(2)]
     out = {}
     for task in ("s4", "avss"):
+        head.forward(pred, feats, [task])          # first call per task kind: warm-up + graph capture
         n0 = ops.launch_count()
         head.forward(pred, feats, [task])
         launches = ops.launch_count() - n0
@@ -475,7 +476,7 @@ def run_seg_leg(dev):
         e1.record()
         torch.cuda.synchronize()
         out[task] = {"ms_per_object": e0.elapsed_time(e1) / reps, "kernels": int(launches), "mask_shape": list(m[0].shape)}
-    out["timing"] = "CUDA events over 10 calls, inputs resident, eager launches (the head is ~190 small kernels: launch-bound)"
+    out["timing"] = "CUDA events over 10 calls, inputs resident, one CUDA-graph replay per object (193 small kernels; 3.9 ms as eager launches)"
     return out
 
 

@@ -17,6 +17,7 @@ Python here is plumbing only; there is no torch arithmetic on the data path (loa
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Sequence
 
 import torch
@@ -247,26 +248,68 @@ class SegHead:
     @torch.no_grad()
     def forward(self, pred_embeddings: torch.Tensor, multi_scale_feats: Sequence[torch.Tensor], task_names: List[str]):
         """pred_embeddings bf16 [bs, scales*tokens_per_scale, d_model]; multi_scale_feats: `scales` bf16 tensors
-        [bs, n_img*grid^2, 1024] -> list of fp32 [num_classes, image, image] masks (one object per sample, as quick_start)."""
+        [bs, n_img*grid^2, 1024] -> list of fp32 [num_classes, image, image] masks (one object per sample, as quick_start).
+        On a GPU the ~190 small launches of one object are captured in a CUDA graph per task kind and replayed (the head is
+        launch-bound: 3.9 ms eager); CRAB_SEG_GRAPH=0 keeps the eager path."""
         bs, n, D = pred_embeddings.shape
         assert n == self.scales * self.tps and D == self.d_model, "one object per sample: scales * tokens_per_scale hidden states"
         g0, out = self.grid, []
+        use_graph = pred_embeddings.is_cuda and os.environ.get("CRAB_SEG_GRAPH", "1") != "0"
         for i in range(bs):
-            hid = ops.elementwise(ops.gemm(pred_embeddings[i], self.fc0.w, bias=self.fc0.b), ops.EW_RELU)     # [6, D]
-            abuf = torch.zeros((8, self.tps * D), device=hid.device, dtype=torch.bfloat16)
-            ops.gather_rows(hid.view(self.scales, self.tps * D), abuf, self.scales, self.tps * D)              # [scales, 3D] view
-            sparse = ops.gemm(abuf, self.fc2.w, bias=self.fc2.b)                                               # rows 0..scales-1
-            classes = self.n_avss if task_names[i] == "avss" else self.n_s4
-            low = torch.zeros((self.low_res * self.low_res, classes), device=hid.device, dtype=torch.float32)
-            prev = None
-            for l in range(self.scales):
-                f = multi_scale_feats[l][i][: g0 * g0]                                                         # first image's grid
-                x = ops.layernorm(ops.gemm(f, self.neck0.w), *self.neck_ln1, 1e-6)
-                x = ops.layernorm(ops.gemm(ops.im2col3x3(x, g0, g0), self.neck2.w), *self.neck_ln3, 1e-6)
-                srow = torch.zeros((8, E), device=hid.device, dtype=torch.bfloat16)
-                ops.gather_rows(sparse[l:l + 1], srow, 1, E)
-                prev = self._predict(x, srow, l, prev, classes, task_names[i])
-                side = 2 * g0 * (l + 1)                                                                         # 32, 64
-                ops.bilinear_f32(prev, side, side, self.low_res, self.low_res, classes, out=low, alpha=1.0 / self.scales, beta=1.0)
-            out.append(ops.bilinear_f32(low, self.low_res, self.low_res, self.image, self.image, classes, nchw_out=True))
+            feats_i = [multi_scale_feats[l][i][: g0 * g0] for l in range(self.scales)]                        # first image's grid
+            if use_graph:
+                out.append(self._forward_graph(pred_embeddings[i], feats_i, task_names[i]))
+            else:
+                out.append(self._forward_one(pred_embeddings[i], feats_i, task_names[i]))
         return out
+
+    def _forward_graph(self, pred_i: torch.Tensor, feats_i: List[torch.Tensor], task: str) -> torch.Tensor:
+        key = "avss" if task == "avss" else "s4"
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        if key not in self._graphs:
+            p_in = torch.empty_like(pred_i, memory_format=torch.contiguous_format)
+            f_in = [torch.empty_like(f, memory_format=torch.contiguous_format) for f in feats_i]
+            p_in.copy_(pred_i)
+            for d_, s_ in zip(f_in, feats_i):
+                d_.copy_(s_)
+            side = torch.cuda.Stream(device=pred_i.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._forward_one(p_in, f_in, key)            # warm-up outside capture (kernel attributes, allocator)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(gr):
+                o = self._forward_one(p_in, f_in, key)
+            kernels = ops.launch_count() - n0
+            ops.count_launches(-kernels)                       # capture launches nothing
+            self._graphs[key] = (gr, p_in, f_in, o, kernels)
+        gr, p_in, f_in, o, kernels = self._graphs[key]
+        p_in.copy_(pred_i)
+        for d_, s_ in zip(f_in, feats_i):
+            d_.copy_(s_)
+        gr.replay()
+        ops.count_launches(kernels)
+        return o.clone()
+
+    def _forward_one(self, pred_i: torch.Tensor, feats_i: List[torch.Tensor], task: str) -> torch.Tensor:
+        D, g0 = self.d_model, self.grid
+        hid = ops.elementwise(ops.gemm(pred_i, self.fc0.w, bias=self.fc0.b), ops.EW_RELU)                 # [6, D]
+        abuf = torch.zeros((8, self.tps * D), device=hid.device, dtype=torch.bfloat16)
+        ops.gather_rows(hid.view(self.scales, self.tps * D), abuf, self.scales, self.tps * D)              # [scales, 3D] view
+        sparse = ops.gemm(abuf, self.fc2.w, bias=self.fc2.b)                                               # rows 0..scales-1
+        classes = self.n_avss if task == "avss" else self.n_s4
+        low = torch.zeros((self.low_res * self.low_res, classes), device=hid.device, dtype=torch.float32)
+        prev = None
+        for l in range(self.scales):
+            f = feats_i[l]
+            x = ops.layernorm(ops.gemm(f, self.neck0.w), *self.neck_ln1, 1e-6)
+            x = ops.layernorm(ops.gemm(ops.im2col3x3(x, g0, g0), self.neck2.w), *self.neck_ln3, 1e-6)
+            srow = torch.zeros((8, E), device=hid.device, dtype=torch.bfloat16)
+            ops.gather_rows(sparse[l:l + 1], srow, 1, E)
+            prev = self._predict(x, srow, l, prev, classes, task)
+            side = 2 * g0 * (l + 1)                                                                         # 32, 64
+            ops.bilinear_f32(prev, side, side, self.low_res, self.low_res, classes, out=low, alpha=1.0 / self.scales, beta=1.0)
+        return ops.bilinear_f32(low, self.low_res, self.low_res, self.image, self.image, classes, nchw_out=True)
