@@ -198,6 +198,9 @@ class CrabEngine:
             k_, v_ = kv.split(":")
             self.skinny_splits[k_] = int(v_)
         # flag slots in a ring (each launch zeroes its predecessor's) and several statistics clusters per launch (0 = library's choice)
+        # CUDA graphs around launch-bound call sites outside the decode loop (encoders of <= 32 frames / segments, prefill of <= 2048 rows)
+        self.call_graphs = os.environ.get("CRAB_CALL_GRAPHS", "1") != "0"
+        self._call_graphs = {}
         self.flag_ring = os.environ.get("CRAB_FLAG_RING", "1") != "0"
         self.stats_clusters = int(os.environ.get("CRAB_STATS_CLUSTERS", "0"))
         # L2 prefetch of the next linear's weights from the tail of each decode linear (MB per launch, 0 = off)
@@ -226,6 +229,44 @@ class CrabEngine:
         return t
 
     # ---- decoder weights -------------------------------------------------------------------------------------
+    def _graph_replay(self, key, static_inputs: Sequence[torch.Tensor], inputs: Sequence[torch.Tensor], fn):
+        """Launch-bound call sites (a single sample's encoders / prefill are ~1.2 k launches of a few microseconds): run
+        `fn(*static_inputs)` as ONE CUDA-graph replay, captured once per `key` (shapes); `inputs` are copied into the static
+        buffers first.  Returns what fn returned at capture time (tensors in the graph's memory pool: valid until the next replay
+        of the same key).  At most 8 graphs are kept; beyond that the call runs eagerly."""
+        ent = self._call_graphs.get(key)
+        if ent is None:
+            if len(self._call_graphs) >= 8:
+                for d_, s_ in zip(static_inputs, inputs):
+                    d_.copy_(s_)
+                return fn(*static_inputs)
+            for d_, s_ in zip(static_inputs, inputs):
+                d_.copy_(s_)
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn(*static_inputs)                      # warm-up outside capture: kernel attributes, lazily built tables, allocator
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for d_, s_ in zip(static_inputs, inputs):   # fn may consume its input in place
+                d_.copy_(s_)
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                out = fn(*static_inputs)
+            kernels = ops.launch_count() - n0
+            ops.count_launches(-kernels)                # capture launches nothing
+            ent = self._call_graphs[key] = (g, out, kernels)
+        g, out, kernels = ent
+        for d_, s_ in zip(static_inputs, inputs):
+            d_.copy_(s_)
+        g.replay()
+        ops.count_launches(kernels)
+        return out
+
+    def _small_call_graphs(self) -> bool:
+        return self.call_graphs and self.dev.type == "cuda" and ops._timer is None and not torch.cuda.is_current_stream_capturing()
+
     def _pack_decoder(self, sd: SD):
         c, dev = self.cfg.decoder, self.dev
         D, F, H, KV, hd = c.hidden, c.inter, c.heads, c.kv_heads, c.head_dim
@@ -665,7 +706,19 @@ class CrabEngine:
             u8 = all(items[i].dtype == torch.uint8 for i in idxs)  # raw frames stay uint8 (fused normalise + im2col)
             xs = torch.cat([items[i].to(self.dev, dtype=torch.uint8 if u8 else torch.float32, non_blocking=True)
                             for i in idxs], 0).contiguous()
-            y = fn(xs)
+            if self._small_call_graphs() and xs.shape[0] <= 32:
+                name = "video" if fn == self.encode_video else "audio"
+                static = self._buf("graph_in_" + name + "_" + "x".join(map(str, xs.shape)), tuple(xs.shape), xs.dtype)
+
+                def run(xs_, fn=fn):   # the ViT taps are a side output of encode_video: they belong to the graph's outputs
+                    y_ = fn(xs_)
+                    return y_, dict(getattr(self, "_last_taps", {}))
+                y, taps = self._graph_replay((name, tuple(xs.shape), xs.dtype), [static], [xs], run)
+                y = y.clone()
+                if name == "video":
+                    self._last_taps = taps
+            else:
+                y = fn(xs)
             r = 0
             for i in idxs:
                 nrows = items[i].shape[0] * nq
@@ -689,6 +742,7 @@ class CrabEngine:
                         for _ in range(c.layers)]
         self.v_cache = [torch.zeros_like(k) for k in self.k_cache]
         self._graph = None
+        self._call_graphs = {k: v for k, v in self._call_graphs.items() if k[0] != "prefill"}   # they hold the old cache's addresses
 
     def _decoder_layers(self, x: torch.Tensor, B: int, S: int, past: int, past_dev=None, len_dev=None, nsplit=1,
                         ws=None, tag="pf"):
@@ -784,12 +838,24 @@ class CrabEngine:
         if inputs_embeds.dtype != torch.bfloat16 or not inputs_embeds.is_cuda or not inputs_embeds.is_contiguous():
             inputs_embeds = inputs_embeds.to(device=self.dev, dtype=torch.bfloat16).contiguous()
         x = inputs_embeds.view(B * S, D)
+        t = getattr(self, "_tail_rows", 0)
+        if self._small_call_graphs() and B * S <= 2048 and not t:
+            self.logits = self._buf("logits", (B, self.vocab_pad), torch.float32)
+            self.next_ids = self._buf("next_ids", (B,), torch.int64)
+
+            def body(xs):
+                self._decoder_layers(xs, B, S, past=0)
+                last_ = self._buf("last_x", (B, D))
+                ops.gather_rows(xs, last_, B, D, src_rows=(torch.arange(B, device=self.dev) * S + (S - 1)))
+                self._head(last_, self.logits, self.next_ids)
+            self._graph_replay(("prefill", B, S, id(self.k_cache[0])), [self._buf("graph_in_prefill_%dx%d" % (B, S), (B * S, D))], [x], body)
+            self.cur_len = S
+            return self.logits[:, : self.vocab], self.next_ids
         self._decoder_layers(x, B, S, past=0)
         self.cur_len = S
         last = self._buf("last_x", (B, D))
         rows = (torch.arange(B, device=self.dev) * S + (S - 1))
         ops.gather_rows(x, last, B, D, src_rows=rows)
-        t = getattr(self, "_tail_rows", 0)
         if t:  # final-normed hidden states of the last t prompt positions (HF hidden_states[0][-1][:, -t:])
             trows = (torch.arange(B, device=self.dev).view(B, 1) * S + torch.arange(S - t, S, device=self.dev).view(1, t)).reshape(-1)
             tail = torch.empty((B * t, D), device=self.dev, dtype=torch.bfloat16)
