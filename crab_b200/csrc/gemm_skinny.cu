@@ -446,15 +446,20 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
           sc[0] = make_float4(ss, t[0], t[1], t[2]);
           sc[1] = make_float4(t[3], t[4], t[5], t[6]);
           sc[2] = make_float4(t[7], t[8], t[9], t[10]);
-          __threadfence();
+          // one acq_rel ticket by thread 0 between two CTA barriers: its release covers the block's partial stores (cumulativity
+          // through the barrier), its acquire the last block's loads below — instead of a GPU-scope fence per thread on each side
+          // (each costs ~2 us while 300 CTAs stream weights)
           asm volatile("bar.sync 2, %0;" ::"r"(32 * nw) : "memory");
           __shared__ int ticket_s;
-          if (tt == 0) ticket_s = atomicAdd(p.flags + 1, 1);
+          if (tt == 0) {
+            int tk;
+            asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(tk) : "l"(p.flags + 1) : "memory");
+            ticket_s = tk;
+          }
           asm volatile("bar.sync 2, %0;" ::"r"(32 * nw) : "memory");
           fin = ticket_s == SC - 1;
           if (threadIdx.x == 64) trace_stamp(p.trace, 14);
           if (fin) {
-            __threadfence();
             ss = 0.f;
 #pragma unroll
             for (int j = 0; j < 11; ++j) t[j] = 0.f;
@@ -490,8 +495,8 @@ gemm_skinny_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __g
               *reinterpret_cast<uint4*>(zrow + i * 8) = v;
             }
           }
-          __threadfence();
-          asm volatile("fence.proxy.async;" ::: "memory");
+          // rstd / z' stores of the block -> CTA barrier -> ONE release store (cumulative over the barrier); the consumers pair it
+          // with ld.acquire + fence.proxy.async before their TMA loads of z'
           asm volatile("bar.sync 2, %0;" ::"r"(32 * nw) : "memory");
           if (tt == 0) {
             asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags), "r"(1) : "memory");
@@ -767,7 +772,10 @@ extern "C" int crab_gemm_skinny_bf16(const crab_skinny_args* a, void* stream_) {
   // k-block behind the weight streams of 300 other CTAs), at most 8; more than one needs the scratch buffer
   int sc = 0;
   if (has_stats) {
-    sc = a->stats_clusters > 0 ? a->stats_clusters : (a->stats_scratch ? (kb_main + splits * 8 - 1) / (splits * 8) : 1);
+    // the cross-cluster combine costs ~8 us of dependent global round trips: worth it only when one cluster would stream long
+    // (0.4 us per k-block and CTA).  Qwen2 qkv (56 k-blocks over 4 ranks): one cluster; LLaMA gate/up (64 over 1): eight
+    const int per_cta = kb_main / splits;
+    sc = a->stats_clusters > 0 ? a->stats_clusters : ((a->stats_scratch && per_cta > 24) ? (per_cta + 7) / 8 : 1);
     if (sc > 8) sc = 8;
     if (sc * splits > kb_main) sc = kb_main / splits > 0 ? kb_main / splits : 1;
     CRAB_REQUIRE(sc == 1 || a->stats_scratch, "crab_gemm_skinny_bf16: stats_clusters > 1 needs stats_scratch (8 x 36 x 32 floats)");
