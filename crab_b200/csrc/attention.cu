@@ -385,13 +385,18 @@ __device__ __forceinline__ void lora_prepass_tail(float (&t11)[11], int b, int s
     float v = 0.f;
     for (int w = 0; w < nwarps; ++w) v += sh_red[w][threadIdx.x];
     lora_ws[((size_t)b * nblocks + slot) * 11 + threadIdx.x] = v;
-    __threadfence();
+  }
+  // one acq_rel ticket between two block barriers: its release covers the 11 partial stores above (cumulative over the barrier),
+  // its acquire the last block's loads below — a GPU-scope fence per thread on either side costs ~2 us each on the step's critical
+  // path (this tail sits between the attention's last key and o_proj's first operand)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tk;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(tk) : "l"(lora_cnt + b) : "memory");
+    *sh_ticket = tk;
   }
   __syncthreads();
-  if (threadIdx.x == 0) *sh_ticket = atomicAdd(lora_cnt + b, 1);
-  __syncthreads();
   if (*sh_ticket == nblocks - 1) {
-    __threadfence();
     if (threadIdx.x < 11) {
       const volatile float* wsp = lora_ws + (size_t)b * nblocks * 11 + threadIdx.x;
       float t = 0.f;
