@@ -248,6 +248,19 @@ flash_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         pk[i] = pack_bf16x2(p0, p1);
       }
       l_run += rs;
+      if (k0 + FT_BN > p.Sk) {
+        // the tile reaches past the last key: its P columns are 0, but 0 x NaN would still poison O if the memory behind the
+        // tensor holds NaN bit patterns (an uninitialised cache).  Zero the V rows past Sk in shared memory before PV_j reads them.
+        const uint32_t stage_v = (uint32_t)j % FT_STAGES;
+        mbar_wait(v_full(stage_v), ((uint32_t)j / FT_STAGES) & 1);   // the tile has landed (a second waiter next to the MMA warp)
+        const uint32_t sv = sKV + stage_v * FT_STAGE_BYTES + FT_KV_TILE;
+        const int r0 = max(0, p.Sk - k0), nrows = FT_BN - r0;
+        for (int i = quarter * 32 + lane; i < nrows * 16; i += 128) {
+          const int r = r0 + (i >> 4), piece = i & 15;
+          const uint32_t addr = sv + (uint32_t)((piece >> 3) * (FT_KV_TILE / 2) + r * 128 + (piece & 7) * 16);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+        }
+      }
       // P buffer free and O stable only once PV_{j-1} has completed
       if (j > 0) {
         mbar_wait(pv_done, (uint32_t)(j - 1) & 1);

@@ -108,9 +108,9 @@ int crab_rope_kv_append(void* qkv, int ldq, const float* cos_sin, void* k_cache,
  *           (models/modeling_llama.py:405-450, models/qwen/modeling_qwen2.py:190-199 repeat_kv).
  *           All strides are in elements; head_dim in {64,128}; bias = gate[B,H,Sq] * bias_table[H,Sq,Sk] (fp32) or NULL.
  *           head_dim-128 problems with >= 128 queries, no bias and TMA-describable strides run on the tcgen05 / TMEM kernel,
- *           which fetches whole 64-key tiles: K / V memory up to the next multiple of 64 rows past Sk must hold FINITE values
- *           (masked keys get probability 0, and 0 x NaN would poison the row) — zero-initialised KV caches do; rows past the
- *           end of the tensor are zero-filled by TMA.
+ *           which fetches whole 64-key tiles: rows up to the next multiple of 64 past Sk are read but never contribute (their
+ *           scores are masked before the exponential and the kernel zeroes the V rows past Sk in shared memory, so even NaN bit
+ *           patterns in an uninitialised cache are harmless); rows past the end of the tensor are zero-filled by TMA.
  *           With sk_dev the number of keys is read on the device: the GQA decode step calls this with the G query heads of
  *           a kv group as the Sq = G "rows" of one problem (q_rs = head_dim), so grouped-query decode runs on tensor cores.
  * crab_attn_decode replaces: the same attention at q_len == 1 over the KV cache (decode step), split over the

@@ -114,6 +114,31 @@ def test_flash_attn(cuda_dev, B, H, KVH, Sq, Sk, hd, causal):
     _close(o, ref, 2e-2)
 
 
+@pytest.mark.parametrize("Sq,Sk,causal", [(300, 300, True), (257, 257, False), (130, 333, True)])
+def test_flash_attn_tcgen05_ignores_garbage_past_sk(cuda_dev, Sq, Sk, causal):
+    """The tcgen05 kernel fetches whole 64-key tiles: cache rows past Sk (here NaN and Inf bit patterns, as in a torch.empty cache)
+    must not reach the output — their scores are masked and the kernel zeroes the V rows past Sk in shared memory."""
+    from crab_b200 import ops
+
+    B, H, hd, ctx = 2, 4, 128, 384
+    g = _g(Sq * 7 + Sk)
+    q = torch.randn(B, Sq, H, hd, generator=g).to(torch.bfloat16).to(cuda_dev)
+    kc = torch.randn(B, H, ctx, hd, generator=g).to(torch.bfloat16).to(cuda_dev)
+    vc = torch.randn(B, H, ctx, hd, generator=g).to(torch.bfloat16).to(cuda_dev)
+    kc[:, :, Sk:] = float("nan")
+    vc[:, :, Sk:] = float("nan")
+    vc[:, :, Sk::2] = float("inf")
+    o = torch.zeros(B, Sq, H, hd, dtype=torch.bfloat16, device=cuda_dev)
+    ops.flash_attn(q, kc, vc, o, B=B, H=H, KVH=H, Sq=Sq, Sk=Sk, head_dim=hd,
+                   q_strides=(Sq * H * hd, H * hd, hd), k_strides=(H * ctx * hd, hd, ctx * hd),
+                   v_strides=(H * ctx * hd, hd, ctx * hd), o_strides=(Sq * H * hd, H * hd, hd),
+                   scale=1 / math.sqrt(hd), causal=causal)
+    torch.cuda.synchronize()
+    assert torch.isfinite(o.float()).all()
+    ref = _attn_ref(q.transpose(1, 2), kc[:, :, :Sk], vc[:, :, :Sk], 1 / math.sqrt(hd), causal).transpose(1, 2)
+    _close(o, ref, 2e-2)
+
+
 def test_flash_attn_beats_bias(cuda_dev):
     from crab_b200 import ops
 
