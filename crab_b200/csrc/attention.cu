@@ -54,6 +54,9 @@ struct FlashParams {
   int sk_add;          // added to *sk_dev (decode: *past_dev + 1 keys)
   int nsplit;          // > 1: split-KV (Sq <= 64 only): blockIdx.x = split, partial states -> ws, attn_decode_combine_kernel finishes
   float* ws;           // [(b * H * Sq + h * Sq + row) * nsplit + split][HD + 2]: un-normalised acc, running max (log2 domain), sum
+  // TMA staging (head_dim 64, TMA-describable strides): the three tensors as 2-D [rows, row stride] maps, tile (row, col) origins
+  int use_tma;
+  int q_row_per_b, q_col_per_h, k_row_per_b, k_row_per_h, k_col_per_h, v_row_per_b, v_row_per_h, v_col_per_h;
 };
 
 template <int HD, int MT>
@@ -82,9 +85,17 @@ __device__ __forceinline__ void load_tile(uint32_t sbase, const __nv_bfloat16* g
 
 // Each warp owns MT x 16 query rows, so every K / V fragment fetched from shared memory (ldmatrix) feeds MT MMAs.
 template <int HD, int MT>
-__global__ void __launch_bounds__(128, (HD == 64 && MT == 1) ? 4 : 1) flash_attn_kernel(const FlashParams p) {
+__global__ void __launch_bounds__(128, (HD == 64 && MT == 1) ? 4 : 1)
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                  const __grid_constant__ CUtensorMap tmap_v, const FlashParams p) {
   using Cfg = FlashCfg<HD, MT>;
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // head_dim 64: a tile row is exactly one 128-byte swizzle row, and tile_addr's layout (16-byte chunk c of row r at c ^ (r & 7))
+  // IS the TMA SWIZZLE_128B layout — so Q / K / V tiles can be staged by cp.async.bulk.tensor (one thread, two instructions per
+  // 64-key step, completion on an mbarrier) instead of 16 cp.async per thread, with the ldmatrix addressing unchanged.
+  const bool tma = (HD == 64) && p.use_tma;
+  __shared__ __align__(8) uint64_t fbars[3];   // Q, K/V buffer 0, K/V buffer 1
+  const uint32_t q_bar = smem_u32(&fbars[0]);
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sK0 = sQ + MT * Cfg::TILE_BYTES;
   const uint32_t sV0 = sK0 + 2 * Cfg::TILE_BYTES;
@@ -111,11 +122,33 @@ __global__ void __launch_bounds__(128, (HD == 64 && MT == 1) ? 4 : 1) flash_attn
     t_begin = min(n_tiles, split * per);
     t_end = min(n_tiles, t_begin + per);
   }
+  const int qrow = b * p.q_row_per_b + q0, qcol = h * p.q_col_per_h;
+  const int krow = b * p.k_row_per_b + kvh * p.k_row_per_h, kcol = kvh * p.k_col_per_h;
+  const int vrow = b * p.v_row_per_b + kvh * p.v_row_per_h, vcol = kvh * p.v_col_per_h;
+  auto kv_bar = [&](int buf_) { return smem_u32(&fbars[1 + buf_]); };
+  auto tma_kv = [&](int buf_, int t_) {   // one thread: K and V tile of key step t_ -> buffer buf_
+    mbar_arrive_expect_tx(kv_bar(buf_), 2 * Cfg::TILE_BYTES);
+    tma_load_2d(sK0 + buf_ * Cfg::TILE_BYTES, &tmap_k, kv_bar(buf_), kcol, krow + t_ * Cfg::BN);
+    tma_load_2d(sV0 + buf_ * Cfg::TILE_BYTES, &tmap_v, kv_bar(buf_), vcol, vrow + t_ * Cfg::BN);
+  };
+  if (tma) {
+    if (threadIdx.x == 0) {
+      if ((sQ & 1023u) != 0) { printf("crab: flash_attn smem misaligned for TMA\n"); __trap(); }
+      mbar_init(q_bar, 1); mbar_init(kv_bar(0), 1); mbar_init(kv_bar(1), 1);
+      fence_barrier_init();
+      mbar_arrive_expect_tx(q_bar, MT * Cfg::TILE_BYTES);
 #pragma unroll
-  for (int t = 0; t < MT; ++t) load_tile<HD>(sQ + t * Cfg::TILE_BYTES, qg, p.q_rs, q0 + t * 64, p.Sq);
-  load_tile<HD>(sK0, kg, p.k_rs, t_begin * Cfg::BN, Sk);
-  load_tile<HD>(sV0, vg, p.v_rs, t_begin * Cfg::BN, Sk);
-  cp_async_commit();
+      for (int t = 0; t < MT; ++t) tma_load_2d(sQ + t * Cfg::TILE_BYTES, &tmap_q, q_bar, qcol, qrow + t * 64);
+      if (t_begin < t_end) tma_kv(0, t_begin);
+    }
+    __syncthreads();   // barriers initialised before anybody waits on them
+  } else {
+#pragma unroll
+    for (int t = 0; t < MT; ++t) load_tile<HD>(sQ + t * Cfg::TILE_BYTES, qg, p.q_rs, q0 + t * 64, p.Sq);
+    load_tile<HD>(sK0, kg, p.k_rs, t_begin * Cfg::BN, Sk);
+    load_tile<HD>(sV0, vg, p.v_rs, t_begin * Cfg::BN, Sk);
+    cp_async_commit();
+  }
 
   constexpr int DT = HD / 8;  // output n8-tiles per row
   float o_acc[MT][DT][4];
@@ -138,18 +171,25 @@ __global__ void __launch_bounds__(128, (HD == 64 && MT == 1) ? 4 : 1) flash_attn
   const float sl2 = p.scale * 1.4426950408889634f;
   const bool warp_active = q0 + warp * MT * 16 < p.Sq;
 
-  if (t_begin >= t_end) cp_async_wait<0>();   // empty split: nothing to consume
+  if (t_begin >= t_end && !tma) cp_async_wait<0>();   // empty split: nothing to consume
+  if (tma) mbar_wait(q_bar, 0);
   for (int t = t_begin; t < t_end; ++t) {
     const int buf = (t - t_begin) & 1;
-    if (t + 1 < t_end) {
-      load_tile<HD>(sK0 + (buf ^ 1) * Cfg::TILE_BYTES, kg, p.k_rs, (t + 1) * Cfg::BN, Sk);
-      load_tile<HD>(sV0 + (buf ^ 1) * Cfg::TILE_BYTES, vg, p.v_rs, (t + 1) * Cfg::BN, Sk);
-      cp_async_commit();
-      cp_async_wait<1>();
+    if (tma) {
+      // buffer buf ^ 1 was last read in iteration t - 1, which ended with a block barrier: it may be refilled now
+      if (t + 1 < t_end && threadIdx.x == 0) tma_kv(buf ^ 1, t + 1);
+      mbar_wait(kv_bar(buf), (uint32_t)((t - t_begin) >> 1) & 1);
     } else {
-      cp_async_wait<0>();
+      if (t + 1 < t_end) {
+        load_tile<HD>(sK0 + (buf ^ 1) * Cfg::TILE_BYTES, kg, p.k_rs, (t + 1) * Cfg::BN, Sk);
+        load_tile<HD>(sV0 + (buf ^ 1) * Cfg::TILE_BYTES, vg, p.v_rs, (t + 1) * Cfg::BN, Sk);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
     }
-    __syncthreads();
     const uint32_t sK = sK0 + buf * Cfg::TILE_BYTES, sV = sV0 + buf * Cfg::TILE_BYTES;
 
     // a warp whose query rows all lie past Sq (decode over a kv group: Sq = G <= 16 rows, three of the four warps) only helps
@@ -686,6 +726,18 @@ __global__ void attn_decode_combine_kernel(const float* __restrict__ ws, __nv_bf
 
 using namespace crab;
 
+// Can (base, batch stride, row stride, head stride) of a head_dim-64 operand be walked as a 2-D [rows, row stride] tensor by TMA?
+static bool flash64_tma_view(const void* base, long long bs, long long rs, long long hs, int heads, int B, int* row_per_b, int* row_per_h,
+                             int* col_per_h, long long* rows_total) {
+  if (rs < 64 || rs % 8 != 0 || ((uintptr_t)base % 16) != 0 || bs % rs != 0) return false;
+  *row_per_b = (int)(bs / rs);
+  if (hs % rs == 0) { *row_per_h = (int)(hs / rs); *col_per_h = 0; }
+  else if ((long long)heads * hs <= rs && hs >= 64 && hs % 8 == 0) { *row_per_h = 0; *col_per_h = (int)hs; }
+  else return false;
+  *rows_total = (long long)B * (bs / rs);
+  return true;
+}
+
 extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
   CRAB_REQUIRE(a && a->q && a->k && a->v && a->o, "crab_flash_attn: null pointer");
   CRAB_REQUIRE(a->head_dim == 64 || a->head_dim == 128, "crab_flash_attn: head_dim must be 64 or 128 (got %d)", a->head_dim);
@@ -706,6 +758,31 @@ extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
   p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.Sq = a->Sq; p.Sk = a->Sk;
   p.scale = a->scale; p.causal = a->causal; p.gate = a->gate; p.table = a->bias_table; p.sk_dev = a->sk_dev;
   p.sk_add = 0; p.nsplit = 1; p.ws = nullptr;
+  p.use_tma = 0;
+  p.q_row_per_b = p.q_col_per_h = p.k_row_per_b = p.k_row_per_h = p.k_col_per_h = p.v_row_per_b = p.v_row_per_h = p.v_col_per_h = 0;
+  CUtensorMap tq, tk, tv;
+  memset(&tq, 0, sizeof(tq)); memset(&tk, 0, sizeof(tk)); memset(&tv, 0, sizeof(tv));
+  if (a->head_dim == 64 && !a->sk_dev) {
+    static int tma_enabled = -1;
+    if (tma_enabled < 0) { const char* e = getenv("CRAB_FLASH_TMA"); tma_enabled = (e && e[0] == '0') ? 0 : 1; }
+    long long qr, kr, vr;
+    int q_row_per_h = 0;
+    if (tma_enabled &&
+        flash64_tma_view(a->q, a->q_bs, a->q_rs, a->q_hs, a->H, a->B, &p.q_row_per_b, &q_row_per_h, &p.q_col_per_h, &qr) && q_row_per_h == 0 &&
+        flash64_tma_view(a->k, a->k_bs, a->k_rs, a->k_hs, a->KVH, a->B, &p.k_row_per_b, &p.k_row_per_h, &p.k_col_per_h, &kr) &&
+        flash64_tma_view(a->v, a->v_bs, a->v_rs, a->v_hs, a->KVH, a->B, &p.v_row_per_b, &p.v_row_per_h, &p.v_col_per_h, &vr)) {
+      // extents = the last row the call is entitled to read + 1 (the API carries no buffer sizes): whatever a 64-row box covers
+      // beyond that is zero-filled by TMA instead of being read
+      qr = (long long)(a->B - 1) * p.q_row_per_b + a->Sq;
+      kr = (long long)(a->B - 1) * p.k_row_per_b + (long long)(a->KVH - 1) * p.k_row_per_h + a->Sk;
+      vr = (long long)(a->B - 1) * p.v_row_per_b + (long long)(a->KVH - 1) * p.v_row_per_h + a->Sk;
+      int rc = encode_tmap_bf16_2d(&tq, a->q, (uint64_t)qr, (uint64_t)a->q_rs, (uint64_t)a->q_rs, 64, 64);
+      if (rc == 0) rc = encode_tmap_bf16_2d(&tk, a->k, (uint64_t)kr, (uint64_t)a->k_rs, (uint64_t)a->k_rs, 64, 64);
+      if (rc == 0) rc = encode_tmap_bf16_2d(&tv, a->v, (uint64_t)vr, (uint64_t)a->v_rs, (uint64_t)a->v_rs, 64, 64);
+      if (rc != 0) return rc;
+      p.use_tma = 1;
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   {  // head_dim 128 without a bias table and with TMA-describable strides: the tcgen05 / TMEM kernel (flash_tcgen05.cu)
     const int rc = a->sk_dev ? -1 : flash_attn_tcgen05_try(a, st);
@@ -723,7 +800,7 @@ extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
                                            FlashCfg<HD_, MT_>::SMEM));                                                     \
     }                                                                                                                      \
     dim3 grid((a->Sq + FlashCfg<HD_, MT_>::BM - 1) / FlashCfg<HD_, MT_>::BM, a->H, a->B);                                  \
-    flash_attn_kernel<HD_, MT_><<<grid, 128, FlashCfg<HD_, MT_>::SMEM, st>>>(p);                                           \
+    flash_attn_kernel<HD_, MT_><<<grid, 128, FlashCfg<HD_, MT_>::SMEM, st>>>(tq, tk, tv, p);                               \
   }
   if (a->head_dim == 64) {
     if (big) CRAB_FLASH_LAUNCH(64, 2) else CRAB_FLASH_LAUNCH(64, 1)
@@ -809,11 +886,15 @@ extern "C" int crab_attn_decode_fused(const crab_decode_fused_args* a, void* str
     fp.B = a->B; fp.H = a->KVH; fp.KVH = a->KVH; fp.Sq = G; fp.Sk = a->ctx_max;
     fp.scale = a->scale; fp.causal = 0; fp.gate = nullptr; fp.table = nullptr; fp.sk_dev = a->past_dev; fp.sk_add = 1;
     fp.nsplit = a->nsplit; fp.ws = a->workspace;
+    fp.use_tma = 0;
+    fp.q_row_per_b = fp.q_col_per_h = fp.k_row_per_b = fp.k_row_per_h = fp.k_col_per_h = fp.v_row_per_b = fp.v_row_per_h = fp.v_col_per_h = 0;
+    CUtensorMap tnone;
+    memset(&tnone, 0, sizeof(tnone));
     static DeviceOnce fset;
     if (first_on_device(fset))
       CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlashCfg<128, 1>::SMEM));
     cudaStream_t st2 = (cudaStream_t)stream;
-    flash_attn_kernel<128, 1><<<dim3((unsigned)a->nsplit, (unsigned)a->KVH, (unsigned)a->B), 128, FlashCfg<128, 1>::SMEM, st2>>>(fp);
+    flash_attn_kernel<128, 1><<<dim3((unsigned)a->nsplit, (unsigned)a->KVH, (unsigned)a->B), 128, FlashCfg<128, 1>::SMEM, st2>>>(tnone, tnone, tnone, fp);
     CRAB_CHECK_CUDA(cudaGetLastError());
     if (a->nsplit > 1) {
       cudaError_t e2 = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<128>, dim3(a->B * a->H), dim3(128), 0, st2, (const float*)a->workspace,
