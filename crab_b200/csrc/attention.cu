@@ -55,6 +55,7 @@ struct FlashParams {
   int nsplit;          // > 1: split-KV (Sq <= 64 only): blockIdx.x = split, partial states -> ws, attn_decode_combine_kernel finishes
   float* ws;           // [(b * H * Sq + h * Sq + row) * nsplit + split][HD + 2]: un-normalised acc, running max (log2 domain), sum
   // TMA staging (head_dim 64, TMA-describable strides): the three tensors as 2-D [rows, row stride] maps, tile (row, col) origins
+  int stages;          // K/V tile buffers of the cp.async path: 2, or 3 for the split-KV decode (one more 64-key step in flight per block)
   int use_tma;
   int q_row_per_b, q_col_per_h, k_row_per_b, k_row_per_h, k_col_per_h, v_row_per_b, v_row_per_h, v_col_per_h;
 };
@@ -64,6 +65,7 @@ struct FlashCfg {
   static constexpr int BM = 64 * MT, BN = 64, THREADS = 128;  // MT m16-tiles of query rows per warp
   static constexpr int TILE_BYTES = 64 * HD * 2;
   static constexpr int SMEM = TILE_BYTES * (MT + 4);  // Q (MT tiles) + 2 x (K, V)
+  static constexpr int SMEM3 = TILE_BYTES * (MT + 6); // three K / V buffers (split-KV decode)
 };
 
 // smem tile: row-major [64][HD] bf16, 16-byte chunk c of row r stored at chunk (c ^ (r & 7))
@@ -84,7 +86,11 @@ __device__ __forceinline__ void load_tile(uint32_t sbase, const __nv_bfloat16* g
 }
 
 // Each warp owns MT x 16 query rows, so every K / V fragment fetched from shared memory (ldmatrix) feeds MT MMAs.
-template <int HD, int MT>
+// KS (key split, decode over a kv group: Sq <= 16 query rows): the four warps share the SAME 16 query rows and each takes 16 of
+// a tile's 64 keys — with the rows split over the warps three of them would idle and the fourth would do a tile's 128 MMAs
+// alone (2.2 us per 64-key step, measured: the kernel was compute-latency bound at 3.8 TB/s); the four partial softmax
+// states are merged through shared memory after the last tile.
+template <int HD, int MT, bool KS = false>
 __global__ void __launch_bounds__(128, (HD == 64 && MT == 1) ? 4 : 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                   const __grid_constant__ CUtensorMap tmap_v, const FlashParams p) {
@@ -94,11 +100,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   // IS the TMA SWIZZLE_128B layout — so Q / K / V tiles can be staged by cp.async.bulk.tensor (one thread, two instructions per
   // 64-key step, completion on an mbarrier) instead of 16 cp.async per thread, with the ldmatrix addressing unchanged.
   const bool tma = (HD == 64) && p.use_tma;
+  constexpr int NPG = KS ? 1 : 4;      // 16-key groups of a tile handled by one warp
+  constexpr int NT8 = 2 * NPG;         // score n8-tiles per warp and tile
+  constexpr int NKK = KS ? 1 : 4;      // 16-key PV steps per warp and tile
   __shared__ __align__(8) uint64_t fbars[3];   // Q, K/V buffer 0, K/V buffer 1
   const uint32_t q_bar = smem_u32(&fbars[0]);
   const uint32_t sQ = smem_u32(smem);
+  const int NST = tma ? 2 : p.stages;
   const uint32_t sK0 = sQ + MT * Cfg::TILE_BYTES;
-  const uint32_t sV0 = sK0 + 2 * Cfg::TILE_BYTES;
+  const uint32_t sV0 = sK0 + NST * Cfg::TILE_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = p.nsplit > 1 ? (int)blockIdx.x : 0;
   const int m_blk = p.nsplit > 1 ? 0 : (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -145,12 +155,18 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   } else {
 #pragma unroll
     for (int t = 0; t < MT; ++t) load_tile<HD>(sQ + t * Cfg::TILE_BYTES, qg, p.q_rs, q0 + t * 64, p.Sq);
-    load_tile<HD>(sK0, kg, p.k_rs, t_begin * Cfg::BN, Sk);
-    load_tile<HD>(sV0, vg, p.v_rs, t_begin * Cfg::BN, Sk);
-    cp_async_commit();
+    for (int i = 0; i < NST - 1; ++i) {   // NST - 1 key steps in flight before the loop; one commit group per step (possibly empty)
+      if (t_begin + i < t_end) {
+        load_tile<HD>(sK0 + i * Cfg::TILE_BYTES, kg, p.k_rs, (t_begin + i) * Cfg::BN, Sk);
+        load_tile<HD>(sV0 + i * Cfg::TILE_BYTES, vg, p.v_rs, (t_begin + i) * Cfg::BN, Sk);
+      }
+      cp_async_commit();
+    }
   }
 
   constexpr int DT = HD / 8;  // output n8-tiles per row
+  const int wrow = KS ? 0 : warp;          // 16-row block of this warp
+  const int kw = KS ? warp * 16 : 0;       // first key of this warp within a tile
   float o_acc[MT][DT][4];
   float m_run[MT][2], l_run[MT][2];
   int r_lo[MT];               // global query row of c0/c1 for m-tile mt; c2/c3 are r_lo + 8
@@ -161,7 +177,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     for (int i = 0; i < DT; ++i) { o_acc[mt][i][0] = o_acc[mt][i][1] = o_acc[mt][i][2] = o_acc[mt][i][3] = 0.f; }
     m_run[mt][0] = m_run[mt][1] = -INFINITY;
     l_run[mt][0] = l_run[mt][1] = 0.f;
-    r_lo[mt] = q0 + (warp * MT + mt) * 16 + (lane >> 2);
+    r_lo[mt] = q0 + (wrow * MT + mt) * 16 + (lane >> 2);
     gate_lo[mt] = gate_hi[mt] = 0.f;
     if (p.gate) {
       if (r_lo[mt] < p.Sq) gate_lo[mt] = p.gate[((size_t)b * p.H + h) * p.Sq + r_lo[mt]];
@@ -169,50 +185,53 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
   }
   const float sl2 = p.scale * 1.4426950408889634f;
-  const bool warp_active = q0 + warp * MT * 16 < p.Sq;
+  const bool warp_active = q0 + wrow * MT * 16 < p.Sq;
 
   if (t_begin >= t_end && !tma) cp_async_wait<0>();   // empty split: nothing to consume
   if (tma) mbar_wait(q_bar, 0);
   for (int t = t_begin; t < t_end; ++t) {
-    const int buf = (t - t_begin) & 1;
+    const int buf = (t - t_begin) % NST;
     if (tma) {
       // buffer buf ^ 1 was last read in iteration t - 1, which ended with a block barrier: it may be refilled now
       if (t + 1 < t_end && threadIdx.x == 0) tma_kv(buf ^ 1, t + 1);
       mbar_wait(kv_bar(buf), (uint32_t)((t - t_begin) >> 1) & 1);
     } else {
-      if (t + 1 < t_end) {
-        load_tile<HD>(sK0 + (buf ^ 1) * Cfg::TILE_BYTES, kg, p.k_rs, (t + 1) * Cfg::BN, Sk);
-        load_tile<HD>(sV0 + (buf ^ 1) * Cfg::TILE_BYTES, vg, p.v_rs, (t + 1) * Cfg::BN, Sk);
-        cp_async_commit();
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
+      // request key step t + NST - 1 into the buffer that iteration t - 1 released (block barrier at its end), then wait until
+      // only the NST - 1 youngest groups are pending: step t has landed
+      const int tn = t + NST - 1;
+      if (tn < t_end) {
+        const int bn = (tn - t_begin) % NST;
+        load_tile<HD>(sK0 + bn * Cfg::TILE_BYTES, kg, p.k_rs, tn * Cfg::BN, Sk);
+        load_tile<HD>(sV0 + bn * Cfg::TILE_BYTES, vg, p.v_rs, tn * Cfg::BN, Sk);
       }
+      cp_async_commit();
+      if (NST == 3) cp_async_wait<2>(); else cp_async_wait<1>();
       __syncthreads();
     }
-    const uint32_t sK = sK0 + buf * Cfg::TILE_BYTES, sV = sV0 + buf * Cfg::TILE_BYTES;
+    // key split: a row offset of 16 keeps (row & 7), i.e. the swizzle, so the warp's 16 keys are simply a shifted tile base
+    const uint32_t sK = sK0 + buf * Cfg::TILE_BYTES + (uint32_t)(kw * HD * 2), sV = sV0 + buf * Cfg::TILE_BYTES + (uint32_t)(kw * HD * 2);
 
     // a warp whose query rows all lie past Sq (decode over a kv group: Sq = G <= 16 rows, three of the four warps) only helps
     // with the loads: its MMAs / softmax would be work on padding that competes with the one useful warp for the tensor pipe
     if (warp_active) {
     // ---- S = Q K^T  (MT x 16 x 64 per warp) ----
-    float s[MT][8][4];
+    float s[MT][NT8][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[mt][i][0] = s[mt][i][1] = s[mt][i][2] = s[mt][i][3] = 0.f; }
+      for (int i = 0; i < NT8; ++i) { s[mt][i][0] = s[mt][i][1] = s[mt][i][2] = s[mt][i][3] = 0.f; }
 #pragma unroll
     for (int ks = 0; ks < HD / 16; ++ks) {
       uint32_t a[MT][4];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         // A fragment (m16 x k16): matrices (rows 0-7,k0-7), (rows 8-15,k0-7), (rows 0-7,k8-15), (rows 8-15,k8-15)
-        const int rr = (warp * MT + mt) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;  // row within the BM-row Q block
+        const int rr = (wrow * MT + mt) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;  // row within the BM-row Q block
         const int c = ks * 2 + (lane >> 4);
         ldsm_x4(tile_addr<HD>(sQ + (rr >> 6) * Cfg::TILE_BYTES, rr & 63, c), a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
       }
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
+      for (int np = 0; np < NPG; ++np) {
         uint32_t b0, b1, b2, b3;
         // matrices: (n0-7,k0-7), (n0-7,k8-15), (n8-15,k0-7), (n8-15,k8-15)
         const int n = np * 16 + (lane & 7) + (lane >> 4) * 8;
@@ -233,15 +252,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const int k0 = t * Cfg::BN;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const int q_min = q0 + (warp * MT + mt) * 16;  // smallest query row of this m-tile (warp-uniform)
+      const int q_min = q0 + (wrow * MT + mt) * 16;  // smallest query row of this m-tile (warp-uniform)
       const bool general = (p.table != nullptr) || (k0 + Cfg::BN > Sk) || (p.causal && (k0 + Cfg::BN - 1 > q_min + off));
       float mx[2] = {-INFINITY, -INFINITY};
       if (general) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < NT8; ++nt) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int kj = k0 + nt * 8 + (lane & 3) * 2 + (e & 1);
+            const int kj = k0 + kw + nt * 8 + (lane & 3) * 2 + (e & 1);
             const int hi = e >> 1;
             const int qi = r_lo[mt] + hi * 8;
             float v = s[mt][nt][e] * sl2;
@@ -255,7 +274,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       } else {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < NT8; ++nt) {
           mx[0] = fmaxf(mx[0], fmaxf(s[mt][nt][0], s[mt][nt][1]));
           mx[1] = fmaxf(mx[1], fmaxf(s[mt][nt][2], s[mt][nt][3]));
         }
@@ -279,7 +298,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       float rs[2] = {0.f, 0.f};
       if (general) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < NT8; ++nt) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float pv = exp2f(s[mt][nt][e] - msafe[e >> 1]);
@@ -289,7 +308,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       } else {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < NT8; ++nt) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float pv = exp2f(fmaf(s[mt][nt][e], sl2, -msafe[e >> 1]));
@@ -309,7 +328,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
     // ---- O += P V ----
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
+    for (int kk = 0; kk < NKK; ++kk) {  // 16 keys per step
       uint32_t a[MT][4];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
@@ -337,6 +356,47 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   }
 
   // ---- finalise ----
+  if (KS) {
+    // merge the four warps' partial states (same 16 rows, disjoint keys) through the K / V buffers, idle now:
+    // mw[w][16] running max, lw[w][16] sums, ow[w][16][HD] accumulators
+    float* mw = reinterpret_cast<float*>(smem + MT * Cfg::TILE_BYTES);
+    float* lw = mw + 64;
+    float* ow = lw + 64;
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      l_run[0][hi] += __shfl_xor_sync(0xffffffffu, l_run[0][hi], 1);
+      l_run[0][hi] += __shfl_xor_sync(0xffffffffu, l_run[0][hi], 2);
+      const int row = (lane >> 2) + 8 * hi;
+      if ((lane & 3) == 0) { mw[warp * 16 + row] = m_run[0][hi]; lw[warp * 16 + row] = l_run[0][hi]; }
+#pragma unroll
+      for (int i = 0; i < DT; ++i)
+        *reinterpret_cast<float2*>(ow + ((size_t)(warp * 16 + row) * HD + i * 8 + (lane & 3) * 2)) = make_float2(o_acc[0][i][2 * hi], o_acc[0][i][2 * hi + 1]);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 16 * HD; idx += 128) {
+      const int row = idx / HD, col = idx % HD;
+      if (row >= p.Sq) continue;
+      float mm = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) mm = fmaxf(mm, mw[w * 16 + row]);
+      float ll = 0.f, aa = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {   // fixed warp order: deterministic
+        const float mv = mw[w * 16 + row];
+        const float c = (mv == -INFINITY) ? 0.f : exp2f(mv - mm);
+        ll += lw[w * 16 + row] * c;
+        aa += ow[(size_t)(w * 16 + row) * HD + col] * c;
+      }
+      if (p.nsplit > 1) {
+        float* w_ = p.ws + ((((size_t)b * p.H + h) * p.Sq + row) * p.nsplit + split) * (HD + 2);
+        w_[col] = aa;
+        if (col == 0) { w_[HD] = mm; w_[HD + 1] = ll; }
+      } else {
+        p.o[b * p.o_bs + h * p.o_hs + (long long)row * p.o_rs + col] = __float2bfloat16_rn(ll > 0.f ? aa / ll : 0.f);
+      }
+    }
+    return;
+  }
   if (p.nsplit > 1) {
     // partial state of this key range -> workspace (one row per query row, i.e. per q head of the kv group in GQA decode)
 #pragma unroll
@@ -757,7 +817,7 @@ extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
   p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
   p.B = a->B; p.H = a->H; p.KVH = a->KVH; p.Sq = a->Sq; p.Sk = a->Sk;
   p.scale = a->scale; p.causal = a->causal; p.gate = a->gate; p.table = a->bias_table; p.sk_dev = a->sk_dev;
-  p.sk_add = 0; p.nsplit = 1; p.ws = nullptr;
+  p.sk_add = 0; p.nsplit = 1; p.ws = nullptr; p.stages = 2;
   p.use_tma = 0;
   p.q_row_per_b = p.q_col_per_h = p.k_row_per_b = p.k_row_per_h = p.k_col_per_h = p.v_row_per_b = p.v_row_per_h = p.v_col_per_h = 0;
   CUtensorMap tq, tk, tv;
@@ -797,7 +857,7 @@ extern "C" int crab_flash_attn(const crab_attn_args* a, void* stream) {
     static DeviceOnce set;                                                                                                 \
     if (first_on_device(set)) {                                                                                            \
       CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                           FlashCfg<HD_, MT_>::SMEM));                                                     \
+                                           FlashCfg<HD_, MT_>::SMEM3));  /* the larger of the two launch configurations */ \
     }                                                                                                                      \
     dim3 grid((a->Sq + FlashCfg<HD_, MT_>::BM - 1) / FlashCfg<HD_, MT_>::BM, a->H, a->B);                                  \
     flash_attn_kernel<HD_, MT_><<<grid, 128, FlashCfg<HD_, MT_>::SMEM, st>>>(tq, tk, tv, p);                               \
@@ -885,16 +945,20 @@ extern "C" int crab_attn_decode_fused(const crab_decode_fused_args* a, void* str
     fp.o_bs = a->ldo; fp.o_rs = a->head_dim; fp.o_hs = (long long)G * a->head_dim;
     fp.B = a->B; fp.H = a->KVH; fp.KVH = a->KVH; fp.Sq = G; fp.Sk = a->ctx_max;
     fp.scale = a->scale; fp.causal = 0; fp.gate = nullptr; fp.table = nullptr; fp.sk_dev = a->past_dev; fp.sk_add = 1;
-    fp.nsplit = a->nsplit; fp.ws = a->workspace;
+    fp.nsplit = a->nsplit; fp.ws = a->workspace; fp.stages = 3;
     fp.use_tma = 0;
     fp.q_row_per_b = fp.q_col_per_h = fp.k_row_per_b = fp.k_row_per_h = fp.k_col_per_h = fp.v_row_per_b = fp.v_row_per_h = fp.v_col_per_h = 0;
     CUtensorMap tnone;
     memset(&tnone, 0, sizeof(tnone));
     static DeviceOnce fset;
     if (first_on_device(fset))
-      CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlashCfg<128, 1>::SMEM));
+    {
+      CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlashCfg<128, 1>::SMEM3));
+      CRAB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FlashCfg<128, 1>::SMEM3));
+    }
     cudaStream_t st2 = (cudaStream_t)stream;
-    flash_attn_kernel<128, 1><<<dim3((unsigned)a->nsplit, (unsigned)a->KVH, (unsigned)a->B), 128, FlashCfg<128, 1>::SMEM, st2>>>(tnone, tnone, tnone, fp);
+    if (G <= 16) flash_attn_kernel<128, 1, true><<<dim3((unsigned)a->nsplit, (unsigned)a->KVH, (unsigned)a->B), 128, FlashCfg<128, 1>::SMEM3, st2>>>(tnone, tnone, tnone, fp);
+    else flash_attn_kernel<128, 1><<<dim3((unsigned)a->nsplit, (unsigned)a->KVH, (unsigned)a->B), 128, FlashCfg<128, 1>::SMEM3, st2>>>(tnone, tnone, tnone, fp);
     CRAB_CHECK_CUDA(cudaGetLastError());
     if (a->nsplit > 1) {
       cudaError_t e2 = launch_pdl(PDL_ATTN, attn_decode_combine_kernel<128>, dim3(a->B * a->H), dim3(128), 0, st2, (const float*)a->workspace,
