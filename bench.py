@@ -792,9 +792,10 @@ def main():
         cands = {"decode:weight_streaming_linears": lin_us * 1e-3 * n_dec,
                  "decode:attention": dec_roof.get("attention", {}).get("us_per_step", 0.0) * 1e-3 * n_dec,
                  "gemm_bf16_tcgen05<256>": kt.get("gemm_bf16_tcgen05<256>", {}).get("ms", 0.0)}
-        top = max(cands, key=cands.get)
-        if cands["decode:weight_streaming_linears"] >= 0.95 * cands[top]:
-            top = "decode:weight_streaming_linears"
+        # the class with the largest share of the step; classes within 5 % of it are ties, resolved in a FIXED order (decode linears,
+        # decode attention, prefill GEMM) so that the choice does not flip between runs whose shares differ by noise
+        biggest = max(cands.values())
+        top = next(k for k in ("decode:weight_streaming_linears", "decode:attention", "gemm_bf16_tcgen05<256>") if cands[k] >= 0.95 * biggest)
         traffic = load_traffic()
         if top == "decode:weight_streaming_linears":
             ach = lin_bytes / (lin_us * 1e-6) / 1e9 if lin_us else 0.0
