@@ -232,3 +232,32 @@ def test_batched_generate_with_eos_and_unequal_prompts(cuda_dev):
     out = model.generate(batch_input_ids=ids, batch_labels=None, batch_X_modals=X, batch_task_names=["avqa"] * len(ids),
                          max_new_tokens=n, eos_token_id=eos).cpu()
     assert torch.equal(out, exp), (out.tolist(), exp.tolist())
+
+
+def test_call_graphs_replay_equals_eager(cuda_dev):
+    """The launch-bound call sites outside the decode loop (small encoder batches, short prefills) run as one CUDA-graph replay
+    per shape: with inputs that CHANGE between calls the replays must give the eager path's bits (static input buffers refreshed,
+    ViT taps handed over, KV cache and position state as after an eager prefill)."""
+    from crab_b200.engine import CrabEngine
+
+    g, case, sd, ocfg, ids, X = load_golden("llama_small")
+    eng = CrabEngine(sd, engine_cfg(case, ocfg), cuda_dev)
+    assert eng.call_graphs
+    gen = torch.Generator().manual_seed(9)
+    X2 = [{k: v + 0.25 * torch.randn(v.shape, generator=gen) for k, v in x.items()} for x in X]
+    outs = {}
+    for mode in ("graph", "graph_again", "eager"):
+        eng.call_graphs = mode != "eager"
+        res = []
+        for Xi in (X, X2, X):
+            emb, _, _ = eng.prepare_inputs(ids, [{k: v.to(cuda_dev) for k, v in x.items()} for x in Xi])
+            logits, nxt = eng.prefill(emb.clone())
+            eng.begin_decode(emb.shape[0])
+            step_logits, _ = eng.decode_step()
+            res.append((emb.clone(), logits.clone(), step_logits.clone(), eng.cur_len))
+        outs[mode] = res
+    assert any(k[0] == "prefill" for k in eng._call_graphs) and any(k[0] in ("video", "audio") for k in eng._call_graphs)
+    for mode in ("graph", "graph_again"):
+        for a, b in zip(outs[mode], outs["eager"]):
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and a[3] == b[3]
+    assert not torch.equal(outs["eager"][0][1], outs["eager"][1][1])   # the second input really differs
