@@ -35,7 +35,7 @@ eng.cur_len = a.ctx
 L = lib.load()
 L.crab_debug_trace.argtypes = [C.c_void_p, C.c_int, C.c_int]
 L.crab_debug_trace.restype = C.c_int
-NS, NC = 4 * (5 * a.layers + 1) + 8, 1024
+NS, NC = 4 * (5 * a.layers + 1) + 8, 2048
 buf = torch.zeros(NS * NC * 16, dtype=torch.int64, device=dev)
 assert L.crab_debug_trace(C.c_void_p(buf.data_ptr()), NS, NC) == 0
 eng.begin_decode(a.bs, use_graph=True)          # eager warm-up + capture: the graph's launches keep their slots
