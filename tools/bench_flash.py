@@ -26,3 +26,8 @@ bench("llama prefill bs32 S=1086", 32, 32, 32, 1086, 128, True)
 bench("qwen prefill bs32 S=1086 GQA", 32, 28, 4, 1086, 128, True)
 bench("clip 256 frames N=257", 256, 16, 16, 257, 64, False)
 bench("beats 320 segs N=48", 320, 12, 12, 48, 64, False)
+# is the hd-128 tcgen05 kernel waiting for its K / V tiles?  Same per-CTA work, cache-resident vs HBM-resident operands
+bench("llama prefill bs2 (L2-resident)", 2, 32, 32, 1086, 128, True)
+bench("llama prefill bs8", 8, 32, 32, 1086, 128, True)
+bench("non-causal bs32 S=1086", 32, 32, 32, 1086, 128, False)
+bench("qwen GQA bs8 (L2-resident)", 8, 28, 4, 1086, 128, True)
