@@ -465,6 +465,7 @@ struct DecodeParams {
   float* lora_ws;                             // [B, KVH, 11] per-head-group partial dots
   int* lora_cnt;                              // [B] arrival counters, zero on entry and left zero
   unsigned long long* trace;                  // diagnostics: [ctas][16] stamps or nullptr
+  int csplit;                                 // > 1: split KV over the `csplit` blocks of a CLUSTER, merged in rank 0 through DSMEM (no combine launch)
 };
 
 // o_proj hyper-LoRA pre-pass, block tail shared by the fused decode attention (one block per (b, kv head)) and the split-KV
@@ -533,6 +534,17 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
   __shared__ float sh_tot[11];
   __shared__ int sh_ticket;
   __shared__ uint4 sh_new[2][LPK];
+  constexpr int PEERS = (G == 1 && FUSE) ? 7 : 0;              // cluster split is offered for MHA only (host check)
+  __shared__ float sh_peer[PEERS * (HD + 2) + 2];               // rank 0: the other ranks' states (acc[HD], max, sum)
+  __shared__ __align__(8) uint64_t sh_peer_bar;
+  if (p.csplit > 1) {
+    if (threadIdx.x == 0) {
+      mbar_init(smem_u32(&sh_peer_bar), 1);
+      fence_barrier_init();
+      mbar_arrive_expect_tx(smem_u32(&sh_peer_bar), (uint32_t)((p.csplit - 1) * (HD + 2) * 4));
+    }
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");   // waited for by ranks > 0 before their first remote store
+  }
   // With an early trigger the next kernels of a PDL chain (ultimately the streaming GEMM, 100 KB smem / 32 K registers per
   // CTA) become resident while this grid still streams the cache and squat on its SM slots; a late trigger releases them
   // only when every CTA is past its loop, which still hides their launch latency behind the combine/tail.
@@ -542,11 +554,19 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
   if (threadIdx.x == 0) trace_stamp(p.trace, 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / LPK, li = lane % LPK;
-  const int b = blockIdx.x / p.KVH, kvh = blockIdx.x % p.KVH;
-  const int split = blockIdx.y;
+  // cluster split (small batches: one block per (b, kv head) would leave most SMs idle): the `csplit` blocks of a cluster share
+  // one (b, kv head) and take a key range each; ranks > 0 hand their softmax state to rank 0 through distributed shared memory,
+  // which merges in rank order and finishes (output, o_proj pre-pass) — one launch instead of split kernel + combine kernel
+  // (7.5 + 7.5 us per layer at bs 1, where the whole cache read is 0.3 MB).
+  uint32_t crank = 0;
+  if (p.csplit > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int blk = p.csplit > 1 ? (int)blockIdx.x / p.csplit : (int)blockIdx.x;
+  const int b = blk / p.KVH, kvh = blk % p.KVH;
+  const int split = p.csplit > 1 ? (int)crank : (int)blockIdx.y;
+  const int nsp = p.csplit > 1 ? p.csplit : p.nsplit;
   const int past = FUSE ? *p.past_dev : 0;
   const int len = FUSE ? past + 1 : (p.len_dev ? *p.len_dev : p.len_host);
-  const int per = (len + p.nsplit - 1) / p.nsplit;
+  const int per = (len + nsp - 1) / nsp;
   const int k_begin = split * per, k_end = min(len, k_begin + per);
   const float sl2 = p.scale * 1.4426950408889634f;
 
@@ -711,6 +731,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
   float t11[11];
 #pragma unroll
   for (int j = 0; j < 11; ++j) t11[j] = 0.f;
+  if (p.csplit > 1 && crank != 0) asm volatile("barrier.cluster.wait.acquire;" ::: "memory");   // rank 0's barrier is initialised and armed
   for (int idx = threadIdx.x; idx < G * HD; idx += 128) {
     const int g = idx / HD, d = idx % HD;
     float mm = -INFINITY;
@@ -726,6 +747,31 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
       }
     }
     const int hq = kvh * G + g;
+    if (PEERS > 0 && p.csplit > 1) {
+      if (crank != 0) {
+        // state of this rank's key range -> rank 0's shared memory, bytes counted on its barrier
+        uint32_t rbase, rbar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbase) : "r"(smem_u32(sh_peer)), "r"(0u));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&sh_peer_bar)), "r"(0u));
+        rbase += (uint32_t)((crank - 1) * (HD + 2) * 4);
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(rbase + (uint32_t)(d * 4)), "f"(aa), "r"(rbar) : "memory");
+        if (d == 0) {
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(rbase + (uint32_t)(HD * 4)), "f"(mm), "r"(rbar) : "memory");
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(rbase + (uint32_t)((HD + 1) * 4)), "f"(ll), "r"(rbar) : "memory");
+        }
+        continue;
+      }
+      mbar_wait(smem_u32(&sh_peer_bar), 0);
+      for (int r = 1; r < p.csplit; ++r) {   // rank order: deterministic
+        const float* pp = sh_peer + (r - 1) * (HD + 2);
+        const float pm = pp[HD], pl = pp[HD + 1], pa = pp[d];
+        const float mt = fmaxf(mm, pm);
+        const float c0 = (mm == -INFINITY) ? 0.f : exp2f(mm - mt), c1 = (pm == -INFINITY) ? 0.f : exp2f(pm - mt);
+        ll = ll * c0 + pl * c1;
+        aa = aa * c0 + pa * c1;
+        mm = mt;
+      }
+    }
     if (p.nsplit == 1) {
       const __nv_bfloat16 ob = __float2bfloat16_rn(ll > 0.f ? aa / ll : 0.f);
       p.o[(size_t)b * p.ldo + (size_t)hq * HD + d] = ob;
@@ -741,7 +787,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeParams p) 
       if (d == 0) { w[HD] = mm; w[HD + 1] = ll; }
     }
   }
-  if (lora) lora_prepass_tail(t11, b, kvh, p.KVH, p.lora_ws, p.lora_cnt, p.z, p.ldz, p.lora_scale, sh_red, sh_tot, &sh_ticket);
+  if (lora && crank == 0) lora_prepass_tail(t11, b, kvh, p.KVH, p.lora_ws, p.lora_cnt, p.z, p.ldz, p.lora_scale, sh_red, sh_tot, &sh_ticket);
   if (threadIdx.x == 0) trace_stamp(p.trace, 7);
 }
 
@@ -894,7 +940,7 @@ extern "C" int crab_attn_decode(const void* q, int ldq, const void* k_cache, con
   p.late_trigger = (pdl_mask() & PDL_ATTN_LATE) ? 1 : 0;
   p.cos_sin = nullptr; p.past_dev = nullptr; p.kc_w = nullptr; p.vc_w = nullptr; p.ra = nullptr; p.ldra = 0; p.z = nullptr;
   p.ldz = 0; p.lora_scale = 0.f; p.lora_ws = nullptr; p.lora_cnt = nullptr;
-  p.trace = nullptr;
+  p.trace = nullptr; p.csplit = 0;
   dim3 grid(B * KVH, nsplit);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
@@ -976,10 +1022,33 @@ extern "C" int crab_attn_decode_fused(const crab_decode_fused_args* a, void* str
   p.cos_sin = a->cos_sin; p.past_dev = a->past_dev; p.kc_w = (__nv_bfloat16*)a->k_cache; p.vc_w = (__nv_bfloat16*)a->v_cache;
   p.ra = (const __nv_bfloat16*)a->lora_ra; p.ldra = a->ld_ra; p.z = (__nv_bfloat16*)a->lora_z; p.ldz = a->ld_z;
   p.lora_scale = a->lora_scale; p.lora_ws = a->lora_ws; p.lora_cnt = a->lora_counters;
-  p.trace = next_trace_slot(a->B * a->KVH * a->nsplit);
-  dim3 grid(a->B * a->KVH, a->nsplit);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
+  // split KV at MHA / head_dim 128: the splits of one (b, head) are the blocks of a cluster (<= 8) and merge through DSMEM
+  static int cluster_ok = -1;
+  if (cluster_ok < 0) { const char* ev = getenv("CRAB_ATTN_CLUSTER"); cluster_ok = (ev && ev[0] == '0') ? 0 : 1; }
+  p.csplit = 0;
+  if (cluster_ok && a->nsplit > 1 && G == 1 && a->head_dim == 128) {
+    p.csplit = a->nsplit > 8 ? 8 : a->nsplit;
+    p.nsplit = 1;                       // the kernel finishes itself: output + pre-pass as in the unsplit launch
+    p.trace = next_trace_slot(a->B * a->KVH * p.csplit);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a->B * a->KVH * p.csplit));
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)p.csplit; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl_mask() & PDL_ATTN) ? 2 : 1;
+    CRAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<128, 1, true>, p));
+    return CRAB_OK;
+  }
+  p.trace = next_trace_slot(a->B * a->KVH * a->nsplit);
+  dim3 grid(a->B * a->KVH, a->nsplit);
 #define CRAB_DECODE_CASE(HD_, G_) \
   if (a->head_dim == HD_ && G == G_) { e = launch_pdl(PDL_ATTN, attn_decode_kernel<HD_, G_, true>, grid, dim3(128), 0, st, p); } else
   CRAB_DECODE_CASE(128, 1) CRAB_DECODE_CASE(128, 2) CRAB_DECODE_CASE(128, 4) CRAB_DECODE_CASE(128, 7)

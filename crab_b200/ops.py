@@ -5,6 +5,7 @@ PyTorch is only the allocator / stream provider here; every op below is one call
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -282,7 +283,8 @@ def attn_decode_fused(qkv: torch.Tensor, rope: torch.Tensor, k_cache: torch.Tens
         lora_scale=lora_scale, lora_ws=_ptr(lora_ws), lora_counters=_ptr(lora_counters), gqa_tensor_cores=1 if gqa_tc else 0, reserved0=0)
     with _timed("crab_attn_decode_fused"):
         _l.check(_l.load().crab_attn_decode_fused(C.byref(a), _stream()), "crab_attn_decode_fused")
-    count_launches((2 if nsplit > 1 else 1) + (1 if gqa_tc else 0))
+    clustered = nsplit > 1 and H == KVH and head_dim == 128 and not gqa_tc and os.environ.get("CRAB_ATTN_CLUSTER", "1") != "0"
+    count_launches((2 if (nsplit > 1 and not clustered) else 1) + (1 if gqa_tc else 0))   # cluster split: no combine launch
     return out
 
 
