@@ -28,3 +28,44 @@ def test_engine_on_the_stand_in_library_reproduces_the_reference(monkeypatch, na
     e2, mask, pos = eng.prepare_inputs(ids, X)
     assert tuple(e2.shape) == tuple(g["inputs_embeds"].shape) and rel_l2(e2, g["inputs_embeds"]) < 3e-2
     assert torch.equal(mask, g["attention_mask"]) and torch.equal(pos, g["position_ids"])
+
+
+def test_flag_ring_and_split_policy(monkeypatch):
+    """Host-side bookkeeping of the fused decode linears: flag slots are handed round a ring (launch k raises slot k and zeroes slot
+    k - 1; the first launch of a step zeroes the last slot of the previous one), every statistics-carrying launch of a step gets a
+    distinct slot, and the decode step hands out exactly as many slots as it has such launches; short contexts skip the KV split."""
+    from crab_b200 import engine
+
+    monkeypatch.setattr(engine, "ops", fake_ops)
+    monkeypatch.setattr(fake_ops, "MIN_K", 8)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    g, case, sd, ocfg, ids, X = load_golden("llama_small")
+    eng = engine.CrabEngine(sd, engine_cfg(case, ocfg), torch.device("cpu"))
+    n = 7
+    slot = eng._flag_ring(n)
+    kws = [slot() for _ in range(n)]
+    ring = eng._buf("dec_flag_ring_%d" % n, (n, 32), torch.int32, zero=True)
+    for k, kw in enumerate(kws):
+        assert kw["flags"].data_ptr() == ring[k].data_ptr() and kw["flags_clear"].data_ptr() == ring[(k - 1) % n].data_ptr()
+        assert kw["stats_scratch"].numel() >= 8 * 36 * 32 and kw["stats_scratch"].dtype == torch.float32
+    assert len({kw["flags"].data_ptr() for kw in kws}) == n
+    with pytest.raises(StopIteration):
+        slot()
+    # the decode step asks for one slot per statistics-carrying launch: qkv + gate/up (+ o, + down with LoRA) per layer, + lm_head
+    asked = []
+    real = eng._flag_ring
+
+    def spy(m):
+        asked.append(m)
+        return real(m)
+    monkeypatch.setattr(eng, "_flag_ring", spy)
+    emb = g["inputs_embeds"].to(torch.bfloat16)
+    eng.generate_from_embeds(emb.clone(), 3)
+    L = len(eng.layers)
+    assert asked and all(m in (L * 3 + 1, L * 4 + 1, L * 2 + 1) for m in asked), asked
+    # KV split policy: contexts of at most 256 keys over the whole request run unsplit (no combine launch)
+    eng.prefill(emb.clone())
+    eng.begin_decode(emb.shape[0], use_graph=False, max_len=200)
+    assert eng._dec_args[1] == 1
+    eng.begin_decode(emb.shape[0], use_graph=False, max_len=2000)
+    assert eng._dec_args[1] >= 1
